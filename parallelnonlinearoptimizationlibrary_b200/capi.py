@@ -1,0 +1,391 @@
+"""ctypes binding of the C-ABI declared in include/pnol_b200.h.
+
+This is the thin Python face of libpnol_b200.so (hand-written sm_100a CUDA kernels behind `extern "C"`).
+There is no CPU fallback: loading fails loudly if the library has not been built (`python -c "import
+__graft_entry__ as g; g.build()"` or `make`), and every compute call fails with PnolError on a box without a GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpnol_b200.so")
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "libpnol_b200_host.so")
+
+PNOL_OK = 0
+ERR_NAMES = {1: "INVALID", 2: "CUDA", 3: "NO_FUNCTOR", 4: "NONFINITE", 5: "NOT_SPD", 6: "COMM", 7: "STREAM"}
+
+# functor kinds (include/pnol_b200.h)
+F_ROSENBROCK, F_POWER, F_BOOTH, F_GOLDSTEIN, F_RASTRIGIN, F_EXPCURVE_SINGLE = 1, 2, 3, 4, 5, 6
+F_EXPCURVE, F_CUBIC, F_LORENTZ_SUM = 101, 102, 103
+JAC_AUTO, JAC_BLACKBOX, JAC_STRUCTURED = 0, 1, 2
+HINV_LITERAL, HINV_RANK2 = 0, 1
+COMM_ID_BYTES = 128
+
+c_double_p = C.POINTER(C.c_double)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+c_int_p = C.POINTER(C.c_int)
+
+
+class PnolError(RuntimeError):
+    pass
+
+
+class FunctorDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int),
+        ("scalars", C.c_double * 8),
+        ("ints", C.c_longlong * 4),
+        ("n_columns", C.c_int),
+        ("columns", C.c_void_p * 8),
+        ("m", C.c_longlong),
+    ]
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("n_values", C.c_uint64), ("seed", C.c_uint64), ("scale", C.c_double)]
+
+
+class GaParams(C.Structure):
+    _fields_ = [
+        ("npop", C.c_int),
+        ("max_generations", C.c_int),
+        ("elite_frac", C.c_double),
+        ("cross_frac", C.c_double),
+        ("elite_mutation_frac", C.c_double),
+        ("mutation_size", C.c_double),
+        ("elite_mutation_size", C.c_double),
+        ("n_static_generations", C.c_double),
+    ]
+
+
+class GaStatus(C.Structure):
+    _fields_ = [
+        ("generation", C.c_int),
+        ("n_static", C.c_int),
+        ("stopped", C.c_int),
+        ("f_best", C.c_double),
+        ("stream_pos", C.c_uint64),
+        ("n_elite", C.c_int),
+        ("n_elite_mut", C.c_int),
+        ("n_cross", C.c_int),
+        ("n_rand", C.c_int),
+    ]
+
+
+# every symbol include/pnol_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+EXPORTS = [
+    "pnol_ctx_create", "pnol_ctx_destroy", "pnol_last_error", "pnol_ctx_device", "pnol_ctx_stream", "pnol_ctx_sync",
+    "pnol_ctx_sm_count", "pnol_ctx_launches", "pnol_version", "pnol_malloc", "pnol_free", "pnol_memcpy", "pnol_memset",
+    "pnol_host_alloc", "pnol_host_free", "pnol_comm_unique_id", "pnol_comm_init", "pnol_comm_rank", "pnol_comm_size",
+    "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
+    "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
+    "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
+    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
+    "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
+    "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
+    "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
+    "pnol_ga_check_identical", "pnol_measure_dmma_peak", "pnol_measure_copy_bandwidth", "pnol_timer_enable",
+    "pnol_timer_get", "pnol_timer_reset",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libpnol_b200.so (once). Raises PnolError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnolError(
+            "libpnol_b200.so is missing (%s): build it with `make` or __graft_entry__.build(); "
+            "this package has no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib.pnol_last_error.restype = C.c_char_p
+    lib.pnol_version.restype = C.c_char_p
+    lib.pnol_ctx_stream.restype = C.c_void_p
+    lib.pnol_ctx_launches.restype = C.c_uint64
+    lib.pnol_functor_rows.restype = C.c_longlong
+    lib.pnol_compute_alpha_bnd.restype = C.c_double
+    lib.pnol_stream_uniform.restype = C.c_double
+    lib.pnol_stream_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_double]
+    lib.pnol_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.pnol_ctx_destroy.argtypes = [C.c_void_p]
+    lib.pnol_ctx_destroy.restype = None
+    lib.pnol_functor_destroy.argtypes = [C.c_void_p]
+    lib.pnol_functor_destroy.restype = None
+    lib.pnol_ga_destroy.argtypes = [C.c_void_p]
+    lib.pnol_ga_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """void* of a numpy array, a raw int device pointer, a torch tensor, or None."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError("unsupported buffer %r" % type(a))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Functor:
+    def __init__(self, ctx, handle, kind, m, keep):
+        self.ctx, self.handle, self.kind, self.m, self._keep = ctx, handle, kind, m, keep
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.pnol_functor_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One pnol_ctx: one GPU, one stream."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.pnol_ctx_create(C.byref(h), int(device))
+        if st != PNOL_OK:
+            raise PnolError("pnol_ctx_create(device=%d) failed with %s: a CUDA device is required, there is no CPU "
+                            "fallback" % (device, ERR_NAMES.get(st, st)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pnol_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st):
+        if st != PNOL_OK:
+            msg = self.lib.pnol_last_error(self.h)
+            raise PnolError("%s: %s" % (ERR_NAMES.get(st, st), msg.decode() if msg else ""))
+
+    # ---- plumbing ----
+    @property
+    def stream(self):
+        return self.lib.pnol_ctx_stream(self.h)
+
+    @property
+    def sm_count(self):
+        return self.lib.pnol_ctx_sm_count(self.h)
+
+    def launches(self):
+        return int(self.lib.pnol_ctx_launches(self.h))
+
+    def sync(self):
+        self.check(self.lib.pnol_ctx_sync(self.h))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.pnol_malloc(self.h, C.byref(p), C.c_size_t(nbytes)))
+        return p.value
+
+    def free(self, p):
+        self.check(self.lib.pnol_free(self.h, C.c_void_p(p)))
+
+    def memcpy(self, dst, src, nbytes):
+        self.check(self.lib.pnol_memcpy(self.h, _ptr(dst), _ptr(src), C.c_size_t(nbytes)))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.malloc(arr.nbytes)
+        self.memcpy(p, arr, arr.nbytes)
+        return p
+
+    def to_host(self, p, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        self.memcpy(out, p, out.nbytes)
+        return out
+
+    def timer_enable(self, on=True):
+        self.check(self.lib.pnol_timer_enable(self.h, int(on)))
+
+    def timer_reset(self):
+        self.check(self.lib.pnol_timer_reset(self.h))
+
+    def timer_get(self, name):
+        ms, cnt = C.c_double(), C.c_longlong()
+        self.check(self.lib.pnol_timer_get(self.h, name.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def measure_dmma_peak(self):
+        v = C.c_double()
+        self.check(self.lib.pnol_measure_dmma_peak(self.h, C.byref(v)))
+        return v.value
+
+    def measure_copy_bandwidth(self):
+        v = C.c_double()
+        self.check(self.lib.pnol_measure_copy_bandwidth(self.h, C.byref(v)))
+        return v.value
+
+    # ---- communicator ----
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        st = self.lib.pnol_comm_unique_id(buf)
+        if st != PNOL_OK:
+            raise PnolError("pnol_comm_unique_id failed (NCCL not loadable)")
+        return buf.raw
+
+    def comm_init(self, uid, nranks, rank):
+        buf = C.create_string_buffer(bytes(uid), COMM_ID_BYTES)
+        self.check(self.lib.pnol_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_size(self):
+        return self.lib.pnol_comm_size(self.h)
+
+    def comm_rank(self):
+        return self.lib.pnol_comm_rank(self.h)
+
+    def allreduce_sum(self, buf, count):
+        self.check(self.lib.pnol_comm_allreduce_sum(self.h, _ptr(buf), C.c_size_t(count)))
+
+    # ---- functors ----
+    def functor(self, kind, scalars=(), ints=(), columns=(), m=0):
+        d = FunctorDesc()
+        d.kind = kind
+        for i, v in enumerate(scalars):
+            d.scalars[i] = float(v)
+        for i, v in enumerate(ints):
+            d.ints[i] = int(v)
+        keep = []
+        d.n_columns = len(columns)
+        for i, col in enumerate(columns):
+            if isinstance(col, np.ndarray):
+                col = _f64(col)
+                keep.append(col)
+            d.columns[i] = _ptr(col).value
+        d.m = int(m)
+        h = C.c_void_p()
+        self.check(self.lib.pnol_functor_create(self.h, C.byref(d), C.byref(h)))
+        return Functor(self, h, kind, int(m), keep)
+
+    # ---- scalar objectives ----
+    def eval_batch(self, f, pts, B, n, ld=None, indicator=None, f_out=None):
+        ld = n if ld is None else ld
+        host_out = f_out is None
+        if host_out:
+            f_out = np.zeros(B, dtype=np.float64)
+        self.check(self.lib.pnol_eval_batch(self.h, f.handle, _ptr(pts), C.c_longlong(B), int(n), C.c_longlong(ld),
+                                            _ptr(indicator), _ptr(f_out)))
+        return f_out
+
+    def fd_gradient(self, f, x, dx):
+        x, dx = _f64(x), _f64(dx)
+        g = np.empty_like(x)
+        f0 = C.c_double()
+        self.check(self.lib.pnol_fd_gradient(self.h, f.handle, _ptr(x), _ptr(dx), x.size, _ptr(g), C.byref(f0)))
+        return g, f0.value
+
+    def eval_recur(self, f, xr, const_x, const_ind):
+        xr, const_x = _f64(xr), _f64(const_x)
+        ind = np.ascontiguousarray(const_ind, dtype=np.uint8)
+        out = C.c_double()
+        self.check(self.lib.pnol_eval_recur(self.h, f.handle, _ptr(xr), xr.size, _ptr(const_x), _ptr(ind), const_x.size,
+                                            C.byref(out)))
+        return out.value
+
+    def fd_gradient_recur(self, f, xr, dxr, const_x, const_ind):
+        xr, dxr, const_x = _f64(xr), _f64(dxr), _f64(const_x)
+        ind = np.ascontiguousarray(const_ind, dtype=np.uint8)
+        g = np.empty_like(xr)
+        f0 = C.c_double()
+        self.check(self.lib.pnol_fd_gradient_recur(self.h, f.handle, _ptr(xr), _ptr(dxr), xr.size, _ptr(const_x), _ptr(ind),
+                                                   const_x.size, _ptr(g), C.byref(f0)))
+        return g, f0.value
+
+    def fd_hessian(self, f, x, dx):
+        x, dx = _f64(x), _f64(dx)
+        B = np.empty((x.size, x.size), dtype=np.float64)
+        self.check(self.lib.pnol_fd_hessian(self.h, f.handle, _ptr(x), _ptr(dx), x.size, _ptr(B)))
+        return B
+
+    def alpha_pool(self, f, x, p, alpha, dalpha, want_dphi=True, eval_ind=None, const_x=None, const_ind=None):
+        x, p, alpha = _f64(x), _f64(p), _f64(alpha)
+        npool = alpha.size
+        phi = np.zeros(npool)
+        dphi = np.zeros(npool) if want_dphi else None
+        bad = C.c_int()
+        ei = None if eval_ind is None else np.ascontiguousarray(eval_ind, dtype=np.uint8)
+        cx = None if const_x is None else _f64(const_x)
+        ci = None if const_ind is None else np.ascontiguousarray(const_ind, dtype=np.uint8)
+        nfull = x.size if cx is None else cx.size
+        self.check(self.lib.pnol_alpha_pool(self.h, f.handle, _ptr(x), _ptr(p), x.size, _ptr(alpha), npool,
+                                            C.c_double(dalpha), _ptr(ei), _ptr(cx), _ptr(ci), nfull, _ptr(phi), _ptr(dphi),
+                                            C.byref(bad)))
+        return phi, dphi, bad.value
+
+    # ---- residual models ----
+    def residual_eval(self, f, x, F=None, want_sumsq=True):
+        x = _f64(x)
+        host = F is None
+        if host:
+            F = np.empty(f.m, dtype=np.float64)
+        ss = C.c_double()
+        self.check(self.lib.pnol_residual_eval(self.h, f.handle, _ptr(x), x.size, _ptr(F),
+                                               C.byref(ss) if want_sumsq else None))
+        return F, ss.value
+
+    def fd_jacobian(self, f, x, dx, J=None, F=None, mode=JAC_AUTO):
+        x, dx = _f64(x), _f64(dx)
+        host = J is None
+        if host:
+            J = np.empty((f.m, x.size), dtype=np.float64)
+            F = np.empty(f.m, dtype=np.float64)
+        self.check(self.lib.pnol_fd_jacobian(self.h, f.handle, _ptr(x), _ptr(dx), x.size, _ptr(J), _ptr(F), int(mode)))
+        return J, F
+
+    def lm_normal_eq(self, J, F, m, n, lam, JTJ=None, A=None, rhs=None):
+        host = JTJ is None and A is None and rhs is None
+        if host:
+            JTJ, A, rhs = np.empty((n, n)), np.empty((n, n)), np.empty(n)
+        self.check(self.lib.pnol_lm_normal_eq(self.h, _ptr(J), _ptr(F), C.c_longlong(m), int(n), C.c_double(lam), _ptr(JTJ),
+                                              _ptr(A), _ptr(rhs)))
+        return JTJ, A, rhs
+
+    def spd_solve(self, A, rhs, n, x=None):
+        host = x is None
+        if host:
+            x = np.empty(n)
+        info = C.c_int()
+        self.check(self.lib.pnol_spd_solve(self.h, _ptr(A), _ptr(rhs), int(n), _ptr(x), C.byref(info)))
+        return x
+
+    # ---- BFGS dense pieces ----
+    def matvec_neg(self, D, g, n, p=None):
+        if p is None:
+            p = np.empty(n)
+        self.check(self.lib.pnol_matvec_neg(self.h, _ptr(D), _ptr(g), int(n), _ptr(p)))
+        return p
+
+    def bfgs_update_hinv(self, D, g, s, n, mode=HINV_RANK2):
+        self.check(self.lib.pnol_bfgs_update_hinv(self.h, _ptr(D), _ptr(g), _ptr(s), int(n), int(mode)))
+        return D
+
+    def dgemm_nn(self, A, B, Cm, M, N, K):
+        self.check(self.lib.pnol_dgemm_nn(self.h, _ptr(A), _ptr(B), _ptr(Cm), int(M), int(N), int(K)))
+        return Cm

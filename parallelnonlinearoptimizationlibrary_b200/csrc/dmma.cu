@@ -1,0 +1,480 @@
+// dmma.cu -- the dense FP64 contractions on the tensor cores (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05
+// has no FP64 kind, so the warp-level DMMA is the Blackwell FP64 tensor path -- SURVEY.md 7.4, Appendix C).
+//
+//  * syrk_kernel   : packed[JTJ | JTr] partials of J^T J (lower-triangle tiles only) and J^T F, split-K over the
+//                    rows of J with persistent CTAs; replaces matrixTranspose + matrixMultiply(JT,J,JTJ) +
+//                    matrixVectorMultiply(JT,F,rhs) of Source/LevenbergMarquardtMPI.cpp:64-65,83.
+//  * syrk_finish   : fixed-order reduction of the partials (deterministic), mirroring to the upper triangle.
+//  * gemm_nn_kernel: C = A B for the literal updateHessianInv (Source/BFGS_with_linesearch.cpp:421-422).
+//
+// Tiling: CTA tile 128 x 128 (16 warps, warp tile 32 x 32 = 4 x 4 DMMA tiles, 32 FP64 accumulators per thread),
+// K chunk of 16 rows staged with cp.async into a 4-stage shared-memory ring. Operand rows are padded to a pitch
+// = 4 (mod 16) doubles so that the DMMA fragment loads (4 k-rows x 8 columns per warp) hit 16 distinct 8-byte
+// banks per half-warp. For SYRK the A and B fragments come from the SAME staged rows of J.
+#include "common.cuh"
+
+namespace pnol {
+
+constexpr int kBT = 128;            // CTA tile edge
+constexpr int kKC = 16;             // K rows per stage
+constexpr int kStages = 4;
+constexpr int kPitchB = kBT + 4;    // pitch of a [kKC][kBT] operand tile (132 = 4 mod 16)
+constexpr int kPitchA = kKC + 4;    // pitch of a [kBT][kKC] operand tile (20 = 4 mod 16)
+constexpr int kDmmaThreads = 512;
+
+__device__ __forceinline__ void dmma_8x8x4(double & d0, double & d1, double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+	             : "+d"(d0), "+d"(d1)
+	             : "d"(a), "d"(b));
+}
+
+template <int BYTES> __device__ __forceinline__ void cp_async_zfill(void * smem_dst, const void * gsrc, bool valid)
+{
+	unsigned dst = (unsigned) __cvta_generic_to_shared(smem_dst);
+	int sz = valid ? BYTES : 0;
+	if (BYTES == 16)
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(sz));
+	else
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---------------------------------------------------------------------------------------------------
+// SYRK
+// ---------------------------------------------------------------------------------------------------
+struct SyrkWork {
+	int bi, bj;                 // tile row / col block (bj <= bi)
+	int slot;                   // partial-result slot
+	int pad;
+	long long chunk0, chunk1;   // K chunks [chunk0, chunk1) of kKC rows
+};
+
+struct SyrkStage {
+	double A[kKC * kPitchB];
+	double B[kKC * kPitchB];
+	double F[kKC];
+};
+
+template <bool kVec16>
+__device__ __forceinline__ void syrk_load_rows(double * dst, const double * __restrict__ J, long long m, int n,
+                                               long long row0, int col0, int tid)
+{
+	if (kVec16) {
+		// kKC rows x 64 sixteen-byte pieces
+#pragma unroll
+		for (int e = tid; e < kKC * (kBT / 2); e += kDmmaThreads) {
+			int r = e >> 6, c = (e & 63) * 2;
+			long long row = row0 + r;
+			bool valid = row < m && (col0 + c) < n;
+			const double * src = valid ? (J + row * n + col0 + c) : J;
+			cp_async_zfill<16>(dst + r * kPitchB + c, src, valid);
+		}
+	} else {
+#pragma unroll
+		for (int e = tid; e < kKC * kBT; e += kDmmaThreads) {
+			int r = e >> 7, c = e & 127;
+			long long row = row0 + r;
+			bool valid = row < m && (col0 + c) < n;
+			const double * src = valid ? (J + row * n + col0 + c) : J;
+			cp_async_zfill<8>(dst + r * kPitchB + c, src, valid);
+		}
+	}
+}
+
+template <bool kVec16>
+__global__ void __launch_bounds__(kDmmaThreads, 1)
+syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long long m, int n,
+            const SyrkWork * __restrict__ work, double * __restrict__ part_tiles, double * __restrict__ part_rhs)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	SyrkStage * stages = reinterpret_cast<SyrkStage *>(smem_raw);
+
+	const SyrkWork wk = work[blockIdx.x];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int wi = warp >> 2, wj = warp & 3;
+	const bool diag = wk.bi == wk.bj;
+	const bool active = !diag || wj <= wi;          // warp tile in the lower triangle
+	const bool diagwarp = diag && wi == wj;
+	const int colA = wk.bi * kBT, colB = wk.bj * kBT;
+
+	// idle warps of a diagonal tile accumulate J^T F for the tile's 128 columns
+	int rhs_col = -1;
+	if (diag && !active) {
+		// (wi,wj) in {(0,1),(0,2),(0,3),(1,2),(1,3),(2,3)} -> 0..5
+		int ord = (wi == 0) ? (wj - 1) : (wi == 1) ? (wj + 1) : 5;
+		int t = ord * 32 + lane;
+		if (t < kBT) rhs_col = t;
+	}
+	double rhs_acc = 0;
+
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+
+	auto issue = [&](long long chunk) {
+		if (chunk < wk.chunk1) {
+			SyrkStage & st = stages[(int) ((chunk - wk.chunk0) % kStages)];
+			long long row0 = chunk * kKC;
+			syrk_load_rows<kVec16>(st.A, J, m, n, row0, colA, tid);
+			if (!diag) syrk_load_rows<kVec16>(st.B, J, m, n, row0, colB, tid);
+			if (diag && Fv && tid < kKC) {
+				long long row = row0 + tid;
+				bool valid = row < m;
+				cp_async_zfill<8>(&st.F[tid], valid ? (Fv + row) : Fv, valid);
+			}
+		}
+		cp_async_commit();
+	};
+
+#pragma unroll
+	for (int s = 0; s < kStages - 1; s++) issue(wk.chunk0 + s);
+
+	for (long long chunk = wk.chunk0; chunk < wk.chunk1; chunk++) {
+		cp_async_wait<kStages - 2>();
+		__syncthreads();
+		issue(chunk + kStages - 1);
+		const SyrkStage & st = stages[(int) ((chunk - wk.chunk0) % kStages)];
+		const double * As = st.A;
+		const double * Bs = diag ? st.A : st.B;
+		if (active) {
+#pragma unroll
+			for (int kk = 0; kk < kKC; kk += 4) {
+				double a[4], b[4];
+				const int krow = (kk + (lane & 3)) * kPitchB + (lane >> 2);
+#pragma unroll
+				for (int i = 0; i < 4; i++) a[i] = As[krow + wi * 32 + i * 8];
+#pragma unroll
+				for (int j = 0; j < 4; j++) b[j] = Bs[krow + wj * 32 + j * 8];
+#pragma unroll
+				for (int i = 0; i < 4; i++)
+#pragma unroll
+					for (int j = 0; j < 4; j++)
+						if (!diagwarp || j <= i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+			}
+		} else if (rhs_col >= 0 && Fv) {
+#pragma unroll
+			for (int k = 0; k < kKC; k++) rhs_acc = fma(As[k * kPitchB + rhs_col], st.F[k], rhs_acc);
+		}
+	}
+	cp_async_wait<0>();
+
+	// partial tile -> workspace slot (row-major 128 x 128)
+	double * tile = part_tiles + (size_t) wk.slot * kBT * kBT;
+	if (active) {
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (diagwarp && j > i) continue;
+				int p = wi * 32 + i * 8 + (lane >> 2);
+				int q = wj * 32 + j * 8 + 2 * (lane & 3);
+				*reinterpret_cast<double2 *>(tile + p * kBT + q) = make_double2(acc[i][j][0], acc[i][j][1]);
+			}
+	}
+	if (rhs_col >= 0) part_rhs[(size_t) wk.slot * kBT + rhs_col] = rhs_acc;
+}
+
+// packed[p*n + q] (and its mirror) = sum over the role's slots, in slot order; packed[n*n + p] = sum of rhs partials
+__global__ void __launch_bounds__(256)
+syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __restrict__ part_rhs,
+                   const int * __restrict__ role_slot0, const int * __restrict__ role_nslots, int n, int nb,
+                   double * __restrict__ packed)
+{
+	long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	long long total = (long long) n * n;
+	if (idx < total) {
+		int p = (int) (idx / n), q = (int) (idx - (long long) p * n);
+		if (q <= p) {
+			int bi = p / kBT, bj = q / kBT;
+			int role = bi * (bi + 1) / 2 + bj;
+			int pl = p - bi * kBT, ql = q - bj * kBT;
+			const double * src = part_tiles + (size_t) role_slot0[role] * kBT * kBT + pl * kBT + ql;
+			double s = 0;
+			int ns = role_nslots[role];
+			for (int k = 0; k < ns; k++) s = s + src[(size_t) k * kBT * kBT];
+			packed[(long long) p * n + q] = s;
+			packed[(long long) q * n + p] = s;
+		}
+	} else if (idx < total + n) {
+		int p = (int) (idx - total);
+		int b = p / kBT;
+		int role = b * (b + 1) / 2 + b;
+		const double * src = part_rhs + (size_t) role_slot0[role] * kBT + (p - b * kBT);
+		double s = 0;
+		int ns = role_nslots[role];
+		for (int k = 0; k < ns; k++) s = s + src[(size_t) k * kBT];
+		packed[total + p] = s;
+	}
+	(void) nb;
+}
+
+int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed)
+{
+	PNOL_REQUIRE(ctx, n >= 1 && m >= 0, "syrk: bad shape m=%lld n=%d", m, n);
+	const int nb = (n + kBT - 1) / kBT;
+	const int nroles = nb * (nb + 1) / 2;
+	const long long nchunks = (m + kKC - 1) / kKC;
+
+	// CTA budget per role, proportional to its DMMA count (diagonal tiles do 136 of 256 warp-tile products)
+	int grid_cap = ctx->sm_count;
+	std::vector<int> nslots(nroles), slot0(nroles);
+	{
+		double wsum = 0;
+		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) wsum += (bi == bj) ? 136.0 : 256.0;
+		int used = 0;
+		for (int bi = 0, r = 0; bi < nb; bi++)
+			for (int bj = 0; bj <= bi; bj++, r++) {
+				double w = (bi == bj) ? 136.0 : 256.0;
+				int c = (int) (grid_cap * w / wsum + 0.5);
+				if (c < 1) c = 1;
+				if ((long long) c > nchunks) c = (int) (nchunks > 0 ? nchunks : 1);
+				nslots[r] = c; used += c;
+			}
+		// trim overshoot from the largest roles so that one wave holds everything when possible
+		while (used > grid_cap && nroles <= grid_cap) {
+			int big = 0;
+			for (int r = 1; r < nroles; r++) if (nslots[r] > nslots[big]) big = r;
+			if (nslots[big] <= 1) break;
+			nslots[big]--; used--;
+		}
+		int s = 0;
+		for (int r = 0; r < nroles; r++) { slot0[r] = s; s += nslots[r]; }
+	}
+	int total_slots = slot0[nroles - 1] + nslots[nroles - 1];
+
+	std::vector<SyrkWork> work(total_slots);
+	for (int bi = 0, r = 0; bi < nb; bi++)
+		for (int bj = 0; bj <= bi; bj++, r++)
+			for (int k = 0; k < nslots[r]; k++) {
+				SyrkWork & w = work[slot0[r] + k];
+				w.bi = bi; w.bj = bj; w.slot = slot0[r] + k; w.pad = 0;
+				w.chunk0 = nchunks * k / nslots[r];
+				w.chunk1 = nchunks * (k + 1) / nslots[r];
+			}
+
+	size_t bytes_work = total_slots * sizeof(SyrkWork);
+	size_t bytes_roles = (size_t) 2 * nroles * sizeof(int);
+	size_t bytes_tiles = (size_t) total_slots * kBT * kBT * sizeof(double);
+	size_t bytes_rhs = (size_t) total_slots * kBT * sizeof(double);
+	size_t off_roles = (bytes_work + 255) & ~(size_t) 255;
+	size_t off_tiles = (off_roles + bytes_roles + 255) & ~(size_t) 255;
+	size_t off_rhs = off_tiles + bytes_tiles;
+	PNOL_CHECK(ws_reserve(ctx, 0, off_rhs + bytes_rhs));
+	unsigned char * ws = (unsigned char *) ctx->ws[0];
+	// the descriptor tables are tiny; stage them through one pageable->device copy each (stream ordered)
+	std::vector<int> roles(2 * nroles);
+	for (int r = 0; r < nroles; r++) { roles[r] = slot0[r]; roles[nroles + r] = nslots[r]; }
+	PNOL_CUDA(ctx, cudaMemcpyAsync(ws, work.data(), bytes_work, cudaMemcpyHostToDevice, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(ws + off_roles, roles.data(), bytes_roles, cudaMemcpyHostToDevice, ctx->stream));
+	PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors die at scope exit
+	double * part_tiles = (double *) (ws + off_tiles);
+	double * part_rhs = (double *) (ws + off_rhs);
+	PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));
+
+	const bool vec16 = (n % 2 == 0) && ((((size_t) J) & 15) == 0);
+	size_t smem = sizeof(SyrkStage) * kStages;
+	{
+		TimerScope ts(ctx, "syrk");
+		if (vec16) {
+			auto kern = syrk_kernel<true>;
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
+		} else {
+			auto kern = syrk_kernel<false>;
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
+		}
+	}
+	{
+		TimerScope ts(ctx, "syrk_finish");
+		long long total = (long long) n * n + n;
+		PNOL_LAUNCH(ctx, syrk_finish_kernel, (unsigned) ((total + 255) / 256), 256, 0, part_tiles, part_rhs,
+		            (const int *) (ws + off_roles), (const int *) (ws + off_roles) + nroles, n, nb, packed);
+	}
+	return PNOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GEMM  C[M x N] = A[M x K] B[K x N], all row-major
+// ---------------------------------------------------------------------------------------------------
+struct GemmStage {
+	double A[kBT * kPitchA];
+	double B[kKC * kPitchB];
+};
+
+template <bool kVec16>
+__global__ void __launch_bounds__(kDmmaThreads, 1)
+gemm_nn_kernel(const double * __restrict__ A, const double * __restrict__ B, double * __restrict__ C, int M, int N, int K)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	GemmStage * stages = reinterpret_cast<GemmStage *>(smem_raw);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int wi = warp >> 2, wj = warp & 3;
+	const int m0 = blockIdx.y * kBT, n0 = blockIdx.x * kBT;
+	const int nchunks = (K + kKC - 1) / kKC;
+
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+
+	auto issue = [&](int chunk) {
+		if (chunk < nchunks) {
+			GemmStage & st = stages[chunk % kStages];
+			const int kc0 = chunk * kKC;
+			if (kVec16) {
+#pragma unroll
+				for (int e = tid; e < kBT * (kKC / 2); e += kDmmaThreads) {       // A: 128 rows x 8 pieces
+					int r = e >> 3, c = (e & 7) * 2;
+					bool valid = (m0 + r) < M && (kc0 + c) < K;
+					const double * src = valid ? (A + (long long) (m0 + r) * K + kc0 + c) : A;
+					cp_async_zfill<16>(st.A + r * kPitchA + c, src, valid);
+				}
+#pragma unroll
+				for (int e = tid; e < kKC * (kBT / 2); e += kDmmaThreads) {       // B: 16 rows x 64 pieces
+					int r = e >> 6, c = (e & 63) * 2;
+					bool valid = (kc0 + r) < K && (n0 + c) < N;
+					const double * src = valid ? (B + (long long) (kc0 + r) * N + n0 + c) : B;
+					cp_async_zfill<16>(st.B + r * kPitchB + c, src, valid);
+				}
+			} else {
+#pragma unroll
+				for (int e = tid; e < kBT * kKC; e += kDmmaThreads) {
+					int r = e >> 4, c = e & 15;
+					bool valid = (m0 + r) < M && (kc0 + c) < K;
+					const double * src = valid ? (A + (long long) (m0 + r) * K + kc0 + c) : A;
+					cp_async_zfill<8>(st.A + r * kPitchA + c, src, valid);
+				}
+#pragma unroll
+				for (int e = tid; e < kKC * kBT; e += kDmmaThreads) {
+					int r = e >> 7, c = e & 127;
+					bool valid = (kc0 + r) < K && (n0 + c) < N;
+					const double * src = valid ? (B + (long long) (kc0 + r) * N + n0 + c) : B;
+					cp_async_zfill<8>(st.B + r * kPitchB + c, src, valid);
+				}
+			}
+		}
+		cp_async_commit();
+	};
+
+#pragma unroll
+	for (int s = 0; s < kStages - 1; s++) issue(s);
+
+	for (int chunk = 0; chunk < nchunks; chunk++) {
+		cp_async_wait<kStages - 2>();
+		__syncthreads();
+		issue(chunk + kStages - 1);
+		const GemmStage & st = stages[chunk % kStages];
+#pragma unroll
+		for (int kk = 0; kk < kKC; kk += 4) {
+			double a[4], b[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) a[i] = st.A[(wi * 32 + i * 8 + (lane >> 2)) * kPitchA + kk + (lane & 3)];
+#pragma unroll
+			for (int j = 0; j < 4; j++) b[j] = st.B[(kk + (lane & 3)) * kPitchB + wj * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+		}
+	}
+	cp_async_wait<0>();
+
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			int p = m0 + wi * 32 + i * 8 + (lane >> 2);
+			int q = n0 + wj * 32 + j * 8 + 2 * (lane & 3);
+			if (p < M) {
+				if (kVec16 && q + 1 < N) {
+					*reinterpret_cast<double2 *>(C + (long long) p * N + q) = make_double2(acc[i][j][0], acc[i][j][1]);
+				} else {
+					if (q < N) C[(long long) p * N + q] = acc[i][j][0];
+					if (q + 1 < N) C[(long long) p * N + q + 1] = acc[i][j][1];
+				}
+			}
+		}
+}
+
+int launch_dgemm_nn(pnol_ctx * ctx, const double * A, const double * B, double * C, int M, int N, int K)
+{
+	PNOL_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "dgemm: bad shape %d %d %d", M, N, K);
+	TimerScope ts(ctx, "dgemm_nn");
+	dim3 grid((N + kBT - 1) / kBT, (M + kBT - 1) / kBT);
+	size_t smem = sizeof(GemmStage) * kStages;
+	bool vec16 = (N % 2 == 0) && (K % 2 == 0) && ((((size_t) A) | ((size_t) B) | ((size_t) C)) & 15) == 0;
+	if (vec16) {
+		auto kern = gemm_nn_kernel<true>;
+		PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		PNOL_LAUNCH(ctx, kern, grid, kDmmaThreads, smem, A, B, C, M, N, K);
+	} else {
+		auto kern = gemm_nn_kernel<false>;
+		PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		PNOL_LAUNCH(ctx, kern, grid, kDmmaThreads, smem, A, B, C, M, N, K);
+	}
+	return PNOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// register-resident DMMA peak microbenchmark (roofline denominator for the tensor-bound kernels)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDmmaThreads, 1)
+dmma_peak_kernel(int iters, double * __restrict__ sink)
+{
+	double acc[4][4][2];
+	double a[4], b[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+		b[i] = 1.0 - 1e-9 * (threadIdx.x + i);
+#pragma unroll
+		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+	}
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+	}
+	double s = 0;
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
+	if (s == 123.456) sink[0] = s;
+}
+
+} // namespace pnol
+
+extern "C" int pnol_measure_dmma_peak(pnol_ctx * ctx, double * tflops_out)
+{
+	using namespace pnol;
+	if (!ctx || !tflops_out) return PNOL_ERR_INVALID;
+	PNOL_CHECK(ws_reserve(ctx, 3, 64));
+	const int iters = 20000;
+	cudaEvent_t e0, e1;
+	PNOL_CUDA(ctx, cudaEventCreate(&e0));
+	PNOL_CUDA(ctx, cudaEventCreate(&e1));
+	double best = 0;
+	for (int rep = 0; rep < 4; rep++) {
+		PNOL_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+		PNOL_LAUNCH(ctx, dmma_peak_kernel, ctx->sm_count, kDmmaThreads, 0, iters, (double *) ctx->ws[3]);
+		PNOL_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+		PNOL_CUDA(ctx, cudaEventSynchronize(e1));
+		float ms = 0;
+		PNOL_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+		// per warp per iteration: 16 DMMA.8x8x4 = 16 * 2*8*8*4 flop
+		double flops = (double) ctx->sm_count * (kDmmaThreads / 32) * (double) iters * 16.0 * 512.0;
+		double tf = flops / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*tflops_out = best;
+	return PNOL_OK;
+}
