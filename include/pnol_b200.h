@@ -155,7 +155,7 @@ int pnol_alpha_pool(pnol_ctx * ctx, const pnol_functor * f, const double * x, co
 /* ---------------------------------------------------------------------------------------------------
  * a2 / a10: residual evaluation F = F(x) over this context's rows; sumsq_out (optional) receives the
  * sequentially-ordered-per-block sum of F^2 over ALL ranks (MultiObjective::objEval + vector2Norm^2,
- * Source/LevenbergMarquardtMPI.cpp:103-108). F may be NULL when only sumsq is wanted... no: F is required.
+ * Source/LevenbergMarquardtMPI.cpp:103-108). F is required (host or device, m doubles).
  * ------------------------------------------------------------------------------------------------- */
 int pnol_residual_eval(pnol_ctx * ctx, const pnol_functor * f, const double * x, int n, double * F, double * sumsq_out);
 
@@ -274,6 +274,9 @@ int pnol_measure_copy_bandwidth(pnol_ctx * ctx, double * gbs_out);
 int pnol_timer_enable(pnol_ctx * ctx, int on);
 int pnol_timer_get(pnol_ctx * ctx, const char * name, double * total_ms, long long * count);
 int pnol_timer_reset(pnol_ctx * ctx);
+/* self test: number of (x, d) pairs out of `pairs` pseudo-random / adversarial ones for which the reciprocal-based
+ * exact division of the Jacobian kernels (csrc/exact_div.cuh) differs from x / d. Must return 0 mismatches. */
+int pnol_selftest_exact_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches);
 
 #ifdef __cplusplus
 }

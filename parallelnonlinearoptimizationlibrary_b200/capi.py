@@ -87,7 +87,7 @@ EXPORTS = [
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
     "pnol_ga_check_identical", "pnol_measure_dmma_peak", "pnol_measure_copy_bandwidth", "pnol_timer_enable",
-    "pnol_timer_get", "pnol_timer_reset",
+    "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div",
 ]
 
 _lib = None
@@ -137,7 +137,20 @@ def _ptr(a):
 
 
 def _f64(a):
+    """Host arrays are made contiguous float64; raw device pointers (int) and torch tensors pass through."""
+    if a is None or isinstance(a, (int, np.integer)) or hasattr(a, "data_ptr"):
+        return a
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _len(a, n):
+    if n is not None:
+        return int(n)
+    if isinstance(a, np.ndarray):
+        return int(a.size)
+    if hasattr(a, "numel"):
+        return int(a.numel())
+    raise TypeError("pass n= explicitly when the point is a raw device pointer")
 
 
 class Functor:
@@ -243,6 +256,11 @@ class Context:
         self.check(self.lib.pnol_measure_copy_bandwidth(self.h, C.byref(v)))
         return v.value
 
+    def selftest_exact_div(self, pairs, seed=1):
+        bad = C.c_ulonglong()
+        self.check(self.lib.pnol_selftest_exact_div(self.h, C.c_longlong(pairs), C.c_ulonglong(seed), C.byref(bad)))
+        return int(bad.value)
+
     # ---- communicator ----
     def comm_unique_id(self):
         buf = C.create_string_buffer(COMM_ID_BYTES)
@@ -340,23 +358,25 @@ class Context:
         return phi, dphi, bad.value
 
     # ---- residual models ----
-    def residual_eval(self, f, x, F=None, want_sumsq=True):
+    def residual_eval(self, f, x, F=None, want_sumsq=True, n=None):
         x = _f64(x)
+        n = _len(x, n)
         host = F is None
         if host:
             F = np.empty(f.m, dtype=np.float64)
         ss = C.c_double()
-        self.check(self.lib.pnol_residual_eval(self.h, f.handle, _ptr(x), x.size, _ptr(F),
+        self.check(self.lib.pnol_residual_eval(self.h, f.handle, _ptr(x), n, _ptr(F),
                                                C.byref(ss) if want_sumsq else None))
         return F, ss.value
 
-    def fd_jacobian(self, f, x, dx, J=None, F=None, mode=JAC_AUTO):
+    def fd_jacobian(self, f, x, dx, J=None, F=None, mode=JAC_AUTO, n=None):
         x, dx = _f64(x), _f64(dx)
+        n = _len(x, n)
         host = J is None
         if host:
-            J = np.empty((f.m, x.size), dtype=np.float64)
+            J = np.empty((f.m, n), dtype=np.float64)
             F = np.empty(f.m, dtype=np.float64)
-        self.check(self.lib.pnol_fd_jacobian(self.h, f.handle, _ptr(x), _ptr(dx), x.size, _ptr(J), _ptr(F), int(mode)))
+        self.check(self.lib.pnol_fd_jacobian(self.h, f.handle, _ptr(x), _ptr(dx), n, _ptr(J), _ptr(F), int(mode)))
         return J, F
 
     def lm_normal_eq(self, J, F, m, n, lam, JTJ=None, A=None, rhs=None):

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" glue of include/pnol_b200.h: context, memory, functors, and the evaluation / LM / BFGS
 // entry points (the GA entry points live in ga.cu, the communicator in comm.cu).
 #include "common.cuh"
+#include "exact_div.cuh"
 
 #include <math.h>
 
@@ -69,6 +70,12 @@ extern "C" int pnol_ctx_create(pnol_ctx ** out, int device)
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PNOL_ERR_CUDA; }
+	// staging buffers come from the stream-ordered pool: keep freed blocks cached across synchronisations
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		uint64_t keep = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
 	*out = ctx;
 	return PNOL_OK;
 }
@@ -620,4 +627,51 @@ extern "C" int pnol_measure_copy_bandwidth(pnol_ctx * ctx, double * gbs_out)
 	cudaFree(a); cudaFree(b);
 	*gbs_out = best;
 	return PNOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// self test of exact_div.cuh: counts pairs where div_exact(x, d) differs from x / d (must be 0)
+// ---------------------------------------------------------------------------------------------------
+__global__ void exact_div_selftest_kernel(unsigned long long seed, long long per_thread, unsigned long long * __restrict__ bad)
+{
+	unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (1 + (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x);
+	unsigned long long nbad = 0;
+	for (long long i = 0; i < per_thread; i++) {
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		unsigned long long md = s;
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		unsigned long long mx = s;
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		const int mode = (int) (i & 7);
+		if (mode == 1) md |= 0xFFFFFFFFFF000ULL;
+		if (mode == 2) md &= 0xFFFULL;
+		if (mode == 3) mx |= 0xFFFFFFFFFFFF0ULL;
+		if (mode == 4) mx &= 0xFFULL;
+		if (mode == 5) md = 0xFFFFFFFFFFFFFULL - (s & 0xF);
+		int ed = (int) ((s >> 8) % 60) - 40, exx = (int) ((s >> 20) % 80) - 40;
+		if (mode == 6) exx = (int) ((s >> 20) % 2040) - 1020;      // whole exponent range incl. subnormal-ish, inf/nan
+		double d = __longlong_as_double((long long) (((unsigned long long) (ed + 1023) << 52) | (md & 0xFFFFFFFFFFFFFULL)));
+		double x = __longlong_as_double((long long) (((unsigned long long) (exx + 1023) << 52) | (mx & 0xFFFFFFFFFFFFFULL)));
+		if (mode == 7 && (i & 8)) x = 0.0;
+		if (s & 1) x = -x;
+		if (s & 2) d = -d;
+		pnol::RecipDiv rd = pnol::make_recip(d);
+		double got = pnol::div_exact(x, rd);
+		double want = x / d;
+		if (__double_as_longlong(got) != __double_as_longlong(want) && !(got != got && want != want)) nbad++;
+	}
+	if (nbad) atomicAdd(bad, nbad);
+}
+
+extern "C" int pnol_selftest_exact_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches)
+{
+	if (!ctx || !mismatches) return PNOL_ERR_INVALID;
+	PNOL_CHECK(ws_reserve(ctx, 3, 64));
+	unsigned long long * bad = (unsigned long long *) ctx->ws[3];
+	PNOL_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
+	const int blocks = ctx->sm_count * 8, threads = 256;
+	long long per_thread = (pairs + (long long) blocks * threads - 1) / ((long long) blocks * threads);
+	PNOL_LAUNCH(ctx, exact_div_selftest_kernel, blocks, threads, 0, seed, per_thread, bad);
+	PNOL_CUDA(ctx, cudaMemcpyAsync(mismatches, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	return finish(ctx);
 }

@@ -229,19 +229,22 @@ int launch_matvec_neg(pnol_ctx * ctx, const double * D, const double * g, int n,
 // a11: updateHessianInv(D, g, s)   (Source/BFGS_with_linesearch.cpp:389-432)
 // ---------------------------------------------------------------------------------------------------
 // rank-2 form. pass 1: u = D g (row sums), v = D^T g (column sums), both from ONE read of D.
-constexpr int kR2Rows = 32;   // rows per block in pass 1
+constexpr int kR2Rows = 32;     // rows per block in pass 1
+constexpr int kR2Cols = 512;    // columns per block in pass 1 (8 warps x 512 x 8 B = 32 KB static smem)
 
 __global__ void __launch_bounds__(256)
-hinv_pass1_kernel(const double * __restrict__ D, const double * __restrict__ g, int n, double * __restrict__ u,
+hinv_pass1_kernel(const double * __restrict__ D, const double * __restrict__ g, int n, double * __restrict__ upart /* gridDim.y x n */,
                   double * __restrict__ vpart /* gridDim.x x n */)
 {
-	// block = 8 warps, rows [r0, r0 + 32): warp w handles rows r0 + w, r0 + w + 8, ...; each lane keeps column
-	// partials for the columns it touches in shared memory (one slice per warp, combined at the end).
-	extern __shared__ double sm[];      // 8 x n column partials
+	// block = 8 warps, rows [r0, r0 + 32) x columns [c0, c0 + 1024): warp w handles rows r0 + w, r0 + w + 8, ...;
+	// column partials are kept per warp in shared memory and combined at the end (fixed order).
+	__shared__ double sm[8 * kR2Cols];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int r0 = blockIdx.x * kR2Rows;
-	double * vcol = sm + (size_t) warp * n;
-	for (int k = lane; k < n; k += 32) vcol[k] = 0;
+	const int c0 = blockIdx.y * kR2Cols;
+	const int c1 = min(n, c0 + kR2Cols);
+	double * vcol = sm + warp * kR2Cols;
+	for (int k = lane; k < kR2Cols; k += 32) vcol[k] = 0;
 	__syncwarp();
 	for (int rr = warp; rr < kR2Rows; rr += 8) {
 		int row = r0 + rr;
@@ -249,31 +252,31 @@ hinv_pass1_kernel(const double * __restrict__ D, const double * __restrict__ g, 
 		const double * Dr = D + (long long) row * n;
 		const double gi = g[row];
 		double s = 0;
-		for (int k = lane; k < n; k += 32) {
+		for (int k = c0 + lane; k < c1; k += 32) {
 			double d = Dr[k];
 			s = fma(d, g[k], s);
-			vcol[k] = fma(gi, d, vcol[k]);
+			vcol[k - c0] = fma(gi, d, vcol[k - c0]);
 		}
 		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-		if (lane == 0) u[row] = s;
+		if (lane == 0) upart[(size_t) blockIdx.y * n + row] = s;
 	}
 	__syncthreads();
-	for (int k = threadIdx.x; k < n; k += blockDim.x) {
+	for (int k = threadIdx.x; k < c1 - c0; k += blockDim.x) {
 		double s = 0;
-		for (int w = 0; w < 8; w++) s = s + sm[(size_t) w * n + k];
-		vpart[(size_t) blockIdx.x * n + k] = s;
+		for (int w = 0; w < 8; w++) s = s + sm[w * kR2Cols + k];
+		vpart[(size_t) blockIdx.x * n + c0 + k] = s;
 	}
 }
 
-// v[k] = sum over blocks of vpart (fixed order); scalars: gs = g.s, gamma = g.u
+// out[k] = sum over parts of part[b][k] (fixed order)
 __global__ void __launch_bounds__(256)
-hinv_pass1_finish_kernel(const double * __restrict__ vpart, int nblocks, int n, double * __restrict__ v)
+hinv_pass1_finish_kernel(const double * __restrict__ part, int nparts, int n, double * __restrict__ out)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= n) return;
 	double s = 0;
-	for (int b = 0; b < nblocks; b++) s = s + vpart[(size_t) b * n + k];
-	v[k] = s;
+	for (int b = 0; b < nparts; b++) s = s + part[(size_t) b * n + k];
+	out[k] = s;
 }
 
 // scal[0] = g.s , scal[1] = g.u   (single block, fixed-order tree)
@@ -328,18 +331,18 @@ hinv_pass2_scalar_kernel(double * __restrict__ D, const double * __restrict__ s,
 int launch_hinv_rank2(pnol_ctx * ctx, double * D, const double * g, const double * s, int n)
 {
 	TimerScope ts(ctx, "hinv_rank2");
-	int nblocks = (n + kR2Rows - 1) / kR2Rows;
-	size_t need = ((size_t) 2 * n + 2 + (size_t) nblocks * n) * sizeof(double);
+	int nrb = (n + kR2Rows - 1) / kR2Rows;
+	int ncb = (n + kR2Cols - 1) / kR2Cols;
+	size_t need = ((size_t) 2 * n + 2 + (size_t) nrb * n + (size_t) ncb * n) * sizeof(double);
 	PNOL_CHECK(ws_reserve(ctx, 1, need));
 	double * u = (double *) ctx->ws[1];
 	double * v = u + n;
 	double * scal = v + n;
 	double * vpart = scal + 2;
-	size_t smem = (size_t) 8 * n * sizeof(double);
-	PNOL_REQUIRE(ctx, smem <= ctx->smem_optin, "hinv rank-2: n = %d too large for the column-sum staging", n);
-	PNOL_CUDA(ctx, cudaFuncSetAttribute(hinv_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	PNOL_LAUNCH(ctx, hinv_pass1_kernel, nblocks, 256, smem, D, g, n, u, vpart);
-	PNOL_LAUNCH(ctx, hinv_pass1_finish_kernel, (n + 255) / 256, 256, 0, vpart, nblocks, n, v);
+	double * upart = vpart + (size_t) nrb * n;
+	PNOL_LAUNCH(ctx, hinv_pass1_kernel, dim3(nrb, ncb), 256, 0, D, g, n, upart, vpart);
+	PNOL_LAUNCH(ctx, hinv_pass1_finish_kernel, (n + 255) / 256, 256, 0, vpart, nrb, n, v);
+	PNOL_LAUNCH(ctx, hinv_pass1_finish_kernel, (n + 255) / 256, 256, 0, upart, ncb, n, u);
 	PNOL_LAUNCH(ctx, dot2_kernel, 1, 1024, 0, g, s, u, n, scal);
 	int grid = ctx->sm_count * 8;
 	if (n % 2 == 0 && (((size_t) D) & 15) == 0)

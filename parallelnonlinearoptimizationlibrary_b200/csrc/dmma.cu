@@ -8,7 +8,7 @@
 //  * gemm_nn_kernel: C = A B for the literal updateHessianInv (Source/BFGS_with_linesearch.cpp:421-422).
 //
 // Tiling: CTA tile 128 x 128 (16 warps, warp tile 32 x 32 = 4 x 4 DMMA tiles, 32 FP64 accumulators per thread),
-// K chunk of 16 rows staged with cp.async into a 4-stage shared-memory ring. Operand rows are padded to a pitch
+// K chunk of 32 rows staged with cp.async into a 3-stage shared-memory ring (~200 KB). Operand rows are padded to a pitch
 // = 4 (mod 16) doubles so that the DMMA fragment loads (4 k-rows x 8 columns per warp) hit 16 distinct 8-byte
 // banks per half-warp. For SYRK the A and B fragments come from the SAME staged rows of J.
 #include "common.cuh"
@@ -16,8 +16,8 @@
 namespace pnol {
 
 constexpr int kBT = 128;            // CTA tile edge
-constexpr int kKC = 16;             // K rows per stage
-constexpr int kStages = 4;
+constexpr int kKC = 32;             // K rows per stage
+constexpr int kStages = 3;
 constexpr int kPitchB = kBT + 4;    // pitch of a [kKC][kBT] operand tile (132 = 4 mod 16)
 constexpr int kPitchA = kKC + 4;    // pitch of a [kBT][kKC] operand tile (20 = 4 mod 16)
 constexpr int kDmmaThreads = 512;
@@ -57,31 +57,55 @@ struct SyrkStage {
 	double F[kKC];
 };
 
-template <bool kVec16>
-__device__ __forceinline__ void syrk_load_rows(double * dst, const double * __restrict__ J, long long m, int n,
-                                               long long row0, int col0, int tid)
+// one warp tile, one K chunk: 4 x 4 DMMA tiles per k-step. kLower: diagonal warp tile, only j <= i is needed.
+template <bool kLower>
+__device__ __forceinline__ void warp_tile_chunk(double (&acc)[4][4][2], const double * __restrict__ As,
+                                                const double * __restrict__ Bs, int lane)
 {
-	if (kVec16) {
-		// kKC rows x 64 sixteen-byte pieces
 #pragma unroll
-		for (int e = tid; e < kKC * (kBT / 2); e += kDmmaThreads) {
-			int r = e >> 6, c = (e & 63) * 2;
-			long long row = row0 + r;
-			bool valid = row < m && (col0 + c) < n;
-			const double * src = valid ? (J + row * n + col0 + c) : J;
-			cp_async_zfill<16>(dst + r * kPitchB + c, src, valid);
-		}
-	} else {
+	for (int kk = 0; kk < kKC; kk += 4) {
+		double a[4], b[4];
+		const int krow = (kk + (lane & 3)) * kPitchB + (lane >> 2);
 #pragma unroll
-		for (int e = tid; e < kKC * kBT; e += kDmmaThreads) {
-			int r = e >> 7, c = e & 127;
-			long long row = row0 + r;
-			bool valid = row < m && (col0 + c) < n;
-			const double * src = valid ? (J + row * n + col0 + c) : J;
-			cp_async_zfill<8>(dst + r * kPitchB + c, src, valid);
-		}
+		for (int i = 0; i < 4; i++) a[i] = As[krow + i * 8];
+#pragma unroll
+		for (int j = 0; j < 4; j++) b[j] = Bs[krow + j * 8];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				if (!kLower || j <= i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 	}
 }
+
+// per-thread cp.async plan for one [kKC][kBT] operand tile: piece e = tid + q * 512
+template <bool kVec16> struct RowLoader {
+	static constexpr int kPieces = kVec16 ? (kKC * (kBT / 2)) / kDmmaThreads : (kKC * kBT) / kDmmaThreads;
+	const double * src[kPieces];   // address in chunk 0 of the CTA's range (nullptr: column out of range)
+	int dst[kPieces];              // element offset inside the stage tile
+	int row[kPieces];              // row inside the chunk
+	__device__ __forceinline__ void init(const double * J, int n, long long row0, int col0, int tid)
+	{
+#pragma unroll
+		for (int q = 0; q < kPieces; q++) {
+			int e = tid + q * kDmmaThreads;
+			int r = kVec16 ? (e >> 6) : (e >> 7);
+			int c = kVec16 ? (e & 63) * 2 : (e & 127);
+			row[q] = r;
+			dst[q] = r * kPitchB + c;
+			src[q] = (col0 + c) < n ? (J + (row0 + r) * (long long) n + col0 + c) : nullptr;
+		}
+	}
+	// rows_valid: number of rows of this chunk that exist (>= kKC except in the last chunk)
+	__device__ __forceinline__ void issue(double * tile, const double * J, long long elem_off, long long rows_valid) const
+	{
+#pragma unroll
+		for (int q = 0; q < kPieces; q++) {
+			bool valid = src[q] != nullptr && row[q] < rows_valid;
+			cp_async_zfill<kVec16 ? 16 : 8>(tile + dst[q], valid ? src[q] + elem_off : J, valid);
+		}
+	}
+};
 
 template <bool kVec16>
 __global__ void __launch_bounds__(kDmmaThreads, 1)
@@ -93,18 +117,23 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 
 	const SyrkWork wk = work[blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int wi = warp >> 2, wj = warp & 3;
 	const bool diag = wk.bi == wk.bj;
-	const bool active = !diag || wj <= wi;          // warp tile in the lower triangle
+	// Warp -> 32 x 32 warp tile. The tensor pipe is per SM sub-partition (warp % 4), so in a diagonal CTA tile
+	// (10 live warp tiles, 4 of them 10/16 full) the live tiles are dealt out so that every sub-partition carries
+	// 32..36 DMMA per k-step instead of 64 on one and 10 on another. -1 = idle warp (it sums J^T F instead).
+	//                         warp:  0  1  2  3   4  5  6  7   8  9 10 11  12 13 14 15
+	const int diag_wi[16] =         { 1, 2, 3, 3,  2, 3, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
+	const int diag_wj[16] =         { 0, 1, 1, 2,  0, 0, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
+	const int diag_idle_ord[16] =   {-1,-1,-1,-1, -1,-1,-1,-1,  0, 1,-1,-1,  2, 3, 4, 5};
+	const int wi = diag ? diag_wi[warp] : (warp >> 2);
+	const int wj = diag ? diag_wj[warp] : (warp & 3);
+	const bool active = wi >= 0;
 	const bool diagwarp = diag && wi == wj;
-	const int colA = wk.bi * kBT, colB = wk.bj * kBT;
 
 	// idle warps of a diagonal tile accumulate J^T F for the tile's 128 columns
 	int rhs_col = -1;
 	if (diag && !active) {
-		// (wi,wj) in {(0,1),(0,2),(0,3),(1,2),(1,3),(2,3)} -> 0..5
-		int ord = (wi == 0) ? (wj - 1) : (wi == 1) ? (wj + 1) : 5;
-		int t = ord * 32 + lane;
+		int t = diag_idle_ord[warp] * 32 + lane;
 		if (t < kBT) rhs_col = t;
 	}
 	double rhs_acc = 0;
@@ -115,14 +144,21 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 #pragma unroll
 		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
 
+	RowLoader<kVec16> ldA, ldB;
+	const long long row_begin = wk.chunk0 * kKC;
+	ldA.init(J, n, row_begin, wk.bi * kBT, tid);
+	if (!diag) ldB.init(J, n, row_begin, wk.bj * kBT, tid);
+	const long long chunk_elems = (long long) kKC * n;
+
 	auto issue = [&](long long chunk) {
 		if (chunk < wk.chunk1) {
-			SyrkStage & st = stages[(int) ((chunk - wk.chunk0) % kStages)];
-			long long row0 = chunk * kKC;
-			syrk_load_rows<kVec16>(st.A, J, m, n, row0, colA, tid);
-			if (!diag) syrk_load_rows<kVec16>(st.B, J, m, n, row0, colB, tid);
+			const long long rel = chunk - wk.chunk0;
+			SyrkStage & st = stages[(int) (rel % kStages)];
+			const long long rows_valid = m - chunk * kKC;
+			ldA.issue(st.A, J, rel * chunk_elems, rows_valid);
+			if (!diag) ldB.issue(st.B, J, rel * chunk_elems, rows_valid);
 			if (diag && Fv && tid < kKC) {
-				long long row = row0 + tid;
+				long long row = chunk * kKC + tid;
 				bool valid = row < m;
 				cp_async_zfill<8>(&st.F[tid], valid ? (Fv + row) : Fv, valid);
 			}
@@ -133,32 +169,22 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 #pragma unroll
 	for (int s = 0; s < kStages - 1; s++) issue(wk.chunk0 + s);
 
+	const int aoff = (wi > 0 ? wi : 0) * 32, boff = (wj > 0 ? wj : 0) * 32;
 	for (long long chunk = wk.chunk0; chunk < wk.chunk1; chunk++) {
 		cp_async_wait<kStages - 2>();
 		__syncthreads();
-		issue(chunk + kStages - 1);
 		const SyrkStage & st = stages[(int) ((chunk - wk.chunk0) % kStages)];
-		const double * As = st.A;
-		const double * Bs = diag ? st.A : st.B;
+		const double * As = st.A + aoff;
+		const double * Bs = (diag ? st.A : st.B) + boff;
 		if (active) {
-#pragma unroll
-			for (int kk = 0; kk < kKC; kk += 4) {
-				double a[4], b[4];
-				const int krow = (kk + (lane & 3)) * kPitchB + (lane >> 2);
-#pragma unroll
-				for (int i = 0; i < 4; i++) a[i] = As[krow + wi * 32 + i * 8];
-#pragma unroll
-				for (int j = 0; j < 4; j++) b[j] = Bs[krow + wj * 32 + j * 8];
-#pragma unroll
-				for (int i = 0; i < 4; i++)
-#pragma unroll
-					for (int j = 0; j < 4; j++)
-						if (!diagwarp || j <= i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-			}
+			if (diagwarp) warp_tile_chunk<true>(acc, As, Bs, lane);
+			else warp_tile_chunk<false>(acc, As, Bs, lane);
 		} else if (rhs_col >= 0 && Fv) {
 #pragma unroll
-			for (int k = 0; k < kKC; k++) rhs_acc = fma(As[k * kPitchB + rhs_col], st.F[k], rhs_acc);
+			for (int k = 0; k < kKC; k++) rhs_acc = fma(st.A[k * kPitchB + rhs_col], st.F[k], rhs_acc);
 		}
+		// refill the stage consumed in the previous iteration (every thread is past this iteration's barrier)
+		issue(chunk + kStages - 1);
 	}
 	cp_async_wait<0>();
 
@@ -219,16 +245,16 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	const int nroles = nb * (nb + 1) / 2;
 	const long long nchunks = (m + kKC - 1) / kKC;
 
-	// CTA budget per role, proportional to its DMMA count (diagonal tiles do 136 of 256 warp-tile products)
+	// CTA budget per role, proportional to the time one K chunk takes there (busiest sub-partition)
 	int grid_cap = ctx->sm_count;
 	std::vector<int> nslots(nroles), slot0(nroles);
 	{
 		double wsum = 0;
-		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) wsum += (bi == bj) ? 136.0 : 256.0;
+		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) wsum += (bi == bj) ? 36.0 : 64.0;
 		int used = 0;
 		for (int bi = 0, r = 0; bi < nb; bi++)
 			for (int bj = 0; bj <= bi; bj++, r++) {
-				double w = (bi == bj) ? 136.0 : 256.0;
+				double w = (bi == bj) ? 36.0 : 64.0;   // DMMA per k-step on the busiest sub-partition
 				int c = (int) (grid_cap * w / wsum + 0.5);
 				if (c < 1) c = 1;
 				if ((long long) c > nchunks) c = (int) (nchunks > 0 ? nchunks : 1);
@@ -329,14 +355,14 @@ gemm_nn_kernel(const double * __restrict__ A, const double * __restrict__ B, dou
 			const int kc0 = chunk * kKC;
 			if (kVec16) {
 #pragma unroll
-				for (int e = tid; e < kBT * (kKC / 2); e += kDmmaThreads) {       // A: 128 rows x 8 pieces
-					int r = e >> 3, c = (e & 7) * 2;
+				for (int e = tid; e < kBT * (kKC / 2); e += kDmmaThreads) {       // A: 128 rows x kKC/2 pieces
+					int r = e / (kKC / 2), c = (e % (kKC / 2)) * 2;
 					bool valid = (m0 + r) < M && (kc0 + c) < K;
 					const double * src = valid ? (A + (long long) (m0 + r) * K + kc0 + c) : A;
 					cp_async_zfill<16>(st.A + r * kPitchA + c, src, valid);
 				}
 #pragma unroll
-				for (int e = tid; e < kKC * (kBT / 2); e += kDmmaThreads) {       // B: 16 rows x 64 pieces
+				for (int e = tid; e < kKC * (kBT / 2); e += kDmmaThreads) {       // B: kKC rows x 64 pieces
 					int r = e >> 6, c = (e & 63) * 2;
 					bool valid = (kc0 + r) < K && (n0 + c) < N;
 					const double * src = valid ? (B + (long long) (kc0 + r) * N + n0 + c) : B;
@@ -345,7 +371,7 @@ gemm_nn_kernel(const double * __restrict__ A, const double * __restrict__ B, dou
 			} else {
 #pragma unroll
 				for (int e = tid; e < kBT * kKC; e += kDmmaThreads) {
-					int r = e >> 4, c = e & 15;
+					int r = e / kKC, c = e % kKC;
 					bool valid = (m0 + r) < M && (kc0 + c) < K;
 					const double * src = valid ? (A + (long long) (m0 + r) * K + kc0 + c) : A;
 					cp_async_zfill<8>(st.A + r * kPitchA + c, src, valid);
@@ -368,7 +394,6 @@ gemm_nn_kernel(const double * __restrict__ A, const double * __restrict__ B, dou
 	for (int chunk = 0; chunk < nchunks; chunk++) {
 		cp_async_wait<kStages - 2>();
 		__syncthreads();
-		issue(chunk + kStages - 1);
 		const GemmStage & st = stages[chunk % kStages];
 #pragma unroll
 		for (int kk = 0; kk < kKC; kk += 4) {
@@ -382,6 +407,7 @@ gemm_nn_kernel(const double * __restrict__ A, const double * __restrict__ B, dou
 #pragma unroll
 				for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 		}
+		issue(chunk + kStages - 1);
 	}
 	cp_async_wait<0>();
 

@@ -321,3 +321,9 @@ def test_lm_iterates_match_oracle(ctx, K, m, iters):
         assert rel(trace[k, :n], wt[k, :n]) < 1e-9, "iterate %d" % k
     assert rel(X, want["X"]) < 1e-9
     assert abs(trace[-1, n] - want["chisq"]) <= 1e-9 * max(want["chisq"], 1e-30) + 1e-24
+
+
+def test_exact_division_by_invariant_divisor(ctx):
+    # the FD quotient (FdX - F)/dX is computed with a hoisted reciprocal + two FMA corrections; it must return the
+    # bits of the IEEE division for every input (random, all-ones / near-power-of-two significands, zeros, inf, nan)
+    assert ctx.selftest_exact_div(200_000_000, seed=7) == 0
