@@ -1,0 +1,102 @@
+/*
+ * Runtime.hpp -- process-wide device runtime behind the PNOL plugin classes.
+ *
+ * The reference's algorithm classes find their "parallel machine" implicitly through MPI_COMM_WORLD
+ * (e.g. /root/reference/Source/LevenbergMarquardtMPI.cpp:15-17). Here the implicit machine is one pnol_ctx
+ * (one B200, optionally one rank of an NCCL communicator) owned by pnol::Runtime. Launchers that already hold a
+ * context (bench.py, tests, a torchrun rank) attach it; otherwise one is created on first use on device
+ * $PNOL_DEVICE (else $LOCAL_RANK, else 0).
+ */
+#ifndef PNOL_RUNTIME_HPP_
+#define PNOL_RUNTIME_HPP_
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../pnol_b200.h"
+
+namespace pnol {
+
+class Error : public std::runtime_error {
+  public:
+	Error(int status, const std::string & what) : std::runtime_error(what), status_(status) {}
+	int status() const { return status_; }
+  private:
+	int status_;
+};
+
+class Runtime {
+  public:
+	static Runtime & instance();
+	pnol_ctx * ctx();                         // creates the context on first use; throws pnol::Error without a GPU
+	void attach(pnol_ctx * ctx);              // use a caller-owned context (not destroyed by the runtime)
+	void reset();                             // drop (and destroy if owned) the current context
+	// width of the alpha pools of the pooled line searches: the reference ties it to the MPI rank count
+	// (Source/BFGS_bnd_linesearch_MPI_SW.cpp:229, BFGS_with_linesearch_MPI.cpp:235); here it is a parameter
+	// ($PNOL_POOL_WIDTH, default 8) independent of the GPU count.
+	int poolWidth() const { return poolWidth_; }
+	void setPoolWidth(int w) { poolWidth_ = w < 1 ? 1 : w; }
+	// random stream used by the genetic algorithms (replaces srand(time(0)) + timeRand(),
+	// Source/GeneticAlgorithmMPI.cpp:57,66)
+	void setRandomStream(const pnol_stream_desc & s) { stream_ = s; haveStream_ = true; }
+	bool haveRandomStream() const { return haveStream_; }
+	const pnol_stream_desc & randomStream() const { return stream_; }
+	// BFGS inverse-Hessian update form (PNOL_HINV_RANK2 default, PNOL_HINV_LITERAL = the reference's two products)
+	int hessianUpdateMode() const { return hinvMode_; }
+	void setHessianUpdateMode(int m) { hinvMode_ = m; }
+	// Jacobian mode for LM (PNOL_JAC_AUTO / PNOL_JAC_BLACKBOX)
+	int jacobianMode() const { return jacMode_; }
+	void setJacobianMode(int m) { jacMode_ = m; }
+	void check(int status) const;             // throws pnol::Error with pnol_last_error() text
+  private:
+	Runtime();
+	~Runtime();
+	pnol_ctx * ctx_;
+	bool owned_;
+	int poolWidth_;
+	pnol_stream_desc stream_;
+	bool haveStream_;
+	int hinvMode_;
+	int jacMode_;
+};
+
+// RAII device functor (the device twin an Objective / MultiObjective hands to the algorithms)
+class DeviceFunctor {
+  public:
+	DeviceFunctor() : f_(nullptr) {}
+	~DeviceFunctor() { release(); }
+	DeviceFunctor(const DeviceFunctor &) = delete;
+	DeviceFunctor & operator=(const DeviceFunctor &) = delete;
+	// (re)creates the functor when none exists yet
+	pnol_functor * get(int kind, const std::vector<double> & scalars = std::vector<double>(),
+	                   const std::vector<long long> & ints = std::vector<long long>(),
+	                   const std::vector<const double *> & columns = std::vector<const double *>(), long long m = 0);
+	void release();
+  private:
+	pnol_functor * f_;
+};
+
+// RAII device array of doubles
+class DeviceArray {
+  public:
+	DeviceArray() : p_(nullptr), n_(0) {}
+	explicit DeviceArray(size_t n) : p_(nullptr), n_(0) { resize(n); }
+	~DeviceArray() { free(); }
+	DeviceArray(const DeviceArray &) = delete;
+	DeviceArray & operator=(const DeviceArray &) = delete;
+	void resize(size_t n);
+	void free();
+	double * data() const { return p_; }
+	size_t size() const { return n_; }
+	void upload(const double * host, size_t n);
+	void download(double * host, size_t n) const;
+	void swap(DeviceArray & o) { double * p = p_; p_ = o.p_; o.p_ = p; size_t n = n_; n_ = o.n_; o.n_ = n; }
+  private:
+	double * p_;
+	size_t n_;
+};
+
+} // namespace pnol
+
+#endif

@@ -144,8 +144,8 @@ int pnol_fd_hessian(pnol_ctx * ctx, const pnol_functor * f, const double * x, co
 
 /* a13: alpha-pool evaluation for the pooled line searches. For k < npool with eval_ind[k] != 0
  * (eval_ind == NULL: all):  phi[k] = f(x + alpha[k] p)  and, when dphi != NULL,
- * dphi[k] = (f(x + (alpha[k] + dalpha) p) - phi[k]) / dalpha.  NaN/inf values are replaced by the 1e10
- * sentinel and *bad_out is set to the number of sentinels (Source/BFGS_bnd_linesearch_MPI_SW.cpp:599-699,
+ * dphi[k] = (f(x + (alpha[k] + dalpha) p) - phi[k]) / dalpha.  NaN/inf values of phi are replaced by the 1e10
+ * sentinel (the slope is computed from the raw phi and left as is) and *bad_out is set to the number of sentinels (Source/BFGS_bnd_linesearch_MPI_SW.cpp:599-699,
  * 703-734; Source/BFGS_with_linesearch_MPI.cpp:163-223). const_x/const_ind may be NULL (no active set). */
 int pnol_alpha_pool(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * p, int n,
                     const double * alpha, int npool, double dalpha, const unsigned char * eval_ind,

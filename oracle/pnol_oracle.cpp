@@ -365,9 +365,7 @@ void oracle_alpha_pool(int kind, const double * scalars, const long long * ints,
 		if (dphi) {
 			for (int i = 0; i < n; i++) Xt[i] = X[i] + (alpha[k] + dalpha) * p[i];
 			double ph2 = const_ind ? o_eval_recur(f, Xt.data(), constantX, const_ind, nfull) : o_scalar(f, Xt.data(), n);
-			double d = (ph2 - ph) / dalpha;
-			if (d != d || isinf(d)) { d = 1e10; nbad++; }
-			dphi[k] = d;
+			dphi[k] = (ph2 - ph) / dalpha;     // (:719-734) no sentinel on the slope
 		}
 		if (ph != ph || isinf(ph)) { ph = 1e10; nbad++; }
 		phi[k] = ph;
@@ -474,11 +472,11 @@ uint64_t oracle_ga_check_identical(double * Xpop, long long Npop, int n, const d
 // Outputs (all optional): Xpop_out (Npop x n sorted), F_out, per-generation parent indices of the LAST generation
 // run: cross_idx (Ncross x n), mut_idx (Nrand), elite_idx (NeliteMut x n); stream_pos_out.
 // Returns the number of generations completed (iter at exit), or -1 if the fractions are invalid (the reference
-// calls exit(0), :40-44).
+// calls exit(0), :40-44). stopAfter >= 0 ends the loop early with maxGenerations (hence the mutation schedule) unchanged.
 int oracle_ga(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
               double * X, const double * Xlb, const double * Xub, int Nparam, int Npop, int maxGenerations, double eliteFrac,
               double crossFrac, double eliteMutationFrac, double mutationSize, double eliteMutationSize,
-              double NstaticGenerations, const double * values, uint64_t n_values, uint64_t seed, double scale,
+              double NstaticGenerations, int stopAfter, const double * values, uint64_t n_values, uint64_t seed, double scale,
               double * f0_out, double * fOpt_out, double * Xpop_out, double * F_out, int * cross_idx, int * mut_idx,
               int * elite_idx, uint64_t * stream_pos_out)
 {
@@ -507,7 +505,8 @@ int oracle_ga(int kind, const double * scalars, const long long * ints, const do
 	double FbestPrev = F[0];
 	int Nstatic = 0;
 	int iter = 0;
-	while (iter < maxGenerations) {                             // :87
+	// stopAfter (test hook, not in the reference): leave the loop after that many completed generations (< 0: never)
+	while (iter < maxGenerations && (stopAfter < 0 || iter < stopAfter)) {   // :87
 		for (int k = 0; k < Npop; k++) fitness[k] = pow(F[Npop - 1] - F[k], 2);   // :101-104
 		double maxFitness = fitness[0];
 		for (int k = 0; k < Npop; k++) ind[k] = 1;

@@ -409,3 +409,103 @@ class Context:
     def dgemm_nn(self, A, B, Cm, M, N, K):
         self.check(self.lib.pnol_dgemm_nn(self.h, _ptr(A), _ptr(B), _ptr(Cm), int(M), int(N), int(K)))
         return Cm
+
+
+    # ---- genetic algorithm ----
+    def _stream_desc(self, stream):
+        d = StreamDesc()
+        keep = None
+        values = stream.get("values")
+        if values is not None:
+            keep = np.ascontiguousarray(values, dtype=np.float64)
+            d.values = keep.ctypes.data
+            d.n_values = keep.size
+        d.seed = int(stream.get("seed", 0))
+        d.scale = float(stream.get("scale", 1.0))
+        return d, keep
+
+    def ga_create(self, f, n, lb, ub, npop, maxgen, stream, elite_frac=0.1, cross_frac=0.3, elite_mut_frac=0.2, mut_size=0.5,
+                  elite_mut_size=0.01, nstatic=50.0):
+        prm = GaParams(int(npop), int(maxgen), elite_frac, cross_frac, elite_mut_frac, mut_size, elite_mut_size, float(nstatic))
+        sd, keep = self._stream_desc(stream)
+        lb, ub = _f64(lb), _f64(ub)
+        h = C.c_void_p()
+        self.check(self.lib.pnol_ga_create(self.h, f.handle, C.byref(prm), int(n), _ptr(lb), _ptr(ub), C.byref(sd), C.byref(h)))
+        return GA(self, h, int(npop), int(n), keep, f)
+
+    def ga_pop_sort(self, xpop, F):
+        xpop, F = _f64(xpop).copy(), _f64(F).copy()
+        self.check(self.lib.pnol_ga_pop_sort(self.h, _ptr(xpop), _ptr(F), C.c_longlong(xpop.shape[0]), int(xpop.shape[1])))
+        return xpop, F
+
+    def _ga_stage(self, fn, xpop, lb, ub, stream, pos):
+        xpop = _f64(xpop).copy()
+        lb, ub = _f64(lb), _f64(ub)
+        ind = np.zeros(xpop.shape[0], dtype=np.uint8)
+        sd, keep = self._stream_desc(stream)
+        p = C.c_uint64(pos)
+        self.check(fn(self.h, _ptr(xpop), C.c_longlong(xpop.shape[0]), int(xpop.shape[1]), _ptr(lb), _ptr(ub), _ptr(ind), C.byref(sd),
+                      C.byref(p)))
+        return xpop, ind, int(p.value)
+
+    def ga_check_bounds(self, xpop, lb, ub, stream, pos=0):
+        return self._ga_stage(self.lib.pnol_ga_check_bounds, xpop, lb, ub, stream, pos)
+
+    def ga_check_identical(self, xpop, lb, ub, stream, pos=0):
+        return self._ga_stage(self.lib.pnol_ga_check_identical, xpop, lb, ub, stream, pos)
+
+
+class GA:
+    """pnol_ga state machine (GeneticAlgorithmMPI::findMinBnd, one generation per call)."""
+
+    def __init__(self, ctx, handle, npop, n, keep, functor):
+        self.ctx, self.handle, self.npop, self.n, self._keep, self._f = ctx, handle, npop, n, keep, functor
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.pnol_ga_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, x0):
+        x0 = _f64(x0)
+        f0 = C.c_double()
+        self.ctx.check(self.ctx.lib.pnol_ga_init(self.handle, _ptr(x0), C.byref(f0)))
+        return f0.value
+
+    def generation(self):
+        self.ctx.check(self.ctx.lib.pnol_ga_generation(self.handle))
+
+    def status(self):
+        s = GaStatus()
+        self.ctx.check(self.ctx.lib.pnol_ga_status_get(self.handle, C.byref(s)))
+        return s
+
+    def population(self):
+        x = np.empty((self.npop, self.n))
+        F = np.empty(self.npop)
+        self.ctx.check(self.ctx.lib.pnol_ga_get_population(self.handle, _ptr(x), _ptr(F)))
+        return x, F
+
+    def indices(self):
+        s = self.status()
+        cross = np.zeros((max(s.n_cross, 1), self.n), dtype=np.int32)
+        mut = np.zeros(max(s.n_rand, 1), dtype=np.int32)
+        elite = np.zeros((max(s.n_elite_mut, 1), self.n), dtype=np.int32)
+        self.ctx.check(self.ctx.lib.pnol_ga_get_indices(self.handle, _ptr(cross), _ptr(mut), _ptr(elite)))
+        return cross, mut, elite
+
+    def run(self, x0, max_generations):
+        """findMinBnd: init + generations until the generation count or the static-generation stop."""
+        f0 = self.init(x0)
+        while True:
+            s = self.status()
+            if s.stopped or s.generation >= max_generations:
+                break
+            self.generation()
+        return f0

@@ -305,11 +305,7 @@ __global__ void alpha_pool_finish_kernel(const double * __restrict__ vals, int n
 	if (eval_ind && !eval_ind[k]) return;
 	double ph = vals[k];
 	int nbad = 0;
-	if (want_dphi) {
-		double d = (vals[npool + k] - ph) / dalpha;
-		if (d != d || isinf(d)) { d = 1e10; nbad++; }
-		dphi[k] = d;
-	}
+	if (want_dphi) dphi[k] = (vals[npool + k] - ph) / dalpha;   // slope keeps NaN/inf: the reference only guards phi
 	if (ph != ph || isinf(ph)) { ph = 1e10; nbad++; }
 	phi[k] = ph;
 	if (nbad) atomicAdd(bad, nbad);

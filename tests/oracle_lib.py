@@ -240,7 +240,7 @@ def ga_check_identical(xpop, lb, ub, stream, pos=0):
 
 
 def ga(f, x0, lb, ub, npop, maxgen, stream, elite_frac=0.1, cross_frac=0.3, elite_mut_frac=0.2, mut_size=0.5,
-       elite_mut_size=0.01, nstatic=50.0):
+       elite_mut_size=0.01, nstatic=50.0, stop_after=-1):
     X = f64(x0).copy()
     n = X.size
     lb, ub = f64(lb), f64(ub)
@@ -256,7 +256,7 @@ def ga(f, x0, lb, ub, npop, maxgen, stream, elite_frac=0.1, cross_frac=0.3, elit
     pos = C.c_uint64()
     it = lib().oracle_ga(*f.args(), _p(X), _p(lb), _p(ub), C.c_int(n), C.c_int(npop), C.c_int(maxgen), C.c_double(elite_frac),
                          C.c_double(cross_frac), C.c_double(elite_mut_frac), C.c_double(mut_size), C.c_double(elite_mut_size),
-                         C.c_double(nstatic), *_stream_args(stream), C.byref(f0), C.byref(fopt), _p(xpop), _p(F), _p(cross),
+                         C.c_double(nstatic), C.c_int(stop_after), *_stream_args(stream), C.byref(f0), C.byref(fopt), _p(xpop), _p(F), _p(cross),
                          _p(mut), _p(elite), C.byref(pos))
     return dict(iters=it, X=X, f0=f0.value, fOpt=fopt.value, xpop=xpop, F=F, cross_idx=cross, mut_idx=mut, elite_idx=elite,
                 stream_pos=int(pos.value), sizes=(nelite, nelmut, ncross, nrand))
