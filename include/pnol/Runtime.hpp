@@ -48,6 +48,10 @@ class Runtime {
 	// Jacobian mode for LM (PNOL_JAC_AUTO / PNOL_JAC_BLACKBOX)
 	int jacobianMode() const { return jacMode_; }
 	void setJacobianMode(int m) { jacMode_ = m; }
+	// LM: keep J^T J across a rejected step (X restored, so J is unchanged). The reference recomputes the identical J
+	// (Source/LevenbergMarquardtMPI.cpp:60 after :120-129); false reproduces that work, the results are the same.
+	bool jacobianCache() const { return jacCache_; }
+	void setJacobianCache(bool on) { jacCache_ = on; }
 	void check(int status) const;             // throws pnol::Error with pnol_last_error() text
   private:
 	Runtime();
@@ -59,6 +63,7 @@ class Runtime {
 	bool haveStream_;
 	int hinvMode_;
 	int jacMode_;
+	bool jacCache_;
 };
 
 // RAII device functor (the device twin an Objective / MultiObjective hands to the algorithms)

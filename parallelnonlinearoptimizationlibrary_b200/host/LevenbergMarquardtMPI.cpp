@@ -53,7 +53,7 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 			Xdev.upload( X.data(), Nparam );
 			rt.check( pnol_fd_jacobian( ctx, f, Xdev.data(), dXdev.data(), Nparam, J.data(), nullptr, rt.jacobianMode() ) );
 			rt.check( pnol_lm_normal_eq( ctx, J.data(), F.data(), Ndata, Nparam, lambda, JTJ.data(), A.data(), rhs.data() ) );
-			jacobianCurrent = true;
+			jacobianCurrent = rt.jacobianCache();
 		}
 		else
 		{

@@ -6,11 +6,13 @@
 
 namespace pnol {
 
-Runtime::Runtime() : ctx_(nullptr), owned_(false), poolWidth_(8), haveStream_(false), hinvMode_(PNOL_HINV_RANK2), jacMode_(PNOL_JAC_AUTO)
+Runtime::Runtime() : ctx_(nullptr), owned_(false), poolWidth_(8), haveStream_(false), hinvMode_(PNOL_HINV_RANK2), jacMode_(PNOL_JAC_AUTO), jacCache_(true)
 {
 	std::memset(&stream_, 0, sizeof stream_);
 	const char * pw = std::getenv("PNOL_POOL_WIDTH");
 	if (pw && std::atoi(pw) > 0) poolWidth_ = std::atoi(pw);
+	const char * jc = std::getenv("PNOL_LM_JACOBIAN_CACHE");
+	if (jc) jacCache_ = std::atoi(jc) != 0;
 }
 
 Runtime::~Runtime() { reset(); }

@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement (oracle/pnol_oracle.cpp) against the committed outputs of the VERBATIM reference
+(tests/golden/ref_golden.npz, made by tests/golden/make_golden.py from /root/reference/Source + oracle/shim). Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+KIND = {"rosenbrock": (1, ()), "booth": (3, ()), "goldstein": (4, ()), "powerprod3": (2, (3,)), "powerprod2": (2, (2,)), "rastrigin": (5, ())}
+
+
+def g(case, name):
+    return G["%s/%s" % (case, name)]
+
+
+@pytest.mark.parametrize("spec,n", [("rosenbrock", 5), ("rosenbrock", 40), ("booth", 2), ("goldstein", 2), ("powerprod3", 5), ("rastrigin", 12)])
+def test_fd_gradient_hessian(spec, n):
+    case = "fdgrad_%s_%d" % (spec, n)
+    kind, ints = KIND[spec]
+    f = O.OFunctor(kind, (), ints)
+    gr, f0 = O.fd_gradient(f, g(case, "x"), g(case, "dx"))
+    assert np.array_equal(gr, g(case, "g")) and np.array_equal(gr, g(case, "g_mpi")) and f0 == g(case, "f")[0]
+    if n <= 12:
+        assert np.array_equal(O.fd_hessian(f, g(case, "x"), g(case, "dxh")), g(case, "B"))
+
+
+def test_reference_known_answers():
+    # SURVEY.md Appendix C; testGradientEvaluation (Source/Examples.cpp:512-540) uses libm pow(x,3): FD-noise level only
+    assert g("testGradientEvaluation", "g")[0] == 27.000008998356861
+    gr, _ = O.fd_gradient(O.OFunctor(2, (), (3,)), np.full(5, 3.0), np.full(5, 1e-6))
+    assert np.allclose(gr, g("testGradientEvaluation", "g"), rtol=1e-7)
+    assert np.allclose(g("testLMExpMPI", "X"), [10.2, 0.4, 0.1], rtol=1e-8)
+    assert np.allclose(g("testLMCubicLinearCoef", "X"), [0.3, 1.1, -4.3, 7.3], rtol=1e-10)
+    assert abs(g("testBFGS", "fOpt")[0] - 3.9308394359855199) < 1e-12
+
+
+def test_recur():
+    c = "recur_rosenbrock_8"
+    gr, f0 = O.fd_gradient_recur(O.OFunctor(1), g(c, "xr"), np.full(7, 1e-6), g(c, "constx"), g(c, "ind"))
+    assert np.array_equal(gr, g(c, "g")) and np.array_equal(gr, g(c, "g_mpi")) and f0 == g(c, "f")[0]
+
+
+@pytest.mark.parametrize("K", [4, 32, 128])
+def test_fd_jacobian(K):
+    c = "fdjac_lorentz_K%d" % K
+    t = g(c, "t")
+    f = O.OFunctor(103, (float(g(c, "w")),), (), (t, g(c, "y")), t.size)
+    J, F = O.fd_jacobian(f, g(c, "x"), g(c, "dx"))
+    assert np.array_equal(J, g(c, "J")) and np.array_equal(J, g(c, "J_mpi")) and np.array_equal(F, g(c, "F"))
+
+
+@pytest.mark.parametrize("K", [8, 16])
+def test_lm(K):
+    c = "lm_lorentz_K%d" % K
+    t = g(c, "t")
+    f = O.OFunctor(103, (float(g(c, "w")),), (), (t, g(c, "y")), t.size)
+    w = O.lm(f, g(c, "x0"), 0.001, 10.0, 1e-7, int(g(c, "iters")), 0.0)
+    assert np.array_equal(w["X"], g(c, "X")) and np.array_equal(w["F"], g(c, "F")) and np.array_equal(w["F0"], g(c, "F0"))
+
+
+@pytest.mark.parametrize("n", [3, 17, 64])
+def test_update_hinv(n):
+    c = "updhinv_%d" % n
+    assert np.array_equal(O.update_hinv(g(c, "D"), g(c, "g"), g(c, "s")), g(c, "Dnew"))
+
+
+def test_box():
+    assert O.compute_alpha_bnd(g("box", "xin"), g("box", "lb"), g("box", "ub"), g("box", "p")) == g("box", "alphabnd")[0]
+    xw, cnt = O.check_box_bounds(g("box", "x"), g("box", "lb"), g("box", "ub"))
+    assert cnt > 0 and np.array_equal(xw, g("box", "Xfixed"))
+
+
+@pytest.mark.parametrize("spec", ["powerprod2", "rastrigin", "rosenbrock"])
+def test_ga(spec):
+    c = "ga_%s" % spec
+    kind, ints = KIND[spec]
+    w = O.ga(O.OFunctor(kind, (), ints), g(c, "x0"), g(c, "lb"), g(c, "ub"), int(g(c, "npop")), int(g(c, "gens")),
+             dict(seed=int(g(c, "seed")), scale=float(g(c, "scale"))))
+    assert np.array_equal(w["X"], g(c, "X")) and w["fOpt"] == g(c, "fOpt")[0] and w["f0"] == g(c, "f0")[0]
+    assert w["stream_pos"] == int(g(c, "stream_pos")[0])
+
+
+def test_ga_stages():
+    c = "ga_stages"
+    Xs, Fs = O.ga_pop_sort(g(c, "X"), g(c, "F"))
+    assert np.array_equal(Xs, g(c, "sortedX")) and np.array_equal(Fs, g(c, "sortedF"))
+    Xb, ib, pb = O.ga_check_bounds(g(c, "X"), g(c, "lb"), g(c, "ub"), dict(seed=5, scale=1.0))
+    assert np.array_equal(Xb, g(c, "boundsX")) and np.array_equal(ib, g(c, "boundsInd")) and pb == int(g(c, "boundsPos")[0])
+    Xi, ii, pi = O.ga_check_identical(g(c, "X"), g(c, "lb"), g(c, "ub"), dict(seed=5, scale=1.0))
+    assert np.array_equal(Xi, g(c, "identX")) and np.array_equal(ii, g(c, "identInd")) and pi == int(g(c, "identPos")[0])
