@@ -81,6 +81,8 @@ template <class R> class FunctorMultiObjective : public MultiObjective {
 		for( size_t c = 0; c < cols.size(); c++ ) ptrs.push_back( cols[c].data() );
 		return dev.get( R::kKind, vector<double>( P.scalars, P.scalars + PNOL_MAX_SCALARS ), vector<long long>( P.ints, P.ints + PNOL_MAX_INTS ), ptrs, P.m );
 	}
+	// drop the device twin (the data columns are uploaded again by the next deviceFunctor() call)
+	void releaseDeviceFunctor(){ dev.release(); }
 	int getDataSize(){ return (int) P.m; }
 };
 }

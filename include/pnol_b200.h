@@ -277,6 +277,8 @@ int pnol_timer_reset(pnol_ctx * ctx);
 /* self test: number of (x, d) pairs out of `pairs` pseudo-random / adversarial ones for which the reciprocal-based
  * exact division of the Jacobian kernels (csrc/exact_div.cuh) differs from x / d. Must return 0 mismatches. */
 int pnol_selftest_exact_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches);
+/* the same for the branch-free cores the speculative row kernels use (div_core, div_exact_core), over their validity range */
+int pnol_selftest_fast_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches);
 
 #ifdef __cplusplus
 }

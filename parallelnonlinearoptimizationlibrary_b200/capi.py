@@ -6,6 +6,7 @@ __graft_entry__ as g; g.build()"` or `make`), and every compute call fails with 
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -87,7 +88,7 @@ EXPORTS = [
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
     "pnol_ga_check_identical", "pnol_measure_dmma_peak", "pnol_measure_copy_bandwidth", "pnol_timer_enable",
-    "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div",
+    "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div", "pnol_selftest_fast_div",
 ]
 
 _lib = None
@@ -156,11 +157,14 @@ def _len(a, n):
 class Functor:
     def __init__(self, ctx, handle, kind, m, keep):
         self.ctx, self.handle, self.kind, self.m, self._keep = ctx, handle, kind, m, keep
+        ctx._children.add(self)
 
     def close(self):
-        if self.handle:
+        # a functor must die before its context (pnol_functor_destroy frees on the context's stream): Context.close()
+        # closes its children first, and a functor that outlives a closed context only drops its handle
+        if self.handle and self.ctx.h:
             self.ctx.lib.pnol_functor_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -181,9 +185,12 @@ class Context:
                             "fallback" % (device, ERR_NAMES.get(st, st)))
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.close()
             self.lib.pnol_ctx_destroy(self.h)
             self.h = None
 
@@ -259,6 +266,11 @@ class Context:
     def selftest_exact_div(self, pairs, seed=1):
         bad = C.c_ulonglong()
         self.check(self.lib.pnol_selftest_exact_div(self.h, C.c_longlong(pairs), C.c_ulonglong(seed), C.byref(bad)))
+        return int(bad.value)
+
+    def selftest_fast_div(self, pairs, seed=1):
+        bad = C.c_ulonglong()
+        self.check(self.lib.pnol_selftest_fast_div(self.h, C.c_longlong(pairs), C.c_ulonglong(seed), C.byref(bad)))
         return int(bad.value)
 
     # ---- communicator ----
@@ -460,11 +472,12 @@ class GA:
 
     def __init__(self, ctx, handle, npop, n, keep, functor):
         self.ctx, self.handle, self.npop, self.n, self._keep, self._f = ctx, handle, npop, n, keep, functor
+        ctx._children.add(self)
 
     def close(self):
-        if self.handle:
+        if self.handle and self.ctx.h:
             self.ctx.lib.pnol_ga_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:

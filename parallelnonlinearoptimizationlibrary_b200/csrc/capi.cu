@@ -88,7 +88,11 @@ extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 	timers_collect(ctx);
 	comm_destroy(ctx);
 	for (int s = 0; s < 4; s++) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+	if (ctx->syrk_plan) cudaFree(ctx->syrk_plan);
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	cudaStreamSynchronize(ctx->stream);
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -107,16 +111,17 @@ extern "C" int pnol_ctx_sync(pnol_ctx * ctx)
 extern "C" int pnol_malloc(pnol_ctx * ctx, void ** dev_ptr, size_t bytes)
 {
 	if (!ctx || !dev_ptr) return PNOL_ERR_INVALID;
+	// stream-ordered pool with an unlimited release threshold (pnol_ctx_create): a freed block is reused by the next
+	// request of that size without going back to the driver -- findMin allocates and frees its J / F work space per call
 	PNOL_CUDA(ctx, cudaSetDevice(ctx->device));
-	PNOL_CUDA(ctx, cudaMalloc(dev_ptr, bytes ? bytes : 1));
+	PNOL_CUDA(ctx, cudaMallocAsync(dev_ptr, bytes ? bytes : 1, ctx->stream));
 	return PNOL_OK;
 }
 extern "C" int pnol_free(pnol_ctx * ctx, void * dev_ptr)
 {
 	if (!ctx) return PNOL_ERR_INVALID;
 	if (!dev_ptr) return PNOL_OK;
-	PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	PNOL_CUDA(ctx, cudaFree(dev_ptr));
+	PNOL_CUDA(ctx, cudaFreeAsync(dev_ptr, ctx->stream));
 	return PNOL_OK;
 }
 extern "C" int pnol_memcpy(pnol_ctx * ctx, void * dst, const void * src, size_t bytes)
@@ -195,7 +200,7 @@ extern "C" int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * des
 		if (is_device_ptr(desc->columns[c])) { f->params.col[c] = desc->columns[c]; continue; }
 		void * d = nullptr;
 		size_t bytes = (size_t) (desc->m > 0 ? desc->m : 1) * sizeof(double);
-		cudaError_t e = cudaMalloc(&d, bytes);
+		cudaError_t e = cudaMallocAsync(&d, bytes, ctx->stream);
 		if (e == cudaSuccess && desc->m > 0)
 			e = cudaMemcpyAsync(d, desc->columns[c], (size_t) desc->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
 		if (e != cudaSuccess) {
@@ -215,8 +220,7 @@ extern "C" int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * des
 extern "C" void pnol_functor_destroy(pnol_functor * f)
 {
 	if (!f) return;
-	cudaStreamSynchronize(f->ctx->stream);
-	for (int c = 0; c < PNOL_MAX_COLUMNS; c++) if (f->owned[c]) cudaFree(f->owned[c]);
+	for (int c = 0; c < PNOL_MAX_COLUMNS; c++) if (f->owned[c]) cudaFreeAsync(f->owned[c], f->ctx->stream);
 	delete f;
 }
 
@@ -672,6 +676,57 @@ extern "C" int pnol_selftest_exact_div(pnol_ctx * ctx, long long pairs, unsigned
 	const int blocks = ctx->sm_count * 8, threads = 256;
 	long long per_thread = (pairs + (long long) blocks * threads - 1) / ((long long) blocks * threads);
 	PNOL_LAUNCH(ctx, exact_div_selftest_kernel, blocks, threads, 0, seed, per_thread, bad);
+	PNOL_CUDA(ctx, cudaMemcpyAsync(mismatches, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	return finish(ctx);
+}
+
+// self test of the branch-free division cores: pairs (a, b) inside the validity predicates for which div_core(a, b) differs
+// from a / b, plus pairs (x, d) with div_exact_x_ok(x) for which div_exact_core differs from x / d (must be 0)
+__global__ void fast_div_selftest_kernel(unsigned long long seed, long long per_thread, unsigned long long * __restrict__ bad)
+{
+	unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (1 + (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x);
+	unsigned long long nbad = 0;
+	for (long long i = 0; i < per_thread; i++) {
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		unsigned long long mb = s;
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		unsigned long long ma = s;
+		s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+		const int mode = (int) (i & 7);
+		if (mode == 1) mb |= 0xFFFFFFFFFF000ULL;
+		if (mode == 2) mb &= 0xFFFULL;
+		if (mode == 3) ma |= 0xFFFFFFFFFFFF0ULL;
+		if (mode == 4) ma &= 0xFFULL;
+		if (mode == 5) mb = 0xFFFFFFFFFFFFFULL - (s & 0xF);
+		int eb = (int) ((s >> 8) % 60) - 30, ea = (int) ((s >> 20) % 80) - 40;
+		if (mode == 6) { eb = (int) ((s >> 8) % 798) - 399; ea = (int) ((s >> 20) % 798) - 399; }     // the whole validity range
+		double b = __longlong_as_double((long long) (((unsigned long long) (eb + 1023) << 52) | (mb & 0xFFFFFFFFFFFFFULL)));
+		double a = __longlong_as_double((long long) (((unsigned long long) (ea + 1023) << 52) | (ma & 0xFFFFFFFFFFFFFULL)));
+		if (mode == 7 && (i & 8)) a = (i & 16) ? 0.0 : -0.0;
+		if (s & 1) a = -a;
+		if (s & 2) b = -b;
+		if (pnol::div_den_ok(b) && pnol::div_num_ok(a)) {
+			double got = pnol::div_core(a, b), want = a / b;
+			if (__double_as_longlong(got) != __double_as_longlong(want)) nbad++;
+		}
+		pnol::RecipDiv rd = pnol::make_recip(b);
+		if (rd.r != 0.0 && pnol::div_exact_x_ok(a)) {
+			double got = pnol::div_exact_core(a, rd), want = a / b;
+			if (__double_as_longlong(got) != __double_as_longlong(want)) nbad++;
+		}
+	}
+	if (nbad) atomicAdd(bad, nbad);
+}
+
+extern "C" int pnol_selftest_fast_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches)
+{
+	if (!ctx || !mismatches) return PNOL_ERR_INVALID;
+	PNOL_CHECK(ws_reserve(ctx, 3, 64));
+	unsigned long long * bad = (unsigned long long *) ctx->ws[3];
+	PNOL_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(unsigned long long), ctx->stream));
+	const int blocks = ctx->sm_count * 8, threads = 256;
+	long long per_thread = (pairs + (long long) blocks * threads - 1) / ((long long) blocks * threads);
+	PNOL_LAUNCH(ctx, fast_div_selftest_kernel, blocks, threads, 0, seed, per_thread, bad);
 	PNOL_CUDA(ctx, cudaMemcpyAsync(mismatches, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	return finish(ctx);
 }

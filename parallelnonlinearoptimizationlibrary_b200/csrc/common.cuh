@@ -35,6 +35,12 @@ struct pnol_ctx {
 	double * pinned = nullptr;
 	size_t pinned_doubles = 0;
 
+	// SYRK work plan of the last (m, n) shape (device copy of the descriptor tables; see launch_syrk)
+	void * syrk_plan = nullptr;
+	size_t syrk_plan_bytes = 0;
+	long long syrk_plan_m = -1;
+	int syrk_plan_n = -1;
+
 	// communicator
 	ncclComm * comm = nullptr;
 	int rank = 0;

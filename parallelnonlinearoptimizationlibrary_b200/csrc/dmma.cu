@@ -287,18 +287,29 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	size_t bytes_tiles = (size_t) total_slots * kBT * kBT * sizeof(double);
 	size_t bytes_rhs = (size_t) total_slots * kBT * sizeof(double);
 	size_t off_roles = (bytes_work + 255) & ~(size_t) 255;
-	size_t off_tiles = (off_roles + bytes_roles + 255) & ~(size_t) 255;
-	size_t off_rhs = off_tiles + bytes_tiles;
-	PNOL_CHECK(ws_reserve(ctx, 0, off_rhs + bytes_rhs));
-	unsigned char * ws = (unsigned char *) ctx->ws[0];
-	// the descriptor tables are tiny; stage them through one pageable->device copy each (stream ordered)
-	std::vector<int> roles(2 * nroles);
-	for (int r = 0; r < nroles; r++) { roles[r] = slot0[r]; roles[nroles + r] = nslots[r]; }
-	PNOL_CUDA(ctx, cudaMemcpyAsync(ws, work.data(), bytes_work, cudaMemcpyHostToDevice, ctx->stream));
-	PNOL_CUDA(ctx, cudaMemcpyAsync(ws + off_roles, roles.data(), bytes_roles, cudaMemcpyHostToDevice, ctx->stream));
-	PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors die at scope exit
-	double * part_tiles = (double *) (ws + off_tiles);
-	double * part_rhs = (double *) (ws + off_rhs);
+	PNOL_CHECK(ws_reserve(ctx, 0, bytes_tiles + bytes_rhs));
+	// the descriptor tables depend on (m, n) only: upload them once per shape (an LM run repeats one shape), so that the
+	// launch does not have to wait for the stream to drain on every call
+	if (ctx->syrk_plan_m != m || ctx->syrk_plan_n != n) {
+		size_t need = off_roles + bytes_roles;
+		if (need > ctx->syrk_plan_bytes) {
+			PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->syrk_plan) PNOL_CUDA(ctx, cudaFree(ctx->syrk_plan));
+			ctx->syrk_plan = nullptr; ctx->syrk_plan_bytes = 0;
+			PNOL_CUDA(ctx, cudaMalloc(&ctx->syrk_plan, need + 4096));
+			ctx->syrk_plan_bytes = need + 4096;
+		}
+		std::vector<int> roles(2 * nroles);
+		for (int r = 0; r < nroles; r++) { roles[r] = slot0[r]; roles[nroles + r] = nslots[r]; }
+		unsigned char * plan = (unsigned char *) ctx->syrk_plan;
+		PNOL_CUDA(ctx, cudaMemcpyAsync(plan, work.data(), bytes_work, cudaMemcpyHostToDevice, ctx->stream));
+		PNOL_CUDA(ctx, cudaMemcpyAsync(plan + off_roles, roles.data(), bytes_roles, cudaMemcpyHostToDevice, ctx->stream));
+		PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors die at scope exit
+		ctx->syrk_plan_m = m; ctx->syrk_plan_n = n;
+	}
+	unsigned char * ws = (unsigned char *) ctx->syrk_plan;
+	double * part_tiles = (double *) ctx->ws[0];
+	double * part_rhs = (double *) ((unsigned char *) ctx->ws[0] + bytes_tiles);
 	PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));
 
 	const bool vec16 = (n % 2 == 0) && ((((size_t) J) & 15) == 0);

@@ -86,6 +86,44 @@ int pnolhost_lm_lorentz( const double * t, const double * y, long long m, double
 	} );
 }
 
+// The same through a problem handle, the way a C++ user holds it: the objective (with its host data) is built once, every run
+// is `lm.setObjPtr(obj); lm.setParams(...); lm.findMin(X, F0, F)` on caller-lifetime vectors -- no copies added by this C face.
+// fresh_device_twin != 0 drops the objective's device functor first, so that the upload of the data columns happens inside
+// this findMin (what a first call on a new objective pays).
+struct LMProblem {
+	LorentzSumObjective obj;
+	vector<double> F0, F;
+	LMProblem( const vector<double> & t, const vector<double> & y, double w ) : obj( t, y, w ), F0( t.size() ), F( t.size() ) {}
+};
+
+void * pnolhost_lm_problem_create( const double * t, const double * y, long long m, double w )
+{
+	void * out = nullptr;
+	guarded( [&] { vector<double> tv( t, t + m ), yv( y, y + m ); out = new LMProblem( tv, yv, w ); } );
+	return out;
+}
+
+void pnolhost_lm_problem_destroy( void * prob ) { guarded( [&] { delete static_cast<LMProblem *>( prob ); } ); }
+
+int pnolhost_lm_problem_run( void * prob, double * X, int n, double lambda0, double factor, double dxgrad, double maxiter, double xmindiff,
+		int serial, int fresh_device_twin, double * report, const double ** F0, const double ** F )
+{
+	return guarded( [&] {
+		CoutSilencer quiet( true );
+		LMProblem * p = static_cast<LMProblem *>( prob );
+		if( !p ) throw pnol::Error( PNOL_ERR_INVALID, "null LM problem" );
+		if( fresh_device_twin ) p->obj.releaseDeviceFunctor();
+		vector<double> Xv( X, X + n );
+		pnol::LMReport rep;
+		if( serial ) { LevMarq lm; lm.setObjPtr( p->obj ); lm.setParams( lambda0, factor, dxgrad, maxiter, xmindiff, -1 ); lm.findMin( Xv, p->F0, p->F ); rep = lm.lastReport(); }
+		else { LevMarqMPI lm; lm.setObjPtr( p->obj ); lm.setParams( lambda0, factor, dxgrad, maxiter, xmindiff, -1 ); lm.findMin( Xv, p->F0, p->F ); rep = lm.lastReport(); }
+		memcpy( X, Xv.data(), n*sizeof(double) );
+		if( F0 ) *F0 = p->F0.data();
+		if( F ) *F = p->F.data();
+		if( report ) { report[0] = rep.iterations; report[1] = rep.accepted; report[2] = rep.rejected; report[3] = rep.chiSq; report[4] = rep.lambda; report[5] = rep.xdiff2Norm; }
+	} );
+}
+
 // LM on the reference's own fixtures: name = "expcurve" | "cubic" (m = 100)
 int pnolhost_lm_example( const char * name, double * X, int n, double lambda0, double factor, double dxgrad, double maxiter, double xmindiff,
 		double * F0, double * F, double * report )

@@ -24,6 +24,9 @@ def lib():
     h.pnolhost_obj_eval.restype = C.c_double
     h.pnolhost_compute_alpha_bnd.restype = C.c_double
     h.pnolhost_attach.argtypes = [C.c_void_p]
+    h.pnolhost_lm_problem_create.restype = C.c_void_p
+    h.pnolhost_lm_problem_destroy.argtypes = [C.c_void_p]
+    h.pnolhost_lm_problem_destroy.restype = None
     _lib = h
     return h
 
@@ -100,6 +103,40 @@ def lm_lorentz(t, y, w, x0, lambda0=0.001, factor=10.0, dxgrad=1e-7, maxiter=10,
                                      _p(rep)))
     return dict(X=Xv, F0=F0, F=F, iterations=int(rep[0]), accepted=int(rep[1]), rejected=int(rep[2]), chiSq=rep[3], lam=rep[4],
                 xdiff2Norm=rep[5])
+
+
+class LMProblem:
+    """A LorentzSumObjective held the way a C++ user holds it (built once from host data); run() is
+    `LevMarqMPI lm; lm.setObjPtr(obj); lm.setParams(...); lm.findMin(X, F0, F)` on vectors that live with the problem."""
+
+    def __init__(self, t, y, w):
+        t, y = _f64(t), _f64(y)
+        self.m = t.size
+        self.h = lib().pnolhost_lm_problem_create(_p(t), _p(y), C.c_longlong(self.m), C.c_double(w))
+        if not self.h:
+            raise capi.PnolError("pnolhost_lm_problem_create failed: %s" % lib().pnolhost_last_error().decode())
+
+    def run(self, x0, lambda0=0.001, factor=10.0, dxgrad=1e-7, maxiter=10, xmindiff=0.0, serial=False, fresh_device_twin=False):
+        Xv = _f64(x0).copy()
+        rep = np.zeros(6)
+        pF0, pF = C.c_void_p(), C.c_void_p()
+        _check(lib().pnolhost_lm_problem_run(C.c_void_p(self.h), _p(Xv), Xv.size, C.c_double(lambda0), C.c_double(factor), C.c_double(dxgrad),
+                                             C.c_double(maxiter), C.c_double(xmindiff), int(bool(serial)), int(bool(fresh_device_twin)), _p(rep),
+                                             C.byref(pF0), C.byref(pF)))
+        view = lambda p: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.m,))   # noqa: E731
+        return dict(X=Xv, F0=view(pF0), F=view(pF), iterations=int(rep[0]), accepted=int(rep[1]), rejected=int(rep[2]), chiSq=rep[3],
+                    lam=rep[4], xdiff2Norm=rep[5])
+
+    def close(self):
+        if self.h:
+            lib().pnolhost_lm_problem_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def lm_example(name, x0, lambda0=0.001, factor=10.0, dxgrad=1e-6, maxiter=100, xmindiff=1e-6, m=100):

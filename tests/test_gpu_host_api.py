@@ -103,11 +103,11 @@ def test_bfgs_cfg1(host, iters, mode):
     c = "bfgs_cfg1_it%d" % iters
     assert r["f0"] == g(c, "f0")[0]
     tx, tf = tol(c)
-    assert rel(r["X"], g(c, "X")) < tx
     if iters == 5:
-        assert abs(r["fOpt"] - g(c, "fOpt")[0]) <= tf * abs(g(c, "fOpt")[0])
+        assert rel(r["X"], g(c, "X")) < tx and abs(r["fOpt"] - g(c, "fOpt")[0]) <= tf * abs(g(c, "fOpt")[0])
     else:
-        assert np.allclose(r["X"], np.ones(10), atol=2e-5) and r["fOpt"] < 1e-7     # converged: f ~ 1e-9 is rounding level
+        # run to convergence: both stop on the optimiser's own xMinDiff = 1e-5 test, so that is the agreement to ask for
+        assert rel(r["X"], g(c, "X")) < 1e-5 and r["fOpt"] < 1e-7 and g(c, "fOpt")[0] < 1e-7
 
 
 def test_bfgs_reference_example(host):
@@ -137,7 +137,8 @@ def test_bfgs_bnd_sw_reference_example(host, P):
     p[10] = 200
     r = host.bfgs("bfgs_bnd_sw", "rosenbrock", g(c, "x0"), p, g(c, "lb"), g(c, "ub"), pool_width=P)
     assert r["f0"] == g(c, "f0")[0]
-    assert np.allclose(r["X"], g(c, "X"), rtol=1e-6) and r["fOpt"] < 1e-7
+    # run to convergence (stops on xMinDiff = 1e-5): agreement to the optimiser's own stop tolerance
+    assert rel(r["X"], g(c, "X")) < 1e-5 and r["fOpt"] < 1e-7
 
 
 @pytest.mark.parametrize("iters", [3, 20])
@@ -164,3 +165,15 @@ def test_genetic_algorithm_bit_exact(host, spec, obj, serial):
 def test_box_helpers(host):
     assert host.compute_alpha_bnd(g("box", "xin"), g("box", "lb"), g("box", "ub"), g("box", "p")) == g("box", "alphabnd")[0]
     assert np.array_equal(host.check_box_bounds(g("box", "x"), g("box", "lb"), g("box", "ub")), g("box", "Xfixed"))
+
+
+def test_lm_problem_handle_matches_one_shot_call(host):
+    c = "lm_lorentz_K8"
+    prob = host.LMProblem(g(c, "t"), g(c, "y"), float(g(c, "w")))
+    a = prob.run(g(c, "x0"), 0.001, 10.0, 1e-7, int(g(c, "iters")), 0.0, fresh_device_twin=True)
+    Xa, Fa = a["X"].copy(), a["F"].copy()
+    b = prob.run(g(c, "x0"), 0.001, 10.0, 1e-7, int(g(c, "iters")), 0.0, fresh_device_twin=False)   # device twin reused
+    one = host.lm_lorentz(g(c, "t"), g(c, "y"), float(g(c, "w")), g(c, "x0"), 0.001, 10.0, 1e-7, int(g(c, "iters")), 0.0)
+    assert np.array_equal(Xa, b["X"]) and np.array_equal(Xa, one["X"]) and np.array_equal(Fa, one["F"])
+    assert np.array_equal(b["F0"], g(c, "F0")) and rel(Xa, g(c, "X")) < RTOL
+    prob.close()

@@ -129,7 +129,7 @@ def test_alpha_pool(ctx):
     phi, dphi, bad = ctx.alpha_pool(f, x, p, alpha, 1e-6)
     phiw, dphiw, badw = O.alpha_pool(of, x, p, alpha, 1e-6)
     assert bad == badw and bad > 0
-    assert np.array_equal(phi, phiw) and np.array_equal(dphi, dphiw)
+    assert np.array_equal(phi, phiw) and np.array_equal(dphi, dphiw, equal_nan=True)
     # with an evaluation mask and an active set
     ind = np.zeros(n + 5, dtype=np.uint8)
     ind[[2, 9, 30, 31, 54]] = 1
@@ -327,3 +327,29 @@ def test_exact_division_by_invariant_divisor(ctx):
     # the FD quotient (FdX - F)/dX is computed with a hoisted reciprocal + two FMA corrections; it must return the
     # bits of the IEEE division for every input (random, all-ones / near-power-of-two significands, zeros, inf, nan)
     assert ctx.selftest_exact_div(200_000_000, seed=7) == 0
+
+
+def test_branch_free_division_cores(ctx):
+    # csrc/exact_div.cuh: div_core / div_exact_core == IEEE `/` over their validity range (4e8 pairs incl. adversarial significands)
+    assert ctx.selftest_fast_div(200_000_000, seed=11) == 0
+    assert ctx.selftest_fast_div(200_000_000, seed=12345) == 0
+
+
+def test_jacobian_rows_outside_the_fast_range_fall_back(ctx):
+    # operands at the exponent extremes, inf and NaN make the speculative pass fail its predicate; the rows are recomputed with `/`
+    K, m = 32, 257
+    rng = np.random.default_rng(3)
+    t = rng.uniform(0, 5, m)
+    y = rng.uniform(0, 2, m)
+    t[5], t[40], t[41], y[77] = 1e200, np.inf, np.nan, 1e-320
+    x = np.empty(2 * K)
+    x[0::2], x[1::2] = rng.uniform(0.5, 1.5, K), np.linspace(0, 5, K)
+    x[6], x[10] = 1e-310, 1e305
+    dx = np.full(2 * K, 1e-7)
+    f = ctx.functor(capi.F_LORENTZ_SUM, (4.0,), (), (t, y), m)
+    of = O.OFunctor(capi.F_LORENTZ_SUM, (4.0,), (), (t, y), m)
+    J, F = ctx.fd_jacobian(f, x, dx)
+    Jw, Fw = O.fd_jacobian(of, x, dx)
+    assert np.array_equal(F, Fw, equal_nan=True) and np.array_equal(J, Jw, equal_nan=True)
+    Fr, _ = ctx.residual_eval(f, x)
+    assert np.array_equal(Fr, Fw, equal_nan=True)
