@@ -18,7 +18,12 @@ CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS))
 HOST_SRCS := $(wildcard $(HOSTSRC)/*.cpp)
 HOST_OBJS := $(patsubst $(HOSTSRC)/%.cpp,$(BUILD)/host_%.o,$(HOST_SRCS))
 
-all: $(LIBDIR)/libpnol_b200.so $(LIBDIR)/libpnol_b200_host.so oracle
+all: $(LIBDIR)/libpnol_b200.so $(LIBDIR)/libpnol_b200_host.so oracle ubench
+
+# tuning aid (FP64 pipe microbenchmark), not part of the library
+ubench: tools/ubench/fp64_ubench
+tools/ubench/fp64_ubench: tools/ubench/fp64_ubench.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -o $@ $<
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h) $(wildcard include/pnol/*)
 	@mkdir -p $(BUILD)
@@ -44,4 +49,4 @@ ref:
 clean:
 	rm -rf $(BUILD) $(LIBDIR)/*.so oracle/*.so oracle/_ref
 
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref clean ubench

@@ -219,7 +219,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -463,7 +463,7 @@ def run_ours(args):
             "cpu_baseline": cb, "secondary": ga,
             "clocks": sampler.summary(windows) if sampler else None,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     launch.barrier()
     e2e_prob.close()
     hostapi.detach()
@@ -477,7 +477,26 @@ def run_ours(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: route everything libraries print to fd 1 (NCCL's version banner, torchrun
+    notices, the reference's own prints) to stderr and keep a private duplicate of stdout for that line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
