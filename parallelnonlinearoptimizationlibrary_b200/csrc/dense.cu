@@ -32,172 +32,240 @@ int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// a9: SPD solve by blocked Cholesky in ONE CTA (n <= 704). Replaces luSolve (LevenbergMarquardtMPI.cpp:88).
-// The factor lives in a global n x n scratch (L2 resident); the 32-wide diagonal block and the panel below it
-// are staged in shared memory.
+// a9: SPD solve  A x = b  by right-looking blocked Cholesky on ONE thread-block cluster of 8 CTAs.
+// Replaces luSolve (Source/LevenbergMarquardtMPI.cpp:88).
+//
+// The work is 5.6 MFLOP at n = 256 -- nothing; the cost is the length of the dependency chain. The first version ran in
+// one CTA (0.56 ms: a 30 us serial rank-1 loop per diagonal block and read-modify-write round trips to L2 in the trailing
+// update). Here:
+//   * the matrix W is (n+1) x n in global memory (L2 resident): rows 0..n-1 the lower triangle of A, row n = b. Carrying b
+//     as an extra row makes the forward substitution L y = b fall out of the factorisation (the panel solve of that row IS
+//     y_k = L_kk^-1 (b_k - ...), its trailing update IS the forward-substitution update), so only L^T x = y remains;
+//   * per 32-column block step: every CTA factors the 32 x 32 diagonal block redundantly (one warp, one matrix row per lane in
+//     REGISTERS, shuffles instead of shared-memory round trips), so no barrier separates it from the panel solve; panel rows
+//     (one thread per row) and the trailing update (one warp per row, lanes along the columns, the whole panel staged in
+//     shared memory) are spread over the 8 x 256 threads of the cluster; two cluster barriers per step order the phases;
+//   * CTA 0 finishes with the blocked back substitution.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kCholNB = 32;
-constexpr int kCholThreads = 512;
+constexpr int kCholThreads = 256;
+constexpr int kCholCluster = 8;
 constexpr int kCholMaxN = 704;
 
-__global__ void __launch_bounds__(kCholThreads, 1)
-spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs, int n, double * __restrict__ L,
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+	unsigned r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	// release/acquire at cluster scope: global-memory writes of one phase are visible to every CTA of the cluster in the next
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// 1/sqrt(d) for a positive normal d without branches: MUFU.RSQ64H seed and three Newton steps (quadratic convergence from
+// >= 20 good bits: the last step only polishes), accurate to about an ulp. The factor needs no more: it is compared with the
+// reference's LU solve at 1e-9 and never bit for bit (the reference's luSolve lives in an un-vendored library).
+__device__ __forceinline__ double rsqrt_nr(double d)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+	for (int it = 0; it < 3; it++) {
+		const double e = fma(-d * y, y, 1.0);        // 1 - d y^2
+		y = fma(y, 0.5 * e, y);
+	}
+	return y;
+}
+
+// Cholesky of a 32 x 32 block by one warp: lane r holds row r (lower part) in registers. On return row[] holds L (lane r:
+// L[r][0..r]) and inv_diag the reciprocal of this lane's diagonal entry; bad_col is the first non-positive pivot (1-based
+// inside the block, 0 = none). Rows / columns past the block's real size must have been padded with the identity.
+// (one template instantiation per column: a doubly nested `#pragma unroll` is only partially honoured at 496 bodies, and a
+// dynamic index would push row[] into local memory)
+template <int J> struct CholColumn {
+	__device__ __forceinline__ static void run(double (&row)[kCholNB], int lane, int & bad_col, double & inv_diag)
+	{
+		double d = __shfl_sync(0xffffffffu, row[J], J);
+		const bool okp = d > 0.0 && d < 0x1p1000;          // false for NaN / inf too
+		if (!okp) { if (bad_col == 0) bad_col = J + 1; d = 1.0; }
+		const double inv = rsqrt_nr(d);
+		double sd = d * inv;
+		sd = fma(fma(-sd, sd, d), 0.5 * inv, sd);          // one correction step on the square root itself
+		const double lj = (lane == J) ? sd : row[J] * inv; // column J of L (meaningful for lane >= J)
+		if (lane == J) inv_diag = inv;
+		row[J] = lj;
+#pragma unroll
+		for (int c = J + 1; c < kCholNB; c++) {
+			const double v = __shfl_sync(0xffffffffu, lj, c);  // L[c][J]
+			row[c] = (lane >= c) ? fma(-lj, v, row[c]) : row[c];
+		}
+		CholColumn<J + 1>::run(row, lane, bad_col, inv_diag);
+	}
+};
+template <> struct CholColumn<kCholNB> {
+	__device__ __forceinline__ static void run(double (&)[kCholNB], int, int &, double &) {}
+};
+__device__ __forceinline__ void warp_chol32(double (&row)[kCholNB], int lane, int & bad_col, double & inv_diag)
+{
+	bad_col = 0;
+	inv_diag = 1.0;
+	CholColumn<0>::run(row, lane, bad_col, inv_diag);
+}
+
+__global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
+spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs, int n, double * __restrict__ W,
                  double * __restrict__ x, int * __restrict__ info)
 {
 	extern __shared__ double sm[];
-	double * Dk = sm;                          // 32 x 33 diagonal block
-	double * Pn = sm + kCholNB * (kCholNB + 1); // (n - 32) x 33 panel
-	double * yv = Pn + (size_t) (n > kCholNB ? n - kCholNB : 0) * (kCholNB + 1);   // n : rhs / solution
-	__shared__ int bad;
-	const int tid = threadIdx.x;
 	constexpr int P = kCholNB + 1;
-	if (tid == 0) bad = 0;
-	// copy lower triangle
-	for (long long e = tid; e < (long long) n * n; e += kCholThreads) {
-		int i = (int) (e / n), j = (int) (e - (long long) i * n);
-		L[e] = (j <= i) ? A[e] : 0.0;
+	double * Dk = sm;                               // 32 x 33: factored diagonal block
+	double * Dinv = sm + kCholNB * P;               // 32: reciprocals of its diagonal
+	double * Pn = Dinv + kCholNB;                   // up to (n + 1 - 32) x 33: the panel below it (incl. the b row)
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int cta = (int) cluster_ctarank();
+	const int gtid = tid * kCholCluster + cta;      // cluster-wide thread index, interleaved over the CTAs
+	const int gthreads = kCholThreads * kCholCluster;
+	const int gwarp = warp * kCholCluster + cta, gwarps = (kCholThreads / 32) * kCholCluster;
+	int bad = 0;
+
+	// W = [lower(A); b]
+	for (long long e = gtid; e < (long long) n * n; e += gthreads) {
+		const int i = (int) (e / n), j = (int) (e - (long long) i * n);
+		W[e] = (j <= i) ? A[e] : 0.0;
 	}
-	for (int i = tid; i < n; i += kCholThreads) yv[i] = rhs[i];
-	__syncthreads();
+	for (int i = gtid; i < n; i += gthreads) W[(long long) n * n + i] = rhs[i];
+	cluster_sync_all();
 
 	for (int kb = 0; kb < n; kb += kCholNB) {
 		const int nbk = min(kCholNB, n - kb);
-		const int below = n - (kb + nbk);
-		// 1. diagonal block -> smem
-		for (int e = tid; e < nbk * nbk; e += kCholThreads) {
-			int r = e / nbk, c = e - r * nbk;
-			Dk[r * P + c] = L[(long long) (kb + r) * n + kb + c];
-		}
-		__syncthreads();
-		// 2. unblocked Cholesky of the diagonal block by warp 0 (lane = row)
-		if (tid < 32) {
-			const int r = tid;
-			for (int j = 0; j < nbk; j++) {
-				double d = Dk[j * P + j];
-				if (!(d > 0.0)) { if (r == 0 && bad == 0) bad = kb + j + 1; d = 1.0; }
-				double sd = sqrt(d);
-				__syncwarp();
-				if (r == j) Dk[j * P + j] = sd;
-				if (r > j && r < nbk) Dk[r * P + j] = Dk[r * P + j] / sd;
-				__syncwarp();
-				if (r > j && r < nbk) {
-					double lrj = Dk[r * P + j];
-					for (int c = j + 1; c <= r; c++) Dk[r * P + c] = fma(-lrj, Dk[c * P + j], Dk[r * P + c]);
-				}
-				__syncwarp();
-			}
-		}
-		__syncthreads();
-		// write the factored block back
-		for (int e = tid; e < nbk * nbk; e += kCholThreads) {
-			int r = e / nbk, c = e - r * nbk;
-			if (c <= r) L[(long long) (kb + r) * n + kb + c] = Dk[r * P + c];
-		}
-		// 3. panel solve: row i of the panel, X L_kk^T = A_ik
-		for (int ri = tid; ri < below; ri += kCholThreads) {
-			const long long grow = (long long) (kb + nbk + ri) * n + kb;
+		const int r0 = kb + nbk;                    // first row below the diagonal block
+		const int below = n + 1 - r0;               // rows below, b row included
+		const int cbelow = n - r0;                  // columns to the right
+		// ---- A: diagonal block, factored by warp 0 of EVERY CTA (no barrier needed before the panel solve) ----
+		if (warp == 0) {
 			double row[kCholNB];
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++) row[c] = c < nbk ? L[grow + c] : 0.0;
+			for (int c = 0; c < kCholNB; c++)
+				row[c] = (lane < nbk && c < nbk) ? (c <= lane ? W[(long long) (kb + lane) * n + kb + c] : 0.0) : (c == lane ? 1.0 : 0.0);
+			int bc;
+			double invd;
+			warp_chol32(row, lane, bc, invd);
+			if (bc != 0 && bc <= nbk && bad == 0) bad = kb + bc;
+#pragma unroll
+			for (int c = 0; c < kCholNB; c++) Dk[lane * P + c] = row[c];
+			Dinv[lane] = invd;
+		}
+		__syncthreads();
+		// ---- B: panel solve, one thread per row:  X L_kk^T = W[row][kb .. kb+nbk) ----
+		for (int ri = gtid; ri < below; ri += gthreads) {
+			double * wrow = W + (long long) (r0 + ri) * n + kb;
+			double v[kCholNB];
+#pragma unroll
+			for (int c = 0; c < kCholNB; c++) v[c] = c < nbk ? wrow[c] : 0.0;
 #pragma unroll
 			for (int c = 0; c < kCholNB; c++) {
-				if (c < nbk) {
-					double s = row[c];
+				double s0 = v[c], s1 = 0;                  // two chains: the dependent FMA latency is what this loop costs
 #pragma unroll
-					for (int t = 0; t < kCholNB; t++)
-						if (t < c) s = fma(-row[t], Dk[c * P + t], s);
-					row[c] = s / Dk[c * P + c];
+				for (int t = 0; t + 1 < c; t += 2) { s0 = fma(-v[t], Dk[c * P + t], s0); s1 = fma(-v[t + 1], Dk[c * P + t + 1], s1); }
+				if (c & 1) s0 = fma(-v[c - 1], Dk[c * P + c - 1], s0);
+				v[c] = (s0 + s1) * Dinv[c];
+			}
+#pragma unroll
+			for (int c = 0; c < kCholNB; c++)
+				if (c < nbk) wrow[c] = v[c];
+		}
+		cluster_sync_all();
+		// every CTA is past its read of the unfactored diagonal block: CTA 0 may now store the factor (back substitution needs it)
+		if (cta == 0) {
+			for (int e = tid; e < nbk * kCholNB; e += kCholThreads) {
+				const int r = e >> 5, c = e & 31;
+				if (c <= r) W[(long long) (kb + r) * n + kb + c] = Dk[r * P + c];
+			}
+		}
+		// ---- C: trailing update  W[i][j] -= sum_t L[i][t] L[j][t]  for r0 <= j <= i (i runs over the b row too) ----
+		for (int e = tid; e < below * kCholNB; e += kCholThreads) {
+			const int ri = e >> 5, c = e & 31;
+			Pn[ri * P + c] = c < nbk ? W[(long long) (r0 + ri) * n + kb + c] : 0.0;
+		}
+		__syncthreads();
+		for (int ri = gwarp; ri < below; ri += gwarps) {
+			const int jmax = min(ri, cbelow - 1);   // columns 0..jmax (relative to r0)
+			double li[kCholNB];
+#pragma unroll
+			for (int t = 0; t < kCholNB; t++) li[t] = Pn[ri * P + t];
+			double * wrow = W + (long long) (r0 + ri) * n + r0;
+			for (int j = lane; j <= jmax; j += 32) {
+				const double w0 = wrow[j];
+				double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+				for (int t = 0; t < kCholNB; t += 4) {
+					s0 = fma(li[t], Pn[j * P + t], s0);
+					s1 = fma(li[t + 1], Pn[j * P + t + 1], s1);
+					s2 = fma(li[t + 2], Pn[j * P + t + 2], s2);
+					s3 = fma(li[t + 3], Pn[j * P + t + 3], s3);
 				}
-			}
-#pragma unroll
-			for (int c = 0; c < kCholNB; c++) {
-				if (c < nbk) { L[grow + c] = row[c]; Pn[ri * P + c] = row[c]; }
+				wrow[j] = w0 - ((s0 + s1) + (s2 + s3));
 			}
 		}
-		__syncthreads();
-		// 4. trailing update of the lower triangle: L[i][j] -= sum_t P[i][t] P[j][t]
-		{
-			const int base = kb + nbk;
-			// enumerate (i, j), j <= i, over a below x below square; threads along j for coalescing
-			for (long long e = tid; e < (long long) below * below; e += kCholThreads) {
-				int i = (int) (e / below), j = (int) (e - (long long) i * below);
-				if (j > i) continue;
-				double s = 0;
-#pragma unroll 8
-				for (int t = 0; t < kCholNB; t++)
-					if (t < nbk) s = fma(Pn[i * P + t], Pn[j * P + t], s);
-				L[(long long) (base + i) * n + base + j] -= s;
-			}
-		}
-		__syncthreads();
+		cluster_sync_all();
 	}
 
-	// forward substitution L y = b (blocked; the diagonal block is staged in shared memory)
-	for (int kb = 0; kb < n; kb += kCholNB) {
-		const int nbk = min(kCholNB, n - kb);
-		for (int e = tid; e < nbk * nbk; e += kCholThreads) {
-			int r = e / nbk, c = e - r * nbk;
-			Dk[r * P + c] = L[(long long) (kb + r) * n + kb + c];
-		}
+	// ---- back substitution L^T x = y (y = row n of W), CTA 0 ----
+	if (cta == 0) {
+		double * yv = Pn;                           // reuse: n doubles
+		for (int i = tid; i < n; i += kCholThreads) yv[i] = W[(long long) n * n + i];
 		__syncthreads();
-		if (tid < 32) {
-			for (int k = 0; k < nbk; k++) {
-				double yk = yv[kb + k] / Dk[k * P + k];
-				__syncwarp();
-				if (tid == 0) yv[kb + k] = yk;
-				int r = k + 1 + tid;
-				if (r < nbk) yv[kb + r] = fma(-Dk[r * P + k], yk, yv[kb + r]);
-				__syncwarp();
+		for (int kb = ((n - 1) / kCholNB) * kCholNB; kb >= 0; kb -= kCholNB) {
+			const int nbk = min(kCholNB, n - kb);
+			for (int e = tid; e < kCholNB * kCholNB; e += kCholThreads) {
+				const int r = e >> 5, c = e & 31;
+				Dk[r * P + c] = (r < nbk && c <= r) ? W[(long long) (kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
 			}
-		}
-		__syncthreads();
-		for (int i = kb + nbk + tid; i < n; i += kCholThreads) {
-			double s = yv[i];
-			const double * Lr = L + (long long) i * n + kb;
-			for (int t = 0; t < nbk; t++) s = fma(-Lr[t], yv[kb + t], s);
-			yv[i] = s;
-		}
-		__syncthreads();
-	}
-	// back substitution L^T x = y (blocked, descending)
-	for (int kb = ((n - 1) / kCholNB) * kCholNB; kb >= 0; kb -= kCholNB) {
-		const int nbk = min(kCholNB, n - kb);
-		for (int e = tid; e < nbk * nbk; e += kCholThreads) {
-			int r = e / nbk, c = e - r * nbk;
-			Dk[r * P + c] = L[(long long) (kb + r) * n + kb + c];
-		}
-		__syncthreads();
-		if (tid < 32) {
-			for (int k = nbk - 1; k >= 0; k--) {
-				double xk = yv[kb + k] / Dk[k * P + k];
-				__syncwarp();
-				if (tid == 0) yv[kb + k] = xk;
-				int r = tid;
-				if (r < k) yv[kb + r] = fma(-Dk[k * P + r], xk, yv[kb + r]);
-				__syncwarp();
+			__syncthreads();
+			if (tid < kCholNB) Dinv[tid] = 1.0 / Dk[tid * P + tid];
+			__syncthreads();
+			if (warp == 0) {
+				// lane r holds y_r; solve the 32 x 32 upper-triangular system L_kk^T x = y from the last unknown up
+				double yr = lane < nbk ? yv[kb + lane] : 0.0;
+#pragma unroll
+				for (int k = kCholNB - 1; k >= 0; k--) {
+					const double xk = __shfl_sync(0xffffffffu, yr, k) * Dinv[k];
+					yr = (lane == k) ? xk : ((lane < k) ? fma(-Dk[k * P + lane], xk, yr) : yr);
+				}
+				if (lane < nbk) yv[kb + lane] = yr;
 			}
+			__syncthreads();
+			for (int i = tid; i < kb; i += kCholThreads) {
+				double s = yv[i];
+				for (int t = 0; t < nbk; t++) s = fma(-W[(long long) (kb + t) * n + i], yv[kb + t], s);
+				yv[i] = s;
+			}
+			__syncthreads();
 		}
-		__syncthreads();
-		for (int i = tid; i < kb; i += kCholThreads) {
-			double s = yv[i];
-			for (int t = 0; t < nbk; t++) s = fma(-L[(long long) (kb + t) * n + i], yv[kb + t], s);
-			yv[i] = s;
+		for (int i = tid; i < n; i += kCholThreads) x[i] = yv[i];
+		if (warp == 0) {
+			// every CTA saw the same pivots; report CTA 0's
+			int b = bad;
+			b = __shfl_sync(0xffffffffu, b, 0);
+			if (lane == 0) *info = b;
 		}
-		__syncthreads();
 	}
-	for (int i = tid; i < n; i += kCholThreads) x[i] = yv[i];
-	if (tid == 0) *info = bad;
 }
 
 int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev)
 {
 	PNOL_REQUIRE(ctx, n >= 1 && n <= kCholMaxN, "spd_solve: n = %d outside [1, %d]", n, kCholMaxN);
 	TimerScope ts(ctx, "spd_solve");
-	PNOL_CHECK(ws_reserve(ctx, 1, (size_t) n * n * sizeof(double)));
-	size_t smem = ((size_t) kCholNB * (kCholNB + 1) + (size_t) (n > kCholNB ? n - kCholNB : 0) * (kCholNB + 1) + n) * sizeof(double);
+	PNOL_CHECK(ws_reserve(ctx, 1, ((size_t) n + 1) * n * sizeof(double)));
+	const int prows = n + 1 > kCholNB ? n + 1 - kCholNB : 1;
+	size_t pn = (size_t) prows * (kCholNB + 1);
+	if (pn < (size_t) n) pn = n;                     // the panel buffer doubles as y in the back substitution
+	size_t smem = ((size_t) kCholNB * (kCholNB + 1) + kCholNB + pn) * sizeof(double);
 	PNOL_REQUIRE(ctx, smem <= ctx->smem_optin, "spd_solve: n = %d needs %zu bytes of shared memory", n, smem);
 	PNOL_CUDA(ctx, cudaFuncSetAttribute(spd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	PNOL_LAUNCH(ctx, spd_solve_kernel, 1, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev);
+	PNOL_LAUNCH(ctx, spd_solve_kernel, kCholCluster, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev);
 	return PNOL_OK;
 }
 
