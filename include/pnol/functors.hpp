@@ -69,16 +69,20 @@ struct RosenbrockFunctor {
  * multiplication ((x*x)*x...): libm pow is not reproducible on the device. */
 struct PowerFunctor {
 	static constexpr int kKind = PNOL_F_POWER;
-	template <class Acc> PNOL_HD static double eval(const FunctorParams & P, const Acc & X, int n)
+	/* separable: f = init + term(x_0) + term(x_1) + ... summed in index order (see the note above RastriginFunctor) */
+	static constexpr bool kSeparable = true;
+	PNOL_HD static double sep_init(const FunctorParams &, int) { return 0.0; }
+	PNOL_HD static double sep_term(const FunctorParams & P, double x)
 	{
 		int power = (int) P.ints[0];
-		double value = 0;
-		for (int k = 0; k < n; k++) {
-			double x = X[k];
-			double v = 1.0;
-			for (int q = 0; q < power; q++) v = v * x;
-			value = value + v;
-		}
+		double v = 1.0;
+		for (int q = 0; q < power; q++) v = v * x;
+		return v;
+	}
+	template <class Acc> PNOL_HD static double eval(const FunctorParams & P, const Acc & X, int n)
+	{
+		double value = sep_init(P, n);
+		for (int k = 0; k < n; k++) value = value + sep_term(P, X[k]);
 		return value;
 	}
 };
@@ -108,16 +112,21 @@ struct GoldsteinFunctor {
 	}
 };
 
-/* ours (BASELINE.json config 4): f = 10 n + sum_k (x_k^2 - 10 cos(2 pi x_k)), sequential sum */
+/* ours (BASELINE.json config 4): f = 10 n + sum_k (x_k^2 - 10 cos(2 pi x_k)), sequential sum.
+ * A functor may declare itself SEPARABLE (kSeparable, sep_init, sep_term): f = init + term(x_0) + term(x_1) + ... with the sum
+ * taken in index order. The population sweep then computes the terms one gene per LANE straight from coalesced loads and
+ * only the (cheap, order-preserving) summation one individual per lane -- same bits as eval(), which is defined through the
+ * same two functions. */
 struct RastriginFunctor {
 	static constexpr int kKind = PNOL_F_RASTRIGIN;
-	template <class Acc> PNOL_HD static double eval(const FunctorParams &, const Acc & X, int n)
+	static constexpr bool kSeparable = true;
+	PNOL_HD static double sep_init(const FunctorParams &, int n) { return 10.0 * n; }
+	PNOL_HD static double sep_term(const FunctorParams &, double x) { return x * x - 10.0 * cos2pi(x); }
+	template <class Acc> PNOL_HD static double eval(const FunctorParams & P, const Acc & X, int n)
 	{
-		double value = 10.0 * n;
-		for (int k = 0; k < n; k++) {
-			double x = X[k];
-			value = value + (x * x - 10.0 * cos2pi(x));
-		}
+		double value = sep_init(P, n);
+		PNOL_UNROLL(4)
+		for (int k = 0; k < n; k++) value = value + sep_term(P, X[k]);
 		return value;
 	}
 };

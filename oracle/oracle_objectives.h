@@ -20,32 +20,18 @@ static double o_cos2pi(double x)
 	r = fabs(r);
 	int neg = r > 0.25;
 	if (neg) r = 0.5 - r;
-	int use_sin = r > 0.125;
-	if (use_sin) r = 0.25 - r;
-	double t = 6.283185307179586 * r;
+	double t = 3.141592653589793 * r;
 	double t2 = t * t;
-	double v;
-	if (use_sin) {
-		double p = -2.8114572543455206e-15;
-		p = p * t2 + 7.6471637318198164e-13;
-		p = p * t2 + -1.6059043836821613e-10;
-		p = p * t2 + 2.5052108385441720e-08;
-		p = p * t2 + -2.7557319223985893e-06;
-		p = p * t2 + 1.9841269841269841e-04;
-		p = p * t2 + -8.3333333333333332e-03;
-		p = p * t2 + 1.6666666666666666e-01;
-		v = t - (t * t2) * p;
-	} else {
-		double p = 4.7794773323873853e-14;
-		p = p * t2 + -1.1470745597729725e-11;
-		p = p * t2 + 2.0876756987868100e-09;
-		p = p * t2 + -2.7557319223985888e-07;
-		p = p * t2 + 2.4801587301587302e-05;
-		p = p * t2 + -1.3888888888888889e-03;
-		p = p * t2 + 4.1666666666666664e-02;
-		p = p * t2 + -0.5;
-		v = 1.0 + t2 * p;
-	}
+	double p = 4.7794773323873853e-14;
+	p = fma(p, t2, -1.1470745597729725e-11);
+	p = fma(p, t2, 2.0876756987868100e-09);
+	p = fma(p, t2, -2.7557319223985888e-07);
+	p = fma(p, t2, 2.4801587301587302e-05);
+	p = fma(p, t2, -1.3888888888888889e-03);
+	p = fma(p, t2, 4.1666666666666664e-02);
+	p = fma(p, t2, -0.5);
+	double c = fma(t2, p, 1.0);
+	double v = fma(c + c, c, -1.0);
 	return neg ? -v : v;
 }
 

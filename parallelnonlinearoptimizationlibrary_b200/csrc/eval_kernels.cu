@@ -6,6 +6,8 @@
 // pitch so that thread r walking row r is bank-conflict free. Functor code is compiled with -fmad=false.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pnol {
 
 // ---------------------------------------------------------------------------------------------------
@@ -54,6 +56,103 @@ eval_batch_tile_kernel(FunctorParams P, const double * __restrict__ pts, long lo
 	}
 }
 
+// Separable objectives (functors.hpp: kSeparable): f = init + sum_k term(x_k) in index order. One WARP takes 32 individuals:
+// the terms are computed one gene per lane directly from coalesced row loads (no staging of the inputs, no block-wide
+// barrier, so the warps of an SM drift apart and loads overlap arithmetic), parked in the warp's private shared-memory tile
+// (odd pitch), and lane r then adds up the terms of individual r in index order -- the same operations in the same order as
+// F::eval, hence the same bits. The tile kernel below spends its time in lock-step load / compute phases instead.
+template <class F> struct is_separable {
+	template <class T> static constexpr bool test(decltype(T::kSeparable) *) { return T::kSeparable; }
+	template <class T> static constexpr bool test(...) { return false; }
+	static constexpr bool value = test<F>(nullptr);
+};
+
+constexpr int kSepThreads = 128;
+
+template <class F, int G>
+__global__ void __launch_bounds__(kSepThreads)
+eval_batch_separable_kernel(FunctorParams P, const double * __restrict__ pts, long long B, int n, long long ld,
+                            const unsigned char * __restrict__ indicator, double * __restrict__ f_out, int pitch)
+{
+	extern __shared__ double sm[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	double * tile = sm + (size_t) warp * 32 * pitch;
+	const long long nbatch = (B + 31) / 32;
+	const long long gwarp = (long long) blockIdx.x * (kSepThreads / 32) + warp, gwarps = (long long) gridDim.x * (kSepThreads / 32);
+	for (long long b = gwarp; b < nbatch; b += gwarps) {
+		const long long row0 = b * 32;
+		const int rows = (int) min((long long) 32, B - row0);
+		const bool mine = lane < rows && (indicator == nullptr || indicator[row0 + lane] != 0);
+		if (!__any_sync(0xffffffffu, mine)) continue;       // e.g. the elite block of a GA generation
+		const double * src = pts + row0 * ld;
+		if (n == 32 && rows == 32) {
+			// software pipeline: the loads of the next 8 rows are in flight while the terms of these 8 are computed
+			double cur[G], nxt[G];
+#pragma unroll
+			for (int q = 0; q < G; q++) cur[q] = __ldg(src + q * ld + lane);
+#pragma unroll
+			for (int r0 = 0; r0 < 32; r0 += G) {
+				if (r0 + G < 32) {
+#pragma unroll
+					for (int q = 0; q < G; q++) nxt[q] = __ldg(src + (r0 + G + q) * ld + lane);
+				}
+#pragma unroll
+				for (int q = 0; q < G; q++) tile[(r0 + q) * pitch + lane] = F::sep_term(P, cur[q]);
+#pragma unroll
+				for (int q = 0; q < G; q++) cur[q] = nxt[q];
+			}
+		} else if (n == 32) {
+			for (int r = 0; r < rows; r++) tile[r * pitch + lane] = F::sep_term(P, __ldg(src + r * ld + lane));
+		} else {
+			for (int r = 0; r < rows; r++)
+				for (int k = lane; k < n; k += 32) tile[r * pitch + k] = F::sep_term(P, __ldg(src + r * ld + k));
+		}
+		__syncwarp();
+		if (mine) {
+			double v = F::sep_init(P, n);
+			const double * mt = tile + lane * pitch;
+#pragma unroll 8
+			for (int k = 0; k < n; k++) v = v + mt[k];
+			f_out[row0 + lane] = v;
+		}
+		__syncwarp();
+	}
+}
+
+template <class F, bool kSep = is_separable<F>::value> struct SeparableLaunch {
+	static int run(pnol_ctx *, const pnol_functor *, const double *, long long, int, long long, const unsigned char *, double *, bool * done)
+	{
+		*done = false;
+		return PNOL_OK;
+	}
+};
+template <class F> struct SeparableLaunch<F, true> {
+	static int run(pnol_ctx * ctx, const pnol_functor * f, const double * pts, long long B, int n, long long ld,
+	               const unsigned char * indicator, double * f_out, bool * done)
+	{
+		*done = false;
+		const int pitch = n | 1;
+		const size_t smem = (size_t) (kSepThreads / 32) * 32 * pitch * sizeof(double);
+		if (smem > ctx->smem_optin / 2 || B < 64 || n < 24) return PNOL_OK;        // long / very short genomes, tiny batches: the generic kernels
+		static const int g = [] { const char * e = getenv("PNOL_SWEEP_G"); return e ? atoi(e) : 8; }();   // tuning override
+		auto go = [&](auto kern) -> int {
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			int per_sm = 1;
+			PNOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSepThreads, smem));
+			if (per_sm < 1) per_sm = 1;
+			const long long blocks = ((B + 31) / 32 + kSepThreads / 32 - 1) / (kSepThreads / 32);
+			static const int waves = [] { const char * e = getenv("PNOL_SWEEP_WAVES"); return e ? atoi(e) : 1; }();   // tuning override
+			const long long grid = min(blocks, (long long) ctx->sm_count * per_sm * waves);
+			PNOL_LAUNCH(ctx, kern, (unsigned) grid, kSepThreads, smem, f->params, pts, B, n, ld, indicator, f_out, pitch);
+			return PNOL_OK;
+		};
+		*done = true;
+		if (g == 4) return go(eval_batch_separable_kernel<F, 4>);
+		if (g == 16) return go(eval_batch_separable_kernel<F, 16>);
+		return go(eval_batch_separable_kernel<F, 8>);
+	}
+};
+
 // large-n fallback: one thread per row straight from global memory
 template <class F>
 __global__ void eval_batch_direct_kernel(FunctorParams P, const double * __restrict__ pts, long long B, int n, long long ld,
@@ -73,6 +172,9 @@ int launch_eval_batch(pnol_ctx * ctx, const pnol_functor * f, const double * pts
 	TimerScope ts(ctx, "eval_batch");
 	return dispatch_scalar(ctx, f->kind, [&](auto tag) -> int {
 		using F = decltype(tag);
+		bool done = false;
+		PNOL_CHECK((SeparableLaunch<F>::run(ctx, f, pts, B, n, ld, indicator, f_out, &done)));
+		if (done) return PNOL_OK;
 		int pitch = n | 1;
 		size_t smem = (size_t) kSweepThreads * pitch * sizeof(double);
 		if (smem <= ctx->smem_optin) {

@@ -120,6 +120,39 @@ __global__ void issue_kernel(int iters, double * sink, long long * cycles)
 	if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+// per iteration (x8 unroll): 4 independent DFMA + NL shared-memory loads (LDS.64, lane-dependent address) feeding nothing critical
+template <int NL>
+__global__ void lds_kernel(int iters, double * sink, long long * cycles)
+{
+	__shared__ double tab[64];
+	if (threadIdx.x < 64) tab[threadIdx.x] = 1.0 + threadIdx.x;
+	__syncthreads();
+	double f[4], acc = 0;
+	for (int i = 0; i < 4; i++) f[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+	const double b = 1.0000001, c = 1e-9;
+	int idx = threadIdx.x & 1;
+	long long t0 = clock64();
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+#pragma unroll
+			for (int i = 0; i < 4; i++) f[i] = fma(f[i], b, c);
+#pragma unroll
+			for (int i = 0; i < NL; i++) {
+				double v;
+				asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned) __cvta_generic_to_shared(&tab[(idx * 8 + i + r) & 63])));
+				acc = __longlong_as_double(__double_as_longlong(acc) ^ __double_as_longlong(v));
+			}
+		}
+		idx ^= (it & 1);
+	}
+	long long t1 = clock64();
+	double s = acc;
+	for (int i = 0; i < 4; i++) s += f[i];
+	if (s == 123.456) sink[0] = s;
+	if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 template <class K> void run(const char * name, K kern, int warps, int iters, double inst_per_iter_per_warp, int sms)
 {
 	double * sink; long long * cyc;
@@ -168,6 +201,10 @@ int main()
 		run("4 DFMA + 4x(2 INT)", issue_kernel<4, 0>, w, it, 8.0 * 4, sms);
 		run("4 DFMA + 4 FFMA", issue_kernel<0, 4>, w, it, 8.0 * 4, sms);
 		run("4 DFMA + 8 FFMA", issue_kernel<0, 8>, w, it, 8.0 * 4, sms);
+	}
+	for (int w : {16}) {
+		run("4 DFMA + 4 LDS.64", lds_kernel<4>, w, it, 8.0 * 4, sms);
+		run("4 DFMA + 8 LDS.64", lds_kernel<8>, w, it, 8.0 * 4, sms);
 	}
 	for (int w : {4}) {
 		run("DMMA x8 only", mix_kernel<8, 0>, w, it, 4.0 * 8, sms);
