@@ -688,6 +688,7 @@ struct pnol_ga {
 	long long * ll_dev;
 	// mutation tables (grown on demand)
 	void * mut_mem; size_t mut_bytes;
+	double * gather = nullptr;           // all-gather buffer of the sharded fitness sweep (multi-GPU)
 	// host state
 	pnol_stream_desc stream;
 	uint64_t pos;
@@ -706,6 +707,32 @@ static StreamDev ga_stream_dev(pnol_ga * ga)
 	st.scale = ga->stream.scale;
 	st.exhausted = ga->exhausted;
 	return st;
+}
+
+template <class T> static int ga_alloc(pnol_ga * ga, T ** p, size_t count);
+
+// The fitness sweep of one population (GeneticAlgorithmMPI::evaluatePopulationParallel, Source/GeneticAlgorithmMPI.cpp:283-414).
+// With a communicator the individuals are SHARDED: rank r evaluates rows [r per, (r+1) per) and the objective values are
+// all-gathered (the reference round-robins the individuals and sums zero-padded copies, :344-401). Every other stage of a
+// generation is replicated: all ranks hold the same population and consume the same random stream, so they stay bit-identical.
+static int ga_evaluate(pnol_ga * ga, const double * X, const unsigned char * indicator, double * Fout)
+{
+	pnol_ctx * ctx = ga->ctx;
+	const int Npop = ga->prm.npop, n = ga->n;
+	if (ctx->nranks <= 1) return launch_eval_batch(ctx, ga->f, X, Npop, n, n, indicator, Fout);
+	const int R = ctx->nranks;
+	const long long per = ((long long) Npop + R - 1) / R;
+	if (!ga->gather) PNOL_CHECK(ga_alloc(ga, &ga->gather, (size_t) per * R));
+	const long long lo = per * ctx->rank < Npop ? per * ctx->rank : Npop;
+	const long long hi = lo + per < Npop ? lo + per : Npop;
+	if (hi > lo) PNOL_CHECK(launch_eval_batch(ctx, ga->f, X + lo * n, hi - lo, n, n, indicator ? indicator + lo : nullptr, Fout + lo));
+	// rows that were not evaluated (elites) already hold the same value on every rank, so gathering whole shards is exact
+	double * slot = ga->gather + per * ctx->rank;
+	PNOL_CUDA(ctx, cudaMemsetAsync(slot, 0, (size_t) per * sizeof(double), ctx->stream));
+	if (hi > lo) PNOL_CUDA(ctx, cudaMemcpyAsync(slot, Fout + lo, (size_t) (hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	PNOL_CHECK(comm_allgather_dev(ctx, slot, ga->gather, (size_t) per));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(Fout, ga->gather, (size_t) Npop * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	return PNOL_OK;
 }
 
 template <class T> static int ga_alloc(pnol_ga * ga, T ** p, size_t count)
@@ -882,7 +909,7 @@ extern "C" int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out)
 	PNOL_CUDA(ctx, cudaMemsetAsync(ga->indicator, 1, (size_t) Npop, ctx->stream));
 	PNOL_CHECK(ga_check_identical_dev(ctx, ga->Xnew, Npop, n, ga->lb, ga->ub, ga->indicator, st, &ga->pos, sc));
 	PNOL_CHECK(ga_check_bounds_dev(ctx, ga->Xpop, Npop, n, ga->lb, ga->ub, ga->indicator, st, &ga->pos, sc));   // (:74)
-	PNOL_CHECK(launch_eval_batch(ctx, ga->f, ga->Xpop, Npop, n, n, nullptr, ga->F));                            // (:77)
+	PNOL_CHECK(ga_evaluate(ga, ga->Xpop, nullptr, ga->F));                                                      // (:77)
 	double f0 = 0;
 	PNOL_CUDA(ctx, cudaMemcpyAsync(&f0, ga->F, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));         // (:78)
 	// popSort (:81): sort into Xnew / Fnew, then swap the buffers
@@ -1037,7 +1064,7 @@ extern "C" int pnol_ga_generation(pnol_ga * ga)
 	PNOL_CHECK(ga_check_bounds_dev(ctx, ga->Xnew, Npop, n, ga->lb, ga->ub, ga->indicator, st, &ga->pos, sc));
 
 	// 6. evaluate the new population (:217): the fitness sweep
-	PNOL_CHECK(launch_eval_batch(ctx, ga->f, ga->Xnew, Npop, n, n, ga->indicator, ga->Fnew));
+	PNOL_CHECK(ga_evaluate(ga, ga->Xnew, ga->indicator, ga->Fnew));
 
 	// 7. sort and copy to the old population (:220-230): sorted rows go straight into Xpop / F
 	PNOL_CHECK(ga_pop_sort_dev(ctx, ga->Xnew, ga->Fnew, Npop, n, ga->Xpop, ga->F, sc));

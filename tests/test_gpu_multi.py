@@ -52,6 +52,11 @@ def _worker(rank, world, port, out_dir):
     r = hostapi.lm_lorentz(t[lo:hi], y[lo:hi], float(G[c + "/w"]), G[c + "/x0"], 0.001, 10.0, 1e-7, int(G[c + "/iters"]), 0.0)
     np.save(os.path.join(out_dir, "X%d.npy" % rank), r["X"])
     np.save(os.path.join(out_dir, "F0_%d.npy" % rank), r["F0"])
+    # GA with the fitness sweep sharded over the ranks (all-gather of F): bit-exact like the single-GPU run
+    c = "ga_rastrigin"
+    hostapi.set_stream(seed=int(G[c + "/seed"]), scale=float(G[c + "/scale"]))
+    r = hostapi.ga("rastrigin", G[c + "/x0"], G[c + "/lb"], G[c + "/ub"], int(G[c + "/npop"]), int(G[c + "/gens"]))
+    assert np.array_equal(r["X"], G[c + "/X"]) and r["fOpt"] == G[c + "/fOpt"][0] and r["stream_pos"] == int(G[c + "/stream_pos"][0])
     hostapi.detach()
     launch.barrier()
     ctx.close()
