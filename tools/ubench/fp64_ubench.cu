@@ -153,6 +153,42 @@ __global__ void lds_kernel(int iters, double * sink, long long * cycles)
 	if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+// per iteration (x4 unroll): 8 independent DMMA + NI integer-op groups (SHF/LOP3/IADD, 3 instructions each) + NL LDS.64
+template <int NI, int NL>
+__global__ void dmma_other_kernel(int iters, double * sink, long long * cycles)
+{
+	__shared__ double tab[512];
+	for (int i = threadIdx.x; i < 512; i += blockDim.x) tab[i] = 1.0 + i;
+	__syncthreads();
+	double acc[8][2];
+	unsigned u[NI > 0 ? NI : 1];
+	double l[NL > 0 ? NL : 1];
+	for (int i = 0; i < 8; i++) { acc[i][0] = 0; acc[i][1] = 0; }
+	for (int i = 0; i < NI; i++) u[i] = threadIdx.x * 2654435761u + i;
+	for (int i = 0; i < NL; i++) l[i] = 0;
+	const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+	const unsigned base = (unsigned) __cvta_generic_to_shared(&tab[threadIdx.x & 31]);
+	long long t0 = clock64();
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				dmma(acc[i][0], acc[i][1], a, b);
+				if (i < NI) u[i] = (u[i] ^ (u[i] >> 7)) + 0x9E3779B9u;
+				if (i < NL) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(l[i]) : "r"(base + 256 * (i + r)));
+			}
+		}
+	}
+	long long t1 = clock64();
+	double s = 0;
+	for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+	for (int i = 0; i < NI; i++) s += u[i];
+	for (int i = 0; i < NL; i++) s += l[i];
+	if (s == 123.456) sink[0] = s;
+	if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 template <class K> void run(const char * name, K kern, int warps, int iters, double inst_per_iter_per_warp, int sms)
 {
 	double * sink; long long * cyc;
@@ -205,6 +241,15 @@ int main()
 	for (int w : {16}) {
 		run("4 DFMA + 4 LDS.64", lds_kernel<4>, w, it, 8.0 * 4, sms);
 		run("4 DFMA + 8 LDS.64", lds_kernel<8>, w, it, 8.0 * 4, sms);
+	}
+	// inst count = the 8 DMMA only: cycles/inst/warp x (4 / warps per scheduler) = 16 means the tensor pipe is saturated
+	for (int w : {16}) {
+		run("8 DMMA + 0 other", dmma_other_kernel<0, 0>, w, it, 4.0 * 8, sms);
+		run("8 DMMA + 4x3 INT", dmma_other_kernel<4, 0>, w, it, 4.0 * 8, sms);
+		run("8 DMMA + 8x3 INT", dmma_other_kernel<8, 0>, w, it, 4.0 * 8, sms);
+		run("8 DMMA + 4 LDS", dmma_other_kernel<0, 4>, w, it, 4.0 * 8, sms);
+		run("8 DMMA + 8 LDS", dmma_other_kernel<0, 8>, w, it, 4.0 * 8, sms);
+		run("8 DMMA + 8 LDS + 8x3 INT", dmma_other_kernel<8, 8>, w, it, 4.0 * 8, sms);
 	}
 	for (int w : {4}) {
 		run("DMMA x8 only", mix_kernel<8, 0>, w, it, 4.0 * 8, sms);
