@@ -39,6 +39,15 @@ class BFGS_Bnd_MPI_SW : public AlgorithmBnd {
 	int procID;
 	bool optimFlag;
 	int recurFlag;
+	bool serialSearch;      // true: one step length at a time, the line search of the serial class BFGS_Bnd
+
+	// the line search of Source/BFGS_bnd_linesearch.cpp (:207-380 and :385-460), used by class BFGS_Bnd
+	void serialLineSearchBnd( vector <double> & X, vector <double> & Xlb, vector <double> & Xub,
+			double FX, vector <double> & dFdX, vector <double> & p, vector<double> & constantX, vector<bool> & constantIndicator,
+			double & alphaOpt, double & Fopt );
+	void serialZoomBnd( double alpha_a, double alpha_b, double phi_a, double phi_b, double dphi_a_dalpha, double dphi_b_dalpha,
+			double phi0, double dphi0dalpha, vector <double> & X, vector <double> & p, vector<double> & constantX, vector<bool> & constantIndicator,
+			int & iter_ls, double & alphaOpt, double & phiOpt, double & dphiOptdalpha );
 
   public:
 	void findMinBnd( vector <double> & X, vector <double> & Xlb, vector <double> & Xub, double & f0, double & fOpt );
@@ -71,6 +80,7 @@ class BFGS_Bnd_MPI_SW : public AlgorithmBnd {
 		xMinDiff = xMinDiffIn; minGrad2Norm = minGrad2NormIn; initHessFD = initHessFDIn; verbose = verboseIn;
 	}
 	void setPoolWidth( int w ){ Nprocs = w < 1 ? 1 : w; }
+	void setSerialLineSearch( bool on ){ serialSearch = on; }
 	int iterations() const { return totalIter; }
 
 	BFGS_Bnd_MPI_SW();

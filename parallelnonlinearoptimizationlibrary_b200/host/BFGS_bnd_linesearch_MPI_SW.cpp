@@ -17,6 +17,7 @@ BFGS_Bnd_MPI_SW::BFGS_Bnd_MPI_SW()
 	optimFlag = true;
 	recurFlag = 0;
 	totalIter = 0;
+	serialSearch = false;
 }
 
 // Source/BFGS_bnd_linesearch_MPI_SW.cpp:12-113
@@ -77,7 +78,8 @@ void BFGS_Bnd_MPI_SW::mainBFGSLoop( double & F, vector <double> & X, vector<doub
 
 		// 2. step length (:148-149)
 		double alpha, Fopt;
-		cubicInterpolationLineSearchBnd( X, Xlb, Xub, F, dFdX, p, constantX, constantIndicator, alpha, Fopt );
+		if( serialSearch ) serialLineSearchBnd( X, Xlb, Xub, F, dFdX, p, constantX, constantIndicator, alpha, Fopt );
+		else cubicInterpolationLineSearchBnd( X, Xlb, Xub, F, dFdX, p, constantX, constantIndicator, alpha, Fopt );
 
 		// 3. update variables and inverse Hessian (:153-174)
 		for( int i = 0; i < Nparam; i++ )
@@ -288,6 +290,129 @@ void computeZoomPool( double alpha_a, double alpha_b, double phi_a, double phi_b
 	phiPool[Npool-1] = phi_b;
 	dphidalphaPool[Npool-1] = dphi_b_dalpha;
 	evalIndicator[Npool-1] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The serial class BFGS_Bnd (Source/BFGS_bnd_linesearch.cpp) shares mainBFGSLoop and boundaryAssessment with this class word
+// for word (its copies differ only in prints and in calling the non-MPI gradient, which returns the same numbers); what
+// differs is the line search: one trial step at a time, bracketing by doubling, then a cubic-interpolation zoom.
+// ---------------------------------------------------------------------------------------------------------------------
+// Source/BFGS_bnd_linesearch.cpp:207-380
+void BFGS_Bnd_MPI_SW::serialLineSearchBnd( vector <double> & X, vector <double> & Xlb, vector <double> & Xub,
+		double FX, vector <double> & dFdX, vector <double> & p, vector<double> & constantX, vector<bool> & constantIndicator,
+		double & alphaOpt, double & Fopt )
+{
+	bool success = false;
+	double dphiOptdalpha;
+	double phii = FX;
+
+	alphaOpt = 0;
+	Fopt = FX;
+
+	// initial values, with the initial slope from the gradient (:222-224)
+	double phi0 = FX;
+	double dphi0dalpha = dotProd( dFdX, p );
+	double alphaim1 = 0;
+	double phiim1 = phi0;
+	double dphiim1dalpha = dphi0dalpha;
+
+	double alphaMax = computeAlphaBnd( X, Xlb, Xub, p );                      // (:232)
+	double alphai = alphaGuess;
+	if( alphai > alphaMax ) alphai = alphaMax;
+
+	int iter_ls = 0;
+	while( iter_ls < maxIterLineSearch )
+	{
+		phii = lineSearchObj( alphai, X, p, constantX, constantIndicator );
+		double dphiidalpha = lineSearchFDDerivative( alphai, phii, X, p, constantX, constantIndicator );
+
+		// 1. sufficient decrease violated, or no longer decreasing: the minimum is bracketed (:266-273)
+		if( ( phii > phi0 + c1*alphai*dphi0dalpha ) || ( phii >= phiim1 && iter_ls > 1 ) )
+		{
+			serialZoomBnd( alphaim1, alphai, phiim1, phii, dphiim1dalpha, dphiidalpha, phi0, dphi0dalpha, X, p, constantX, constantIndicator,
+					iter_ls, alphaOpt, Fopt, dphiOptdalpha );
+			success = true;
+			break;
+		}
+		// 2. curvature condition holds (:277-283)
+		if( fabs( dphiidalpha ) <= fabs( c2*dphi0dalpha ) )
+		{
+			alphaOpt = alphai; Fopt = phii; success = true;
+			break;
+		}
+		// 3. slope turned positive: bracketed (:287-294)
+		if( dphiidalpha >= 0 )
+		{
+			serialZoomBnd( alphaim1, alphai, phiim1, phii, dphiim1dalpha, dphiidalpha, phi0, dphi0dalpha, X, p, constantX, constantIndicator,
+					iter_ls, alphaOpt, Fopt, dphiOptdalpha );
+			success = true;
+			break;
+		}
+		// 4. the box was reached (:297-304)
+		if( alphai == alphaMax )
+		{
+			alphaOpt = alphai; Fopt = phii; success = true;
+			break;
+		}
+		alphaim1 = alphai; phiim1 = phii; dphiim1dalpha = dphiidalpha;
+		// 5. extend the interval (:314-318)
+		alphai = 2*alphai;
+		if( alphai > alphaMax ) alphai = alphaMax;
+		iter_ls++;
+	}
+
+	// ran out of iterations: best of what was seen (:325-343)
+	if( !success )
+	{
+		if( phiim1 < phii ) { alphaOpt = alphaim1; Fopt = phiim1; }
+		else if( phi0 < phii ) { alphaOpt = 0; Fopt = phi0; }
+		else { alphaOpt = alphai; Fopt = phii; }
+	}
+	if( verbose > 0 )
+		cout << "  Line search completed with alpha = " << alphaOpt << " and F = " << Fopt << " after " << iter_ls << " iterations. Note: alphaMax = " << alphaMax << endl;
+}
+
+// Source/BFGS_bnd_linesearch.cpp:385-460
+void BFGS_Bnd_MPI_SW::serialZoomBnd( double alpha_a, double alpha_b, double phi_a, double phi_b, double dphi_a_dalpha, double dphi_b_dalpha,
+		double phi0, double dphi0dalpha, vector <double> & X, vector <double> & p, vector<double> & constantX, vector<bool> & constantIndicator,
+		int & iter_ls, double & alphaOpt, double & phiOpt, double & dphiOptdalpha )
+{
+	bool success = false;
+	while( iter_ls < maxIterLineSearch && ( alpha_b - alpha_a > alphaTol ) )
+	{
+		// 0. new trial step by cubic interpolation (:396-398)
+		double alpha_c = cubicInterpMinSimple( alpha_a, alpha_b, phi_a, phi_b, dphi_a_dalpha, dphi_b_dalpha );
+		double phi_c = lineSearchObj( alpha_c, X, p, constantX, constantIndicator );
+		double dphi_c_dalpha = lineSearchFDDerivative( alpha_c, phi_c, X, p, constantX, constantIndicator );
+
+		// 1. shrink the interval from the side with the larger value (:415-431)
+		double phi_min = phi_a;
+		if( phi_b < phi_a ) phi_min = phi_b;
+		if( phi_c > phi0 + c1*alpha_c*dphi0dalpha || phi_c >= phi_min )
+		{
+			if( phi_a < phi_b ) { alpha_b = alpha_c; phi_b = phi_c; dphi_b_dalpha = dphi_c_dalpha; }
+			else { alpha_a = alpha_c; phi_a = phi_c; dphi_a_dalpha = dphi_c_dalpha; }
+		}
+		else
+		{
+			// 2. close enough (:435-442)
+			if( fabs( dphi_c_dalpha ) <= fabs( c2*dphi0dalpha ) )
+			{
+				alphaOpt = alpha_c; phiOpt = phi_c; dphiOptdalpha = dphi_c_dalpha;
+				success = true;
+				break;
+			}
+			// 3. keep the minimum inside (:445-456)
+			if( dphi_c_dalpha < 0 ) { alpha_a = alpha_c; phi_a = phi_c; dphi_a_dalpha = dphi_c_dalpha; }
+			else { alpha_b = alpha_c; phi_b = phi_c; dphi_b_dalpha = dphi_c_dalpha; }
+		}
+		iter_ls++;
+	}
+	if( !success )                                                           // (:463-477)
+	{
+		if( phi_a < phi_b ) { alphaOpt = alpha_a; phiOpt = phi_a; dphiOptdalpha = dphi_a_dalpha; }
+		else { alphaOpt = alpha_b; phiOpt = phi_b; dphiOptdalpha = dphi_b_dalpha; }
+	}
 }
 
 // Source/BFGS_bnd_linesearch_MPI_SW.cpp:484-548

@@ -128,6 +128,18 @@ def main():
         r = O.ref_cli("bfgs_bnd_sw", arrays=dict(x=x0, xlb=np.full(n, -5.0), xub=np.full(n, 5.0)), obj="rosenbrock", maxiter=iters, nprocs=8, **sw)
         put("bfgs_bnd_sw_n64_P8_it%d" % iters, x0=x0, X=r["X"], f0=r["f0"], fOpt=r["fOpt"],
             **ulp_twin("bfgs_bnd_sw", x0, dict(xlb=np.full(n, -5.0), xub=np.full(n, 5.0)), idx=1, obj="rosenbrock", maxiter=iters, nprocs=8, **sw))
+    # BFGS_Bnd (serial bounded): testBFGSBnd itself (Source/Examples.cpp:49-83: n = 5, X0 = 2, box [-5,5], params :75) run to
+    # convergence, after a fixed 4 iterations, and a start ON a bound (n = 12, X0[0] = -5)
+    for iters in (4, 200):
+        r = O.ref_cli("bfgs_bnd", arrays=dict(x=np.full(5, 2.0), xlb=np.full(5, -5.0), xub=np.full(5, 5.0)), obj="rosenbrock", maxiter=iters, **sw)
+        put("testBFGSBnd_it%d" % iters, X=r["X"], f0=r["f0"], fOpt=r["fOpt"],
+            **ulp_twin("bfgs_bnd", np.full(5, 2.0), dict(xlb=np.full(5, -5.0), xub=np.full(5, 5.0)), obj="rosenbrock", maxiter=iters, **sw))
+    n = 12
+    x0 = np.full(n, 2.0)
+    x0[0] = -5.0
+    r = O.ref_cli("bfgs_bnd", arrays=dict(x=x0, xlb=np.full(n, -5.0), xub=np.full(n, 5.0)), obj="rosenbrock", maxiter=6, **sw)
+    put("bfgs_bnd_n12_it6", x0=x0, X=r["X"], f0=r["f0"], fOpt=r["fOpt"],
+        **ulp_twin("bfgs_bnd", x0, dict(xlb=np.full(n, -5.0), xub=np.full(n, 5.0)), idx=1, obj="rosenbrock", maxiter=6, **sw))
     # ---- GA (Source/GeneticAlgorithmMPI.cpp:12-276) driven by the counter stream (oracle/shim timeRand) ----
     for spec, n, npop, gens, box in (("powerprod:2", 4, 150, 6, 10.0), ("rastrigin", 6, 200, 5, 5.12), ("rosenbrock", 3, 64, 8, 2.0)):
         lb, ub = np.full(n, -box), np.full(n, box)

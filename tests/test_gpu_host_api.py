@@ -152,6 +152,22 @@ def test_bfgs_bnd_sw_box(host, iters):
     assert rel(r["X"], g(c, "X")) < tx and abs(r["fOpt"] - g(c, "fOpt")[0]) <= tf * abs(g(c, "fOpt")[0])
 
 
+@pytest.mark.parametrize("case,n,iters", [("testBFGSBnd_it4", 5, 4), ("testBFGSBnd_it200", 5, 200), ("bfgs_bnd_n12_it6", 12, 6)])
+def test_bfgs_bnd_serial(host, case, n, iters):
+    # BFGS_Bnd (Source/BFGS_bnd_linesearch.cpp): the serial twin -- one trial step at a time in the line search
+    p = list(SW)
+    p[10] = iters
+    x0 = g(case, "x0") if case.startswith("bfgs_bnd") else np.full(n, 2.0)
+    r = host.bfgs("bfgs_bnd", "rosenbrock", x0, p, np.full(n, -5.0), np.full(n, 5.0))
+    assert r["f0"] == g(case, "f0")[0]
+    if iters == 200:
+        # run to convergence (stops on xMinDiff = 1e-5): agreement to the optimiser's own stop tolerance
+        assert rel(r["X"], g(case, "X")) < 1e-5 and abs(r["fOpt"] - g(case, "fOpt")[0]) < 1e-6 * max(1.0, abs(g(case, "fOpt")[0]))
+    else:
+        tx, tf = tol(case)
+        assert rel(r["X"], g(case, "X")) < tx and abs(r["fOpt"] - g(case, "fOpt")[0]) <= tf * abs(g(case, "fOpt")[0])
+
+
 @pytest.mark.parametrize("spec,obj", [("powerprod2", "power:2"), ("rastrigin", "rastrigin"), ("rosenbrock", "rosenbrock")])
 @pytest.mark.parametrize("serial", [False, True])
 def test_genetic_algorithm_bit_exact(host, spec, obj, serial):
