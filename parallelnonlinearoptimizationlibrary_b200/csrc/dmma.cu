@@ -39,6 +39,30 @@ template <int BYTES> __device__ __forceinline__ void cp_async_zfill(void * smem_
 		asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(sz));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+
+// ---- mbarrier plumbing of the SYRK stage ring (shared::cta) ----
+__device__ __forceinline__ void mbar_init(uint64_t * bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count));
+}
+// one arrival that fires when all cp.async of the calling thread issued so far have landed (does not touch the pending count)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t * bar)
+{
+	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, unsigned parity)
+{
+	const unsigned addr = (unsigned) __cvta_generic_to_shared(bar);
+	unsigned done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+		             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+	} while (!done);
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -150,30 +174,43 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 	if (!diag) ldB.init(J, n, row_begin, wk.bj * kBT, tid);
 	const long long chunk_elems = (long long) kKC * n;
 
-	auto issue = [&](long long chunk) {
-		if (chunk < wk.chunk1) {
-			const long long rel = chunk - wk.chunk0;
-			SyrkStage & st = stages[(int) (rel % kStages)];
-			const long long rows_valid = m - chunk * kKC;
-			ldA.issue(st.A, J, rel * chunk_elems, rows_valid);
-			if (!diag) ldB.issue(st.B, J, rel * chunk_elems, rows_valid);
-			if (diag && Fv && tid < kKC) {
-				long long row = chunk * kKC + tid;
-				bool valid = row < m;
-				cp_async_zfill<8>(&st.F[tid], valid ? (Fv + row) : Fv, valid);
-			}
+	// Stage ring without block-wide barriers. full[s] (512 arrivals, one per thread, fired by the hardware when that thread's
+	// cp.async of the stage have landed) says "stage s holds chunk data"; empty[s] (16 arrivals, one per warp) says "every warp
+	// is done reading stage s". A warp waits on full[] before it reads and on empty[] before it overwrites, so the warps of
+	// the CTA drift up to one chunk apart instead of meeting at a __syncthreads() every 32 rows of J (that convoy cost 4.4 %
+	// of the kernel: 8.82 -> 8.43 ms with the barrier removed in a timing-only experiment).
+	__shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], kDmmaThreads); mbar_init(&empty_bar[s], kDmmaThreads / 32); }
+	}
+	__syncthreads();
+
+	const long long nloc = wk.chunk1 - wk.chunk0;           // chunks of this CTA
+	auto issue = [&](long long rel) {                       // rel = chunk index relative to chunk0; uniform across the CTA
+		if (rel >= nloc) return;
+		const int s = (int) (rel % kStages);
+		SyrkStage & st = stages[s];
+		const long long chunk = wk.chunk0 + rel;
+		const long long rows_valid = m - chunk * kKC;
+		ldA.issue(st.A, J, rel * chunk_elems, rows_valid);
+		if (!diag) ldB.issue(st.B, J, rel * chunk_elems, rows_valid);
+		if (diag && Fv && tid < kKC) {
+			long long row = chunk * kKC + tid;
+			bool valid = row < m;
+			cp_async_zfill<8>(&st.F[tid], valid ? (Fv + row) : Fv, valid);
 		}
-		cp_async_commit();
+		mbar_arrive_on_cp_async(&full_bar[s]);
 	};
 
 #pragma unroll
-	for (int s = 0; s < kStages - 1; s++) issue(wk.chunk0 + s);
+	for (int s = 0; s < kStages - 1; s++) issue(s);
 
 	const int aoff = (wi > 0 ? wi : 0) * 32, boff = (wj > 0 ? wj : 0) * 32;
-	for (long long chunk = wk.chunk0; chunk < wk.chunk1; chunk++) {
-		cp_async_wait<kStages - 2>();
-		__syncthreads();
-		const SyrkStage & st = stages[(int) ((chunk - wk.chunk0) % kStages)];
+	for (long long rel = 0; rel < nloc; rel++) {
+		const int s = (int) (rel % kStages);
+		mbar_wait(&full_bar[s], (unsigned) ((rel / kStages) & 1));
+		const SyrkStage & st = stages[s];
 		const double * As = st.A + aoff;
 		const double * Bs = (diag ? st.A : st.B) + boff;
 		if (active) {
@@ -183,10 +220,13 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 #pragma unroll
 			for (int k = 0; k < kKC; k++) rhs_acc = fma(st.A[k * kPitchB + rhs_col], st.F[k], rhs_acc);
 		}
-		// refill the stage consumed in the previous iteration (every thread is past this iteration's barrier)
-		issue(chunk + kStages - 1);
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty_bar[s]);
+		// refill the stage that was read in the previous iteration, once every warp has left it
+		const long long nxt = rel + kStages - 1;
+		if (rel >= 1 && nxt < nloc) mbar_wait(&empty_bar[(int) (nxt % kStages)], (unsigned) (((rel - 1) / kStages) & 1));
+		issue(nxt);
 	}
-	cp_async_wait<0>();
 
 	// partial tile -> workspace slot (row-major 128 x 128)
 	double * tile = part_tiles + (size_t) wk.slot * kBT * kBT;
