@@ -13,11 +13,18 @@
 // banks per half-warp. For SYRK the A and B fragments come from the SAME staged rows of J.
 #include "common.cuh"
 
+#ifndef SYRK_KC
+#define SYRK_KC 32
+#define SYRK_STAGES 3
+#endif
+
 namespace pnol {
 
 constexpr int kBT = 128;            // CTA tile edge
 constexpr int kKC = 32;             // K rows per stage
 constexpr int kStages = 3;
+constexpr int kSKC = SYRK_KC;         // SYRK: K rows per stage and ring depth (tuned apart from the GEMM's)
+constexpr int kSStages = SYRK_STAGES;
 constexpr int kPitchB = kBT + 4;    // pitch of a [kKC][kBT] operand tile (132 = 4 mod 16)
 constexpr int kPitchA = kKC + 4;    // pitch of a [kBT][kKC] operand tile (20 = 4 mod 16)
 constexpr int kDmmaThreads = 512;
@@ -72,13 +79,13 @@ struct SyrkWork {
 	int bi, bj;                 // tile row / col block (bj <= bi)
 	int slot;                   // partial-result slot
 	int pad;
-	long long chunk0, chunk1;   // K chunks [chunk0, chunk1) of kKC rows
+	long long chunk0, chunk1;   // K chunks [chunk0, chunk1) of kSKC rows
 };
 
 struct SyrkStage {
-	double A[kKC * kPitchB];
-	double B[kKC * kPitchB];
-	double F[kKC];
+	double A[kSKC * kPitchB];
+	double B[kSKC * kPitchB];
+	double F[kSKC];
 };
 
 // one warp tile, one K chunk: 4 x 4 DMMA tiles per k-step. kLower: diagonal warp tile, only j <= i is needed.
@@ -87,7 +94,7 @@ __device__ __forceinline__ void warp_tile_chunk(double (&acc)[4][4][2], const do
                                                 const double * __restrict__ Bs, int lane)
 {
 #pragma unroll
-	for (int kk = 0; kk < kKC; kk += 4) {
+	for (int kk = 0; kk < kSKC; kk += 4) {
 		double a[4], b[4];
 		const int krow = (kk + (lane & 3)) * kPitchB + (lane >> 2);
 #pragma unroll
@@ -102,9 +109,9 @@ __device__ __forceinline__ void warp_tile_chunk(double (&acc)[4][4][2], const do
 	}
 }
 
-// per-thread cp.async plan for one [kKC][kBT] operand tile: piece e = tid + q * 512
+// per-thread cp.async plan for one [kSKC][kBT] operand tile: piece e = tid + q * 512
 template <bool kVec16> struct RowLoader {
-	static constexpr int kPieces = kVec16 ? (kKC * (kBT / 2)) / kDmmaThreads : (kKC * kBT) / kDmmaThreads;
+	static constexpr int kPieces = kVec16 ? (kSKC * (kBT / 2)) / kDmmaThreads : (kSKC * kBT) / kDmmaThreads;
 	const double * src[kPieces];   // address in chunk 0 of the CTA's range (nullptr: column out of range)
 	int dst[kPieces];              // element offset inside the stage tile
 	int row[kPieces];              // row inside the chunk
@@ -120,7 +127,7 @@ template <bool kVec16> struct RowLoader {
 			src[q] = (col0 + c) < n ? (J + (row0 + r) * (long long) n + col0 + c) : nullptr;
 		}
 	}
-	// rows_valid: number of rows of this chunk that exist (>= kKC except in the last chunk)
+	// rows_valid: number of rows of this chunk that exist (>= kSKC except in the last chunk)
 	__device__ __forceinline__ void issue(double * tile, const double * J, long long elem_off, long long rows_valid) const
 	{
 #pragma unroll
@@ -169,34 +176,34 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
 
 	RowLoader<kVec16> ldA, ldB;
-	const long long row_begin = wk.chunk0 * kKC;
+	const long long row_begin = wk.chunk0 * kSKC;
 	ldA.init(J, n, row_begin, wk.bi * kBT, tid);
 	if (!diag) ldB.init(J, n, row_begin, wk.bj * kBT, tid);
-	const long long chunk_elems = (long long) kKC * n;
+	const long long chunk_elems = (long long) kSKC * n;
 
 	// Stage ring without block-wide barriers. full[s] (512 arrivals, one per thread, fired by the hardware when that thread's
 	// cp.async of the stage have landed) says "stage s holds chunk data"; empty[s] (16 arrivals, one per warp) says "every warp
 	// is done reading stage s". A warp waits on full[] before it reads and on empty[] before it overwrites, so the warps of
 	// the CTA drift up to one chunk apart instead of meeting at a __syncthreads() every 32 rows of J (that convoy cost 4.4 %
 	// of the kernel: 8.82 -> 8.43 ms with the barrier removed in a timing-only experiment).
-	__shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
 	if (tid == 0) {
 #pragma unroll
-		for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], kDmmaThreads); mbar_init(&empty_bar[s], kDmmaThreads / 32); }
+		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], kDmmaThreads); mbar_init(&empty_bar[s], kDmmaThreads / 32); }
 	}
 	__syncthreads();
 
 	const long long nloc = wk.chunk1 - wk.chunk0;           // chunks of this CTA
 	auto issue = [&](long long rel) {                       // rel = chunk index relative to chunk0; uniform across the CTA
 		if (rel >= nloc) return;
-		const int s = (int) (rel % kStages);
+		const int s = (int) (rel % kSStages);
 		SyrkStage & st = stages[s];
 		const long long chunk = wk.chunk0 + rel;
-		const long long rows_valid = m - chunk * kKC;
+		const long long rows_valid = m - chunk * kSKC;
 		ldA.issue(st.A, J, rel * chunk_elems, rows_valid);
 		if (!diag) ldB.issue(st.B, J, rel * chunk_elems, rows_valid);
-		if (diag && Fv && tid < kKC) {
-			long long row = chunk * kKC + tid;
+		if (diag && Fv && tid < kSKC) {
+			long long row = chunk * kSKC + tid;
 			bool valid = row < m;
 			cp_async_zfill<8>(&st.F[tid], valid ? (Fv + row) : Fv, valid);
 		}
@@ -204,12 +211,12 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 	};
 
 #pragma unroll
-	for (int s = 0; s < kStages - 1; s++) issue(s);
+	for (int s = 0; s < kSStages - 1; s++) issue(s);
 
 	const int aoff = (wi > 0 ? wi : 0) * 32, boff = (wj > 0 ? wj : 0) * 32;
 	for (long long rel = 0; rel < nloc; rel++) {
-		const int s = (int) (rel % kStages);
-		mbar_wait(&full_bar[s], (unsigned) ((rel / kStages) & 1));
+		const int s = (int) (rel % kSStages);
+		mbar_wait(&full_bar[s], (unsigned) ((rel / kSStages) & 1));
 		const SyrkStage & st = stages[s];
 		const double * As = st.A + aoff;
 		const double * Bs = (diag ? st.A : st.B) + boff;
@@ -218,13 +225,13 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 			else warp_tile_chunk<false>(acc, As, Bs, lane);
 		} else if (rhs_col >= 0 && Fv) {
 #pragma unroll
-			for (int k = 0; k < kKC; k++) rhs_acc = fma(st.A[k * kPitchB + rhs_col], st.F[k], rhs_acc);
+			for (int k = 0; k < kSKC; k++) rhs_acc = fma(st.A[k * kPitchB + rhs_col], st.F[k], rhs_acc);
 		}
 		__syncwarp();
 		if (lane == 0) mbar_arrive(&empty_bar[s]);
 		// refill the stage that was read in the previous iteration, once every warp has left it
-		const long long nxt = rel + kStages - 1;
-		if (rel >= 1 && nxt < nloc) mbar_wait(&empty_bar[(int) (nxt % kStages)], (unsigned) (((rel - 1) / kStages) & 1));
+		const long long nxt = rel + kSStages - 1;
+		if (rel >= 1 && nxt < nloc) mbar_wait(&empty_bar[(int) (nxt % kSStages)], (unsigned) (((rel - 1) / kSStages) & 1));
 		issue(nxt);
 	}
 
@@ -283,7 +290,7 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	PNOL_REQUIRE(ctx, n >= 1 && m >= 0, "syrk: bad shape m=%lld n=%d", m, n);
 	const int nb = (n + kBT - 1) / kBT;
 	const int nroles = nb * (nb + 1) / 2;
-	const long long nchunks = (m + kKC - 1) / kKC;
+	const long long nchunks = (m + kSKC - 1) / kSKC;
 
 	// CTA budget per role, proportional to the time one K chunk takes there (busiest sub-partition)
 	int grid_cap = ctx->sm_count;
@@ -353,7 +360,7 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));
 
 	const bool vec16 = (n % 2 == 0) && ((((size_t) J) & 15) == 0);
-	size_t smem = sizeof(SyrkStage) * kStages;
+	size_t smem = sizeof(SyrkStage) * kSStages;
 	{
 		TimerScope ts(ctx, "syrk");
 		if (vec16) {
