@@ -1,0 +1,126 @@
+"""GPU: edge cases of the C-ABI -- empty and one-element inputs, ragged sizes around the warp / tile boundaries, invalid
+arguments (status codes instead of the reference's exit()), non-finite objectives, a singular damped matrix in LM."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from parallelnonlinearoptimizationlibrary_b200 import capi, problems
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_and_single_row_batches(ctx):
+    f = ctx.functor(capi.F_ROSENBROCK)
+    of = O.OFunctor(capi.F_ROSENBROCK)
+    assert ctx.eval_batch(f, np.zeros((0, 4)), 0, 4).size == 0                   # B = 0 is a no-op, not an error
+    for B in (1, 2, 31, 32, 33, 127, 128, 129):
+        pts = np.random.default_rng(B).uniform(-2, 2, size=(B, 7))
+        assert np.array_equal(ctx.eval_batch(f, pts, B, 7), O.eval_batch(of, pts))
+
+
+@pytest.mark.parametrize("B,n", [(1, 32), (63, 32), (64, 32), (65, 32), (1000, 4), (1000, 36), (257, 100)])
+def test_separable_sweep_sizes(ctx, B, n):
+    # Rastrigin takes the row-wise / warp-tile kernels for aligned n and the generic tile kernel otherwise: same bits everywhere
+    f = ctx.functor(capi.F_RASTRIGIN)
+    of = O.OFunctor(capi.F_RASTRIGIN)
+    pts = np.random.default_rng(B + n).uniform(-5.12, 5.12, size=(B, n))
+    assert np.array_equal(ctx.eval_batch(f, pts, B, n), O.eval_batch(of, pts))
+    ind = (np.arange(B) % 3 != 0).astype(np.uint8)
+    out = np.full(B, -1.0)
+    got = ctx.eval_batch(f, pts, B, n, indicator=ind, f_out=out.copy())
+    want = O.eval_batch(of, pts, indicator=ind, f_out=out.copy())
+    assert np.array_equal(got, want) and np.all(got[ind == 0] == -1.0)
+
+
+def test_strided_population(ctx):
+    # ld > n: rows of a wider matrix (the GA never needs it, bindings may)
+    f = ctx.functor(capi.F_RASTRIGIN)
+    of = O.OFunctor(capi.F_RASTRIGIN)
+    wide = np.random.default_rng(3).uniform(-5, 5, size=(300, 40))
+    got = ctx.eval_batch(f, wide, 300, 32, ld=40)
+    assert np.array_equal(got, O.eval_batch(of, np.ascontiguousarray(wide[:, :32])))
+
+
+@pytest.mark.parametrize("m", [1, 2, 31, 33, 95])
+def test_tiny_residual_problems(ctx, m):
+    pr = problems.lorentz_problem(max(m, 2), 4)
+    t, y = pr["t"][:m], pr["y"][:m]
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (t, y), m)
+    of = O.OFunctor(capi.F_LORENTZ_SUM, (pr["w"],), (), (t, y), m)
+    dx = np.full(pr["n"], 1e-7)
+    J, F = ctx.fd_jacobian(f, pr["x0"], dx)
+    Jw, Fw = O.fd_jacobian(of, pr["x0"], dx)
+    assert np.array_equal(J, Jw) and np.array_equal(F, Fw)
+    Jb, Fb = ctx.fd_jacobian(f, pr["x0"], dx, mode=capi.JAC_BLACKBOX)
+    assert np.array_equal(Jb, Jw) and np.array_equal(Fb, Fw)
+    JTJ, A, rhs = ctx.lm_normal_eq(J, F, m, pr["n"], 0.5)
+    JTJw, Aw, rhsw = O.lm_normal_eq(Jw, Fw, 0.5)
+    assert np.allclose(JTJ, JTJw, rtol=1e-12, atol=1e-300) and np.allclose(rhs, rhsw, rtol=1e-12, atol=1e-300)
+
+
+def test_one_parameter_gradient_and_hessian(ctx):
+    f = ctx.functor(capi.F_POWER, (), (3,))
+    of = O.OFunctor(capi.F_POWER, (), (3,))
+    x, dx = np.array([1.7]), np.array([1e-6])
+    g, f0 = ctx.fd_gradient(f, x, dx)
+    gw, f0w = O.fd_gradient(of, x, dx)
+    assert np.array_equal(g, gw) and f0 == f0w
+    assert np.array_equal(ctx.fd_hessian(f, x, np.array([1e-3])), O.fd_hessian(of, x, np.array([1e-3])))
+
+
+def test_invalid_arguments_return_status_codes(ctx):
+    lib = ctx.lib
+    f = ctx.functor(capi.F_ROSENBROCK)
+    x = np.ones(4)
+    out = np.zeros(4)
+    # null pointers / bad sizes: PNOL_ERR_INVALID (1), never a crash or an exit()
+    assert lib.pnol_fd_gradient(ctx.h, f.handle, None, C.c_void_p(x.ctypes.data), 4, C.c_void_p(out.ctypes.data), None) == 1
+    assert lib.pnol_eval_batch(ctx.h, f.handle, C.c_void_p(x.ctypes.data), C.c_longlong(1), 0, C.c_longlong(0), None, C.c_void_p(out.ctypes.data)) == 1
+    assert lib.pnol_spd_solve(ctx.h, C.c_void_p(x.ctypes.data), C.c_void_p(x.ctypes.data), 0, C.c_void_p(out.ctypes.data), None) == 1
+    assert b"spd_solve" in lib.pnol_last_error(ctx.h)
+    # a scalar functor handed to a residual entry point, and the reverse: PNOL_ERR_NO_FUNCTOR (3)
+    F = np.zeros(4)
+    assert lib.pnol_residual_eval(ctx.h, f.handle, C.c_void_p(x.ctypes.data), 4, C.c_void_p(F.ctypes.data), None) == 3
+    with pytest.raises(capi.PnolError):
+        ctx.functor(999)
+    with pytest.raises(capi.PnolError):
+        ctx.functor(capi.F_LORENTZ_SUM, (4.0,), (), (), 10)          # data columns missing
+    with pytest.raises(capi.PnolError):
+        ctx.ga_create(f, 4, np.zeros(4), np.ones(4), 1, 5, dict(seed=1, scale=0.5))    # npop < 2
+    with pytest.raises(capi.PnolError):
+        ctx.ga_create(f, 4, np.zeros(4), np.ones(4), 100, 5, dict(seed=1, scale=0.5), elite_frac=0.6, cross_frac=0.6)   # no room for random children
+
+
+def test_nonfinite_objective_values(ctx):
+    f = ctx.functor(capi.F_ROSENBROCK)
+    of = O.OFunctor(capi.F_ROSENBROCK)
+    pts = np.array([[1.0, 2.0, 3.0], [np.nan, 1.0, 1.0], [1e200, 1.0, 1.0], [np.inf, 0.0, 0.0]])
+    got, want = ctx.eval_batch(f, pts, 4, 3), O.eval_batch(of, pts)
+    assert np.array_equal(got, want, equal_nan=True)
+    g, f0 = ctx.fd_gradient(f, pts[2], np.full(3, 1e-6))
+    gw, f0w = O.fd_gradient(of, pts[2], np.full(3, 1e-6))
+    assert np.array_equal(g, gw, equal_nan=True) and (f0 == f0w or (f0 != f0 and f0w != f0w))
+
+
+def test_lm_with_a_singular_normal_matrix(ctx):
+    # an amplitude of exactly 0 makes the column of its centre vanish: J^T J is singular, Marquardt's damping multiplies a zero
+    # diagonal, the solve reports a non-positive pivot, the step is treated like the NaN step of the reference (rejected)
+    from parallelnonlinearoptimizationlibrary_b200 import hostapi
+    hostapi.attach(ctx)
+    try:
+        pr = problems.lorentz_problem(500, 4)
+        x0 = pr["x0"].copy()
+        x0[2] = 0.0
+        r = hostapi.lm_lorentz(pr["t"], pr["y"], pr["w"], x0, 0.001, 10.0, 1e-7, 5, 0.0)
+        assert r["iterations"] == 5 and r["accepted"] == 0 and r["rejected"] == 5
+        assert np.array_equal(r["X"], x0) and np.array_equal(r["F"], r["F0"])
+        f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), 500)
+        J, F = ctx.fd_jacobian(f, x0, np.full(8, 1e-7))
+        assert np.all(J[:, 3] == 0.0)
+        _, A, rhs = ctx.lm_normal_eq(J, F, 500, 8, 1e-3)
+        with pytest.raises(capi.PnolError, match="NOT_SPD"):
+            ctx.spd_solve(A, rhs, 8)
+    finally:
+        hostapi.detach()
