@@ -10,7 +10,8 @@ m=4M,n=256; GA evals/sec; 1/2/4/8 B200").
 Workload (config.workload = "cfg5"): Levenberg-Marquardt on the tree-summed Lorentzian curve fit of SURVEY.md 8(d),
 m = 4 000 000 residuals x n = 256 parameters, FP64. One STEP = one LM iteration of
 Source/LevenbergMarquardtMPI.cpp:55-141: FD Jacobian (n+1 model evaluations per row) -> J^T J / J^T r on the FP64 tensor
-cores (+ NCCL all-reduce when row-sharded) -> damped Cholesky solve -> trial residual + chi^2 -> accept/reject on the host.
+cores (+ NCCL all-reduce when row-sharded) -> damped Cholesky solve -> trial residual + chi^2 (one C-ABI call, pnol_lm_step, one
+synchronisation) -> accept/reject on the host.
 Every step recomputes the Jacobian (as the reference does, also after a rejected step) and a fresh findMin starts every
 `--restart` steps so that every step does the full work.
 
@@ -238,7 +239,7 @@ class LMDevice:
         n, m = self.n, self.m
         self.J = ctx.malloc(m * n * 8)
         self.F, self.Ft = ctx.malloc(m * 8), ctx.malloc(m * 8)
-        self.JTJ, self.A, self.rhs = ctx.malloc(n * n * 8), ctx.malloc(n * n * 8), ctx.malloc(n * 8)
+        self.JTJ = ctx.malloc((n * n + n) * 8)          # J^T J followed by -J^T F
         self.dx = ctx.to_device(np.full(n, LM_PARAMS["dxgrad"]))
         self.x0 = pr["x0"].copy()
         self.accepted = self.rejected = 0
@@ -252,16 +253,9 @@ class LMDevice:
         self.chi = np.sqrt(ss) ** 2
 
     def step(self):
-        """one iteration of the while loop (Source/LevenbergMarquardtMPI.cpp:55-141), Jacobian always recomputed"""
-        c, n = self.ctx, self.n
-        c.fd_jacobian(self.f, self.X, self.dx, J=self.J, F=None, n=n)
-        c.lm_normal_eq(self.J, self.F, self.m, n, self.lam, JTJ=self.JTJ, A=self.A, rhs=self.rhs)
-        try:
-            sigma = c.spd_solve(self.A, self.rhs, n)
-        except self.capi.PnolError:
-            sigma = np.full(n, np.nan)
-        Xn = self.X + sigma
-        _, ss = c.residual_eval(self.f, Xn, F=self.Ft, n=n)
+        """one iteration of the while loop (Source/LevenbergMarquardtMPI.cpp:55-141), Jacobian always recomputed: the device work
+        is one pnol_lm_step call (one synchronisation), accept / reject on the host"""
+        sigma, Xn, ss, info = self.ctx.lm_step(self.f, self.X, self.dx, self.n, self.J, self.F, self.Ft, self.lam, self.JTJ)
         chi = np.sqrt(ss) ** 2
         if chi >= self.chi or chi != chi:
             self.lam *= LM_PARAMS["factor"]

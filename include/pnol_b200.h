@@ -177,6 +177,19 @@ int pnol_lm_normal_eq(pnol_ctx * ctx, const double * J, const double * F, long l
 /* re-damp only: A = JTJ with A_ii = (1 + lambda) JTJ_ii (J unchanged after a rejected step) */
 int pnol_lm_damp(pnol_ctx * ctx, const double * JTJ, int n, double lambda, double * A);
 
+/* One LM iteration's device work behind one call and ONE host synchronisation (Source/LevenbergMarquardtMPI.cpp:60-108):
+ * FD Jacobian at x -> J^T J | J^T F (+ all-reduce over the ranks) -> Marquardt damping -> Cholesky solve -> x_trial = x + sigma ->
+ * Ftrial = F(x_trial) and its sum of squares (+ all-reduce). The accept / reject decision stays with the caller as in the reference.
+ *   x, dx       host or device, n
+ *   J           device, m x n work space (m = rows of the functor); F device: residuals at x; Ftrial device: receives F(x_trial)
+ *   JTJ         device, n*n + n doubles: receives J^T J followed by -J^T F. reuse_jtj != 0: J^T J / rhs are taken from it instead of
+ *               being recomputed (x unchanged after a rejected step), only the damping is redone with the new lambda
+ *   sigma_out, x_trial_out (host, n), sumsq_trial_out, spd_info_out (host): the step, the trial point, sum Ftrial^2 over all
+ *               ranks and the Cholesky status (k > 0: pivot k not positive; the step is then NaN, which the caller's chi^2 test rejects) */
+int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J, const double * F,
+                 double * Ftrial, double lambda, int jac_mode, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
+                 double * sumsq_trial_out, int * spd_info_out);
+
 /* fused variant: J is never materialised; needs a functor with a structured Jacobian */
 int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n,
                             double lambda, double * JTJ, double * A, double * rhs, double * F);

@@ -83,7 +83,7 @@ EXPORTS = [
     "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
     "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
     "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
-    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
+    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
     "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
@@ -398,6 +398,15 @@ class Context:
         self.check(self.lib.pnol_lm_normal_eq(self.h, _ptr(J), _ptr(F), C.c_longlong(m), int(n), C.c_double(lam), _ptr(JTJ),
                                               _ptr(A), _ptr(rhs)))
         return JTJ, A, rhs
+
+    def lm_step(self, f, x, dx, n, J, F, Ftrial, lam, JTJ, jac_mode=JAC_AUTO, reuse_jtj=False):
+        """one LM iteration's device work, one synchronisation: returns (sigma, x_trial, sumsq_trial, spd_info)"""
+        x, dx = _f64(x), _f64(dx)
+        sigma, xt = np.empty(n), np.empty(n)
+        ss, info = C.c_double(), C.c_int()
+        self.check(self.lib.pnol_lm_step(self.h, f.handle, _ptr(x), _ptr(dx), int(n), _ptr(J), _ptr(F), _ptr(Ftrial), C.c_double(lam), int(jac_mode),
+                                         int(bool(reuse_jtj)), _ptr(JTJ), _ptr(sigma), _ptr(xt), C.byref(ss), C.byref(info)))
+        return sigma, xt, ss.value, info.value
 
     def spd_solve(self, A, rhs, n, x=None):
         host = x is None

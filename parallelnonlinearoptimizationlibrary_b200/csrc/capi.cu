@@ -478,6 +478,79 @@ extern "C" int pnol_lm_damp(pnol_ctx * ctx, const double * JTJ, int n, double la
 	return PNOL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One Levenberg-Marquardt iteration's device work behind ONE call and ONE host synchronisation
+// (Source/LevenbergMarquardtMPI.cpp:60-108): FD Jacobian at x -> J^T J | J^T F (+ all-reduce) -> damping -> Cholesky solve ->
+// x_trial = x + sigma -> residuals at x_trial and their sum of squares (+ all-reduce). The accept / reject decision stays with the
+// caller, exactly as in the reference. The five separate entry points above cost two synchronisations and five boundary
+// crossings per iteration, which is what is left of an iteration at 8 GPUs.
+// ---------------------------------------------------------------------------------------------------
+__global__ void lm_trial_point_kernel(const double * __restrict__ x, const double * __restrict__ sigma, const int * __restrict__ info, int n,
+                                      double * __restrict__ xt, double * __restrict__ sigma_out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	// a non-positive pivot: the reference's luSolve would have produced inf / NaN and the step would be rejected by the NaN test
+	// of its chi^2 (Source/LevenbergMarquardtMPI.cpp:110); hand back a NaN step for the same outcome
+	double s = (*info != 0) ? __longlong_as_double(0x7ff8000000000000LL) : sigma[i];
+	sigma_out[i] = s;
+	xt[i] = x[i] + s;                       // X[i] = X[i] + sigma[i]   (:97-100)
+}
+
+extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J, const double * F,
+                            double * Ftrial, double lambda, int jac_mode, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
+                            double * sumsq_trial_out, int * spd_info_out)
+{
+	if (!ctx || !f) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, x && dx && J && F && Ftrial && JTJ && n >= 1, "lm_step: bad arguments");
+	PNOL_REQUIRE(ctx, is_device_ptr(J) && is_device_ptr(F) && is_device_ptr(Ftrial) && is_device_ptr(JTJ), "lm_step: J, F, Ftrial and JTJ must be device memory");
+	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_step: the functor is not a residual model");
+	const long long m = f->params.m;
+	DevIn<double> dx_, ddx;
+	PNOL_CHECK(dx_.init(ctx, x, n));
+	PNOL_CHECK(ddx.init(ctx, dx, n));
+	// scratch, all in workspace slot 3 (slot 0: SYRK partial tiles, slot 1: the solve's factor, slot 2: sum-of-squares partials):
+	//   A (n*n) | rhs (n) | sigma (n) | xt (n) | sigma_final (n) | sumsq (2) | info (2) | packed J^T J|J^T F (n*n + n)
+	const size_t nn = (size_t) n * n;
+	const size_t packed_count = nn + n;
+	PNOL_CHECK(ws_reserve(ctx, 3, (2 * nn + 5 * (size_t) n + 16) * sizeof(double)));
+	double * A = (double *) ctx->ws[3];
+	double * rhs = A + nn, * sig = rhs + n, * xt = sig + n, * sigf = xt + n, * ss = sigf + n;
+	int * info_dev = (int *) (ss + 2);
+	double * packed = ss + 4;
+	if (!reuse_jtj) {
+		PNOL_CHECK(launch_fd_jacobian(ctx, f, dx_.get(), ddx.get(), n, J, nullptr, jac_mode));
+		PNOL_CHECK(launch_syrk(ctx, J, F, m, n, packed));
+		if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, packed, packed_count));
+		PNOL_CHECK(launch_lm_damp(ctx, packed, n, lambda, JTJ, A, rhs));
+		// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it
+		PNOL_CUDA(ctx, cudaMemcpyAsync(JTJ + nn, rhs, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	} else {
+		long long total = (long long) nn;
+		PNOL_LAUNCH(ctx, redamp_kernel, (unsigned) ((total + 255) / 256), 256, 0, JTJ, n, lambda, A);
+		PNOL_CUDA(ctx, cudaMemcpyAsync(rhs, JTJ + nn, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	PNOL_CHECK(launch_spd_solve(ctx, A, rhs, n, sig, info_dev));
+	PNOL_LAUNCH(ctx, lm_trial_point_kernel, (n + 127) / 128, 128, 0, dx_.get(), sig, info_dev, n, xt, sigf);
+	PNOL_CHECK(launch_residual(ctx, f, xt, n, Ftrial, ss));
+	if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, ss, 1));
+	// one pinned read-back: sigma | x_trial | sumsq | info
+	PNOL_CHECK(pinned_reserve(ctx, 2 * (size_t) n + 4));
+	double * pin = ctx->pinned;
+	PNOL_CUDA(ctx, cudaMemcpyAsync(pin, sigf, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + n, xt, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + 2 * n, ss, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + 2 * n + 1, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CHECK(finish(ctx));
+	if (sigma_out) memcpy(sigma_out, pin, (size_t) n * sizeof(double));
+	if (x_trial_out) memcpy(x_trial_out, pin + n, (size_t) n * sizeof(double));
+	if (sumsq_trial_out) *sumsq_trial_out = pin[2 * n];
+	int inf = 0;
+	memcpy(&inf, pin + 2 * n + 1, sizeof(int));
+	if (spd_info_out) *spd_info_out = inf;
+	return PNOL_OK;
+}
+
 extern "C" int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double,
                                        double *, double *, double *, double *)
 {

@@ -25,12 +25,12 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 	if( (long long) F0.size() != Ndata || (long long) FOpt.size() != Ndata )
 		throw Error( PNOL_ERR_INVALID, "LevMarq::findMin: F0 / FOpt must be pre-sized to the number of residuals" );
 
-	// Storage (:27-38): J and the residual vectors live on the device; there is no JT copy
-	DeviceArray J( (size_t) Ndata*Nparam ), F( Ndata ), Ftrial( Ndata ), A( (size_t) Nparam*Nparam ), JTJ( (size_t) Nparam*Nparam );
-	DeviceArray rhs( Nparam ), dXdev( Nparam ), Xdev( Nparam ), sigmaDev( Nparam );
+	// Storage (:27-38): J and the residual vectors live on the device; there is no JT copy. JTJ holds J^T J followed by -J^T F.
+	DeviceArray J( (size_t) Ndata*Nparam ), F( Ndata ), Ftrial( Ndata ), JTJ( (size_t) Nparam*Nparam + Nparam );
+	DeviceArray dXdev( Nparam );
 	vector <double> dX( Nparam, dXGrad );
 	vector <double> sigma( Nparam, 0 );
-	vector <double> Xprev( Nparam, 0 );
+	vector <double> Xprev( Nparam, 0 ), Xtrial( Nparam, 0 );
 	dXdev.upload( dX.data(), Nparam );
 
 	// Initial f values (:42-49)
@@ -46,37 +46,21 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 	report = LMReport();
 	while( iter < maxIter )
 	{
-		// Update the gradient and the normal equations (:60-85). After a rejected step the reference recomputes the
-		// identical J; re-damping the stored J^T J gives the same A.
-		if( !jacobianCurrent )
-		{
-			Xdev.upload( X.data(), Nparam );
-			rt.check( pnol_fd_jacobian( ctx, f, Xdev.data(), dXdev.data(), Nparam, J.data(), nullptr, rt.jacobianMode() ) );
-			rt.check( pnol_lm_normal_eq( ctx, J.data(), F.data(), Ndata, Nparam, lambda, JTJ.data(), A.data(), rhs.data() ) );
-			jacobianCurrent = rt.jacobianCache();
-		}
-		else
-		{
-			rt.check( pnol_lm_damp( ctx, JTJ.data(), Nparam, lambda, A.data() ) );
-		}
-
-		// Solve for sigma (:88)
+		// Gradient, normal equations, damped solve, parameter update and the trial residuals (:60-103) are one device call with
+		// one synchronisation. After a rejected step the reference recomputes the identical J (:60 after :120-129); re-damping
+		// the stored J^T J gives the same A, so that work is skipped unless the runtime asks for it (jacobianCache off).
+		// A zero / negative pivot (e.g. a zero column of J) comes back as a NaN step: the reference's luSolve would return
+		// inf/NaN there and the step would be rejected through the NaN test at :110. Same outcome here.
 		int info = 0;
-		int st = pnol_spd_solve( ctx, A.data(), rhs.data(), Nparam, sigma.data(), &info );
-		if( st == PNOL_ERR_NOT_SPD )
-		{
-			// a zero / negative pivot (e.g. a zero column of J): the reference's luSolve would return inf/NaN and the
-			// step would be rejected through the NaN test at :110. Same outcome here.
-			for( int i = 0; i < Nparam; i++ ) sigma[i] = NAN;
-		}
-		else rt.check( st );
+		rt.check( pnol_lm_step( ctx, f, X.data(), dXdev.data(), Nparam, J.data(), F.data(), Ftrial.data(), lambda, rt.jacobianMode(),
+				jacobianCurrent ? 1 : 0, JTJ.data(), sigma.data(), Xtrial.data(), &sumsq, &info ) );
+		jacobianCurrent = rt.jacobianCache();
 
-		// store previous, update parameters (:91-100)
+		// store previous, update parameters (:91-100): Xtrial[i] is X[i] + sigma[i], added on the device
 		for( int k = 0; k < Nparam; k++ ) Xprev[k] = X[k];
-		for( int i = 0; i < Nparam; i++ ) X[i] = X[i] + sigma[i];
+		for( int i = 0; i < Nparam; i++ ) X[i] = Xtrial[i];
 
-		// Update F and chi (:103-108)
-		rt.check( pnol_residual_eval( ctx, f, X.data(), Nparam, Ftrial.data(), &sumsq ) );
+		// chi (:107-108)
 		double chiSqPrev = chiSq;
 		chiSq = pow( sqrt(sumsq), 2 );
 

@@ -353,3 +353,28 @@ def test_jacobian_rows_outside_the_fast_range_fall_back(ctx):
     assert np.array_equal(F, Fw, equal_nan=True) and np.array_equal(J, Jw, equal_nan=True)
     Fr, _ = ctx.residual_eval(f, x)
     assert np.array_equal(Fr, Fw, equal_nan=True)
+
+
+def test_lm_step_equals_the_separate_calls(ctx):
+    # pnol_lm_step = fd_jacobian + lm_normal_eq + spd_solve + (x + sigma) + residual_eval behind one call / one synchronisation
+    pr = problems.lorentz_problem(3001, 16)
+    n, m = pr["n"], pr["m"]
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    dx = np.full(n, 1e-7)
+    Jd, Fd, Ft, JTJd = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
+    _, ss0 = ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+    sigma, xt, ss, info = ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-3, JTJd)
+    J, F = ctx.fd_jacobian(f, pr["x0"], dx)
+    JTJ, A, rhs = ctx.lm_normal_eq(J, F, m, n, 1e-3)
+    want = ctx.spd_solve(A, rhs, n)
+    assert info == 0 and np.array_equal(sigma, want) and np.array_equal(xt, pr["x0"] + want)
+    Fw, ssw = ctx.residual_eval(f, xt)
+    assert ss == ssw and np.array_equal(ctx.to_host(Ft, m), Fw)
+    packed = ctx.to_host(JTJd, n * n + n)
+    assert np.array_equal(packed[:n * n].reshape(n, n), JTJ) and np.array_equal(packed[n * n:], rhs)
+    # re-damping from the stored J^T J (after a rejected step) gives the step of a fresh call with the new lambda
+    s2, xt2, ss2, _ = ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-2, JTJd, reuse_jtj=True)
+    _, A2, rhs2 = ctx.lm_normal_eq(J, F, m, n, 1e-2)
+    assert np.array_equal(s2, ctx.spd_solve(A2, rhs2, n))
+    for p in (Jd, Fd, Ft, JTJd):
+        ctx.free(p)
