@@ -96,7 +96,7 @@ npop, n, gens = 1_000_000, 32, 200
 f = ctx.functor(capi.F_RASTRIGIN)
 lb, ub = np.full(n, -5.12), np.full(n, 5.12)
 ga = ctx.ga_create(f, n, lb, ub, npop, gens, dict(seed=12345, scale=1.0 - 2.0 ** -20), nstatic=1e9)
-(_, dt_init) = timed(lambda: ga.init(np.full(n, 1.0)))
+(_, dt_init) = timed(lambda: ga.init(np.full(n, 2.5)))     # f(x0) = 840: away from the integer-lattice local minima
 f_first = ga.status().f_best
 t0 = time.perf_counter()
 for _ in range(gens):
