@@ -380,7 +380,8 @@ bounds_fix_kernel(double * __restrict__ X, long long npop, int n, const double *
 // checkIndenticalChildAndReplace  (Source/GeneticAlgorithm.cpp:313-344)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-row_hash_kernel(const double * __restrict__ X, long long npop, int n, unsigned long long * __restrict__ keys, unsigned * __restrict__ vals)
+row_hash_kernel(const double * __restrict__ X, long long npop, int n, unsigned long long * __restrict__ keys, unsigned * __restrict__ vals,
+                unsigned long long * __restrict__ fullhash)
 {
 	long long row = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int lane = threadIdx.x & 31;
@@ -397,20 +398,25 @@ row_hash_kernel(const double * __restrict__ X, long long npop, int n, unsigned l
 		h += b ^ (b >> 31);                                 // order independent across lanes
 	}
 	for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-	if (lane == 0) { keys[row] = h; vals[row] = (unsigned) row; }
+	// only the top 32 bits are SORTED on (the radix sort skips the four all-zero low digits: half the passes); the full hash is
+	// compared inside the few runs of equal top halves
+	if (lane == 0) { keys[row] = h & 0xFFFFFFFF00000000ULL; fullhash[row] = h; vals[row] = (unsigned) row; }
 }
 
-// sorted by (hash, row): element s is a duplicate iff some later element of its equal-hash run has an equal row
+// sorted by (top half of the hash, row): element s is a duplicate iff some later element of its run has the same full hash and an
+// equal row
 __global__ void __launch_bounds__(256)
 dup_flag_kernel(const double * __restrict__ X, long long npop, int n, const unsigned long long * __restrict__ keys,
-                const unsigned * __restrict__ vals, unsigned * __restrict__ dupflag)
+                const unsigned * __restrict__ vals, const unsigned long long * __restrict__ fullhash, unsigned * __restrict__ dupflag)
 {
 	long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= npop) return;
 	unsigned long long h = keys[s];
 	unsigned row = vals[s];
+	const unsigned long long hf = fullhash[row];
 	unsigned flag = 0;
 	for (long long t = s + 1; t < npop && keys[t] == h; t++) {
+		if (fullhash[vals[t]] != hf) continue;
 		const double * a = X + (long long) row * n;
 		const double * b = X + (long long) vals[t] * n;
 		int same = 0;
@@ -856,9 +862,10 @@ static int ga_check_identical_dev(pnol_ctx * ctx, double * X, long long npop, in
                                   unsigned char * indicator, StreamDev st, uint64_t * pos, GaScratch & sc)
 {
 	TimerScope ts(ctx, "ga_check_identical");
-	PNOL_LAUNCH(ctx, row_hash_kernel, (unsigned) ((npop * 32 + 255) / 256), 256, 0, X, npop, n, sc.keys, sc.perm);
+	// sc.u64a carries the full hashes until the flags are known; the scan below then reuses it for the offsets
+	PNOL_LAUNCH(ctx, row_hash_kernel, (unsigned) ((npop * 32 + 255) / 256), 256, 0, X, npop, n, sc.keys, sc.perm, sc.u64a);
 	PNOL_CHECK(radix_sort_pairs(ctx, sc.keys, sc.perm, npop, *sc.sort));
-	PNOL_LAUNCH(ctx, dup_flag_kernel, (unsigned) ((npop + 255) / 256), 256, 0, X, npop, n, sc.keys, sc.perm, sc.u32a);
+	PNOL_LAUNCH(ctx, dup_flag_kernel, (unsigned) ((npop + 255) / 256), 256, 0, X, npop, n, sc.keys, sc.perm, sc.u64a, sc.u32a);
 	PNOL_CHECK(exclusive_scan_u32(ctx, sc.u32a, npop, sc.u64a, sc.scan_tmp, sc.total_dev));
 	unsigned long long total = 0;
 	PNOL_CUDA(ctx, cudaMemcpyAsync(&total, sc.total_dev, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
