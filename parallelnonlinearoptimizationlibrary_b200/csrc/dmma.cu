@@ -13,6 +13,9 @@
 // banks per half-warp. For SYRK the A and B fragments come from the SAME staged rows of J.
 #include "common.cuh"
 
+#include <cuda.h>
+#include <stdlib.h>
+
 #ifndef SYRK_KC
 #define SYRK_KC 32
 #define SYRK_STAGES 3
@@ -71,6 +74,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, unsigned parity)
 	} while (!done);
 }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// one arrival plus the announcement of `bytes` of TMA traffic that will complete on this barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t * bar, unsigned bytes)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// TMA tile loads (SASS UTMALDG): box of a 3-D / 1-D tensor map into shared memory, completion by byte count on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void * smem_dst, const CUtensorMap * map, int c0, int c1, int c2, uint64_t * bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+	             ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void * smem_dst, const CUtensorMap * map, int c0, uint64_t * bar)
+{
+	asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];\n"
+	             ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------
 // SYRK
@@ -251,6 +271,177 @@ syrk_kernel(const double * __restrict__ J, const double * __restrict__ Fv, long 
 	if (rhs_col >= 0) part_rhs[(size_t) wk.slot * kBT + rhs_col] = rhs_acc;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SYRK fed by the TMA (n a multiple of 16, J 16-byte aligned). Same roles, warp tiles and split-K as syrk_kernel; what changes
+// is how the stage ring is filled: ONE thread issues, per chunk of 32 rows, ONE tensor-map copy per operand plus one 1-D copy of
+// F, all completing on the stage's `full` mbarrier by byte count. J is described to the TMA as a 3-D tensor
+// {16 columns, m rows, n/16 column groups} so that a single 32 KB box {16, 32, 8} lands in shared memory as eight dense
+// [32 rows][16 columns] sub-tiles, each with 128-byte rows and SWIZZLE_128B (eight separate 4 KB 2-D boxes per operand were
+// measured feed-bound: 10.5 ms, the TMA handles about one small box per 0.4 us). No thread computes a copy address, nobody but
+// the hardware arrives on `full` (the LDGSTS ring pays 512 asynchronous arrivals and 4096 16-byte copies per chunk: 0.31 +
+// 0.54 ms of its 8.5 ms in timing experiments), rows beyond m arrive as zeros from the TMA's bounds check, and the tile needs
+// no padding: the swizzle makes the DMMA fragment loads conflict-free provided a k-step takes rows {r, r+2, r+4, r+6} of an
+// 8-row group -- any row order is a valid k order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTBoxCols = 16;                         // 16 doubles = 128 bytes: the swizzle span
+constexpr int kTBoxElems = 32 * kTBoxCols;            // one sub-tile: 32 rows x 16 columns
+struct SyrkTmaStage {
+	double A[kBT / kTBoxCols][kTBoxElems];
+	double B[kBT / kTBoxCols][kTBoxElems];
+	double F[32];
+	double pad[96];                                   // keeps every stage 1024-byte aligned (swizzle atom)
+};
+
+// element (row k of the chunk, column c of the 128-wide operand tile) inside an operand of a stage, in doubles
+__device__ __forceinline__ int tma_tile_off(int c, int k)
+{
+	return (c >> 4) * kTBoxElems + k * kTBoxCols + ((((c & 15) >> 1) ^ (k & 7)) << 1) + (c & 1);
+}
+
+template <bool kLower>
+__device__ __forceinline__ void warp_tile_chunk_tma(double (&acc)[4][4][2], const double * __restrict__ Ab, const double * __restrict__ Bb,
+                                                    const int (&lp)[2][2])
+{
+#pragma unroll
+	for (int t = 0; t < 8; t++) {
+		// k-step t: rows (t >> 1) * 8 + 2 (lane & 3) + (t & 1); the lane-dependent part of the address is in lp
+		const int rb = (t >> 1) * 8 * kTBoxCols;
+		double a[4], b[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+#pragma unroll
+		for (int j = 0; j < 4; j++) b[j] = Bb[(j >> 1) * kTBoxElems + rb + lp[j & 1][t & 1]];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				if (!kLower || j <= i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+	}
+}
+
+__global__ void __launch_bounds__(kDmmaThreads, 1)
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmF, int haveF, long long m, int n,
+                const SyrkWork * __restrict__ work, double * __restrict__ part_tiles, double * __restrict__ part_rhs)
+{
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	SyrkTmaStage * stages = reinterpret_cast<SyrkTmaStage *>(smem_raw);
+	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
+
+	const SyrkWork wk = work[blockIdx.x];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool diag = wk.bi == wk.bj;
+	//                         warp:  0  1  2  3   4  5  6  7   8  9 10 11  12 13 14 15      (see syrk_kernel)
+	const int diag_wi[16] =         { 1, 2, 3, 3,  2, 3, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
+	const int diag_wj[16] =         { 0, 1, 1, 2,  0, 0, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
+	const int diag_idle_ord[16] =   {-1,-1,-1,-1, -1,-1,-1,-1,  0, 1,-1,-1,  2, 3, 4, 5};
+	const int wi = diag ? diag_wi[warp] : (warp >> 2);
+	const int wj = diag ? diag_wj[warp] : (warp & 3);
+	const bool active = wi >= 0;
+	const bool diagwarp = diag && wi == wj;
+	int rhs_col = -1;
+	if (diag && !active) {
+		int t = diag_idle_ord[warp] * 32 + lane;
+		if (t < kBT) rhs_col = t;
+	}
+	double rhs_acc = 0;
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+
+	// lane part of the fragment addresses: row 2 (lane & 3) + p of its 8-row group, column (lane >> 2) of an 8-column tile that
+	// starts at column 0 or 8 of its sub-tile (ib), swizzled
+	int lp[2][2];
+	{
+		const int g = lane >> 2, j2 = 2 * (lane & 3);
+#pragma unroll
+		for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+			for (int pp = 0; pp < 2; pp++) lp[ib][pp] = (j2 + pp) * kTBoxCols + (((ib * 4 + (g >> 1)) ^ (j2 + pp)) << 1) + (g & 1);
+	}
+
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kDmmaThreads / 32); }
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	__syncthreads();
+
+	const long long nloc = wk.chunk1 - wk.chunk0;
+	const int grpA = wk.bi * (kBT / kTBoxCols), grpB = wk.bj * (kBT / kTBoxCols);
+	const unsigned tx_bytes = (unsigned) (sizeof(double) * kBT * 32 * (diag ? 1 : 2) + ((diag && haveF) ? 32 * sizeof(double) : 0));
+	// executed by ONE thread: fill stage (rel % kSStages) with chunk rel
+	auto produce = [&](long long rel) {
+		const int s = (int) (rel % kSStages);
+		SyrkTmaStage & st = stages[s];
+		const int row0 = (int) ((wk.chunk0 + rel) * 32);
+		mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+		tma_load_3d(&st.A[0][0], &tmJ, 0, row0, grpA, &full_bar[s]);
+		if (!diag) tma_load_3d(&st.B[0][0], &tmJ, 0, row0, grpB, &full_bar[s]);
+		else if (haveF) tma_load_1d(st.F, &tmF, row0, &full_bar[s]);
+	};
+
+	if (tid == 0)
+		for (long long r = 0; r < kSStages - 1 && r < nloc; r++) produce(r);
+
+	for (long long rel = 0; rel < nloc; rel++) {
+		const int s = (int) (rel % kSStages);
+		// duty thread of this iteration (rotating over the warps; an idle warp in a diagonal tile): refill the stage everybody read
+		// in iteration rel - 1 with chunk rel + kSStages - 1
+		const long long nxt = rel + kSStages - 1;
+		const int duty = diag ? 8 : (int) (rel & 15);
+		if (warp == duty && lane == 0 && nxt < nloc) {
+			if (rel >= 1) mbar_wait(&empty_bar[(int) (nxt % kSStages)], (unsigned) (((rel - 1) / kSStages) & 1));
+			produce(nxt);
+		}
+		__syncwarp();
+		mbar_wait(&full_bar[s], (unsigned) ((rel / kSStages) & 1));
+		const SyrkTmaStage & st = stages[s];
+		if (active) {
+			const double * Ab = &st.A[0][0] + (wi * 32 / kTBoxCols) * kTBoxElems;
+			const double * Bb = (diag ? &st.A[0][0] : &st.B[0][0]) + (wj * 32 / kTBoxCols) * kTBoxElems;
+			if (diagwarp) warp_tile_chunk_tma<true>(acc, Ab, Bb, lp);
+			else warp_tile_chunk_tma<false>(acc, Ab, Bb, lp);
+		} else if (rhs_col >= 0 && haveF) {
+			const double * A0 = &st.A[0][0];
+#pragma unroll
+			for (int k = 0; k < 32; k++) rhs_acc = fma(A0[tma_tile_off(rhs_col, k)], st.F[k], rhs_acc);
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty_bar[s]);
+	}
+
+	double * tile = part_tiles + (size_t) wk.slot * kBT * kBT;
+	if (active) {
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (diagwarp && j > i) continue;
+				int p = wi * 32 + i * 8 + (lane >> 2);
+				int q = wj * 32 + j * 8 + 2 * (lane & 3);
+				*reinterpret_cast<double2 *>(tile + p * kBT + q) = make_double2(acc[i][j][0], acc[i][j][1]);
+			}
+	}
+	if (rhs_col >= 0) part_rhs[(size_t) wk.slot * kBT + rhs_col] = rhs_acc;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+static PFN_encodeTiled tensor_map_encoder()
+{
+	static PFN_encodeTiled fn = [] {
+		void * p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+		return (PFN_encodeTiled) p;
+	}();
+	return fn;
+}
+
 // packed[p*n + q] (and its mirror) = sum over the role's slots, in slot order; packed[n*n + p] = sum of rhs partials
 __global__ void __launch_bounds__(256)
 syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __restrict__ part_rhs,
@@ -363,7 +554,38 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	size_t smem = sizeof(SyrkStage) * kSStages;
 	{
 		TimerScope ts(ctx, "syrk");
-		if (vec16) {
+		// TMA-fed kernel when the layout allows the 3-D tensor map (n a multiple of 16); PNOL_SYRK_LEGACY=1 forces the LDGSTS ring
+		// (A/B timing runs)
+		static const int legacy = [] { const char * e = getenv("PNOL_SYRK_LEGACY"); return e ? atoi(e) : 0; }();
+		bool done = false;
+		if (vec16 && !legacy && n % kTBoxCols == 0 && m > 0 && m < (1LL << 31) && tensor_map_encoder()) {
+			CUtensorMap tmJ, tmF;
+			cuuint64_t dimJ[3] = {(cuuint64_t) kTBoxCols, (cuuint64_t) m, (cuuint64_t) (n / kTBoxCols)};
+			cuuint64_t strJ[2] = {(cuuint64_t) n * sizeof(double), (cuuint64_t) kTBoxCols * sizeof(double)};
+			cuuint32_t boxJ[3] = {kTBoxCols, 32, kBT / kTBoxCols};
+			cuuint32_t es3[3] = {1, 1, 1};
+			CUresult r1 = tensor_map_encoder()(&tmJ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *) J, dimJ, strJ, boxJ, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			CUresult r2 = CUDA_SUCCESS;
+			const bool haveF = F != nullptr && (((size_t) F) & 15) == 0;
+			if (haveF) {
+				cuuint64_t dimF[1] = {(cuuint64_t) m};
+				cuuint64_t strF[1] = {0};
+				cuuint32_t boxF[1] = {32};
+				cuuint32_t es1[1] = {1};
+				r2 = tensor_map_encoder()(&tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 1, (void *) F, dimF, strF, boxF, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
+				                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			} else tmF = tmJ;
+			if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && (F == nullptr || haveF)) {
+				size_t smem_t = sizeof(SyrkTmaStage) * kSStages + 1024;
+				auto kern = syrk_tma_kernel;
+				PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
+				PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem_t, tmJ, tmF, haveF ? 1 : 0, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
+				done = true;
+			}
+		}
+		if (done) {
+		} else if (vec16) {
 			auto kern = syrk_kernel<true>;
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 			PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
