@@ -11,7 +11,8 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpnol_b200.so")
+# PNOL_B200_LIB: a differently built libpnol_b200.so (kernel tuning runs, tools/build_variants.sh); the product path is lib/
+LIB_PATH = os.environ.get("PNOL_B200_LIB") or os.path.join(_HERE, "lib", "libpnol_b200.so")
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libpnol_b200_host.so")
 
 PNOL_OK = 0

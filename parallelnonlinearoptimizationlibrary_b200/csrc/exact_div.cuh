@@ -83,6 +83,14 @@ __device__ __forceinline__ int div_exact_x_ok(double x)
 	const unsigned h = (unsigned) __double2hiint(x) & 0x7fffffffu;
 	return (int) ((h - 0x14300000u) < 0x57800000u) | is_zero_bits(x);       // 2^-700 <= |x| < 2^700, or a zero
 }
+// 2^-700 <= |x| < 2^700 or x = +0: for these the five operations of div_exact_core end in the IEEE quotient without the final
+// selection (x = +0: q0 = +-0 with the quotient's sign, both residuals are +0 and fma(+0, r, q0) keeps q0; x = -0 would end in
+// +0 for a positive divisor, so it is sent to the ordinary division)
+__device__ __forceinline__ int div_exact_x_ok_pz(double x)
+{
+	const unsigned h = (unsigned) __double2hiint(x);
+	return (int) (((h & 0x7fffffffu) - 0x14300000u) < 0x57800000u) | (int) ((h | (unsigned) __double2loint(x)) == 0u);
+}
 __device__ __forceinline__ double div_exact_core(double x, const RecipDiv & rd)
 {
 	const double q0 = x * rd.r;
