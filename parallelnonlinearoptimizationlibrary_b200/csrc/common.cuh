@@ -40,6 +40,7 @@ struct pnol_ctx {
 	size_t syrk_plan_bytes = 0;
 	long long syrk_plan_m = -1;
 	int syrk_plan_n = -1;
+	int syrk_plan_kind = -1;       // 0: one role per CTA (LDGSTS kernel), 1 / 2: stream-K segments (TMA kernel) without / with J^T F
 
 	// communicator
 	ncclComm * comm = nullptr;

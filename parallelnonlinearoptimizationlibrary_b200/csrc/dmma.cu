@@ -20,6 +20,9 @@
 #define SYRK_KC 32
 #define SYRK_STAGES 3
 #endif
+#ifndef SYRK_NO_RHS
+#define SYRK_NO_RHS 0         // timing experiments only
+#endif
 
 namespace pnol {
 
@@ -298,9 +301,16 @@ __device__ __forceinline__ int tma_tile_off(int c, int k)
 	return (c >> 4) * kTBoxElems + k * kTBoxCols + ((((c & 15) >> 1) ^ (k & 7)) << 1) + (c & 1);
 }
 
+// kLower: diagonal warp tile (only j <= i); its A and B fragments are the same columns of J. With Fl != nullptr the warp also sums
+// J^T F for its 32 columns ON THE TENSOR PIPE: one more DMMA per 8 columns and k-step whose B fragment is F in column 0 (lanes
+// 0-3 hold F[row of k = lane & 3], every other lane 0), accumulated in the tiles acc[0][1..3] and acc[1][2] that a diagonal warp
+// tile leaves unused; lane 4 g ends with (J^T F)[i * 8 + g] in the first element. Fl = stage F + 2 (lane & 3).
+// Why not DFMA: a DFMA in a DMMA warp costs far more than its two issue cycles (four per k-step out of the A fragments: +0.21 ..
+// 0.45 us on a 2.31 us chunk; 32-deep chains in four extra or idle warps paced the whole chunk: 3.07 us; 128 per chunk in one
+// service warp: 11.5 ms per kernel), the four extra DMMA cost their 4/34.
 template <bool kLower>
 __device__ __forceinline__ void warp_tile_chunk_tma(double (&acc)[4][4][2], const double * __restrict__ Ab, const double * __restrict__ Bb,
-                                                    const int (&lp)[2][2])
+                                                    const int (&lp)[2][2], const double * __restrict__ Fl = nullptr, bool flane = false)
 {
 #pragma unroll
 	for (int t = 0; t < 8; t++) {
@@ -310,45 +320,105 @@ __device__ __forceinline__ void warp_tile_chunk_tma(double (&acc)[4][4][2], cons
 #pragma unroll
 		for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
 #pragma unroll
-		for (int j = 0; j < 4; j++) b[j] = Bb[(j >> 1) * kTBoxElems + rb + lp[j & 1][t & 1]];
+		for (int j = 0; j < 4; j++) b[j] = kLower ? a[j] : Bb[(j >> 1) * kTBoxElems + rb + lp[j & 1][t & 1]];
 #pragma unroll
 		for (int i = 0; i < 4; i++)
 #pragma unroll
 			for (int j = 0; j < 4; j++)
 				if (!kLower || j <= i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+		if (kLower && Fl != nullptr) {
+			const double bf = flane ? Fl[(t >> 1) * 8 + (t & 1)] : 0.0;
+			dmma_8x8x4(acc[0][1][0], acc[0][1][1], a[0], bf);
+			dmma_8x8x4(acc[0][2][0], acc[0][2][1], a[1], bf);
+			dmma_8x8x4(acc[0][3][0], acc[0][3][1], a[2], bf);
+			dmma_8x8x4(acc[1][2][0], acc[1][2][1], a[3], bf);
+		}
+	}
+}
+// 32 x 16 half of a warp tile (4 x 2 DMMA tiles): Bb points at the 16-column sub-tile
+__device__ __forceinline__ void warp_half_tile_chunk_tma(double (&acc)[4][4][2], const double * __restrict__ Ab, const double * __restrict__ Bb,
+                                                         const int (&lp)[2][2])
+{
+#pragma unroll
+	for (int t = 0; t < 8; t++) {
+		const int rb = (t >> 1) * 8 * kTBoxCols;
+		double a[4], b[2];
+#pragma unroll
+		for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+#pragma unroll
+		for (int j = 0; j < 2; j++) b[j] = Bb[rb + lp[j][t & 1]];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 2; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 	}
 }
 
-__global__ void __launch_bounds__(kDmmaThreads, 1)
+// Work of one CTA: a run of SEGMENTS (tile role, K-chunk range, partial-result slot). The host deals the chunks of all roles out
+// as one stream in cost units (a diagonal tile's chunk is cheaper than an off-diagonal one), every CTA takes an equal share of
+// the stream and therefore crosses at most a few role boundaries (stream-K); the stage ring keeps running across a boundary.
+// With one role per CTA the 148 CTAs cannot be split 40.7 : 66.6 : 40.7, which is what the measured chunk times ask for
+// (8.38 ms at 39:70:39, 8.10 ms at 41:66:41).
+constexpr int kSyrkMaxSeg = 8;
+
+// 16 DMMA warps + one warpgroup whose first warp is the service warp. Registers: the CTA is launched with 96 per thread (640
+// threads = a pool of 61440; setmaxnreg only moves registers inside the CTA's pool, the SM's other 4096 stay out of reach), the
+// service warpgroup shrinks to 32 (4096) and the four DMMA warpgroups grow to 112 each (57344): the pool to the last register.
+// (A first version shrank to 40 only: the DMMA warps spun in USETMAXREG.TRY_ALLOC forever.)
+constexpr int kSyrkTmaThreads = kDmmaThreads + 128;
+constexpr int kSyrkRingWarps = kDmmaThreads / 32;        // warps that release a stage
+
+__global__ void __launch_bounds__(kSyrkTmaThreads, 1)
 syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmF, int haveF, long long m, int n,
-                const SyrkWork * __restrict__ work, double * __restrict__ part_tiles, double * __restrict__ part_rhs)
+                const SyrkWork * __restrict__ segs, const int * __restrict__ cta_seg0, double * __restrict__ part_tiles,
+                double * __restrict__ part_rhs)
 {
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	SyrkTmaStage * stages = reinterpret_cast<SyrkTmaStage *>(smem_raw);
 	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
+	__shared__ SyrkWork sseg[kSyrkMaxSeg];
 
-	const SyrkWork wk = work[blockIdx.x];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const bool diag = wk.bi == wk.bj;
-	//                         warp:  0  1  2  3   4  5  6  7   8  9 10 11  12 13 14 15      (see syrk_kernel)
-	const int diag_wi[16] =         { 1, 2, 3, 3,  2, 3, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
-	const int diag_wj[16] =         { 0, 1, 1, 2,  0, 0, 0, 2, -1,-1, 1, 3, -1,-1,-1,-1};
-	const int diag_idle_ord[16] =   {-1,-1,-1,-1, -1,-1,-1,-1,  0, 1,-1,-1,  2, 3, 4, 5};
-	const int wi = diag ? diag_wi[warp] : (warp >> 2);
-	const int wj = diag ? diag_wj[warp] : (warp & 3);
-	const bool active = wi >= 0;
-	const bool diagwarp = diag && wi == wj;
-	int rhs_col = -1;
-	if (diag && !active) {
-		int t = diag_idle_ord[warp] * 32 + lane;
-		if (t < kBT) rhs_col = t;
+	const int seg0 = cta_seg0[blockIdx.x];
+	const int nseg = cta_seg0[blockIdx.x + 1] - seg0;
+	if (nseg <= 0) return;
+	if (tid < nseg) sseg[tid] = segs[seg0 + tid];
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kSyrkRingWarps); }
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 	}
-	double rhs_acc = 0;
-	double acc[4][4][2];
-#pragma unroll
-	for (int i = 0; i < 4; i++)
-#pragma unroll
-		for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+	__syncthreads();
+
+	if (warp >= kDmmaThreads / 32) {
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+		if (warp > kDmmaThreads / 32) return;
+		// ---- service warp: feeds the stage ring. A DMMA warp that waits for a stage to drain before it refills it stops feeding
+		// its sub-partition; here the DMMA warps only ever wait for data. (32-bit counters: m < 2^31 rows = 2^26 chunks.)
+		if (lane == 0) {
+			int gp = 0;                  // chunk of the CTA's stream to produce next
+			for (int sg = 0; sg < nseg; sg++) {
+				const SyrkWork w = sseg[sg];
+				const bool dg = w.bi == w.bj;
+				const unsigned tx_bytes = (unsigned) (sizeof(double) * kBT * 32 * (dg ? 1 : 2) + ((dg && haveF) ? 32 * sizeof(double) : 0));
+				const int nloc = (int) (w.chunk1 - w.chunk0);
+				for (int c = 0; c < nloc; c++, gp++) {
+					const int s = gp % kSStages;
+					// stage s last held chunk gp - kSStages: wait until all DMMA warps have released it
+					if (gp >= kSStages) mbar_wait(&empty_bar[s], (unsigned) (((gp / kSStages) - 1) & 1));
+					SyrkTmaStage & st = stages[s];
+					const int row0 = ((int) w.chunk0 + c) * 32;
+					mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+					tma_load_3d(&st.A[0][0], &tmJ, 0, row0, w.bi * (kBT / kTBoxCols), &full_bar[s]);
+					if (!dg) tma_load_3d(&st.B[0][0], &tmJ, 0, row0, w.bj * (kBT / kTBoxCols), &full_bar[s]);
+					else if (haveF) tma_load_1d(st.F, &tmF, row0, &full_bar[s]);
+				}
+			}
+		}
+		return;
+	}
+
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
 
 	// lane part of the fragment addresses: row 2 (lane & 3) + p of its 8-row group, column (lane >> 2) of an 8-column tile that
 	// starts at column 0 or 8 of its sub-tile (ib), swizzled
@@ -361,70 +431,60 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__
 			for (int pp = 0; pp < 2; pp++) lp[ib][pp] = (j2 + pp) * kTBoxCols + (((ib * 4 + (g >> 1)) ^ (j2 + pp)) << 1) + (g & 1);
 	}
 
-	if (tid == 0) {
+	// warp -> work inside a tile.  Off-diagonal tile: 4 x 4 warp tiles of 32 x 32.  Diagonal tile (136 of 256 DMMA tiles live):
+	// warps 0-3 take the diagonal warp tiles (10 DMMA per k-step), warps 4-15 one 32 x 16 HALF of the six full warp tiles
+	// (8 DMMA): every sub-partition (warp % 4) carries 10 + 3 x 8 = 34 DMMA per k-step with four resident warps. (The earlier
+	// deal left 6 warps idle and 36 on the busiest sub-partition; its chunk took 0.611 of an off-diagonal one, this one 0.557.)
+	// full warp tile t = 0..5 -> (wi, wj) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+	const int ht = (warp - 4) >> 1;
+	const int half_wi = ht < 1 ? 1 : (ht < 3 ? 2 : 3);
+	const int half_wj = ht - half_wi * (half_wi - 1) / 2;
+
+	long long g = 0;
+	for (int sg = 0; sg < nseg; sg++) {
+		const SyrkWork wk = sseg[sg];
+		const bool diag = wk.bi == wk.bj;
+		int mode, wi, wj, hh = 0;      // mode 0: full warp tile, 1: diagonal warp tile, 2: half warp tile
+		if (!diag) { mode = 0; wi = warp >> 2; wj = warp & 3; }
+		else if (warp < 4) { mode = 1; wi = warp; wj = warp; }
+		else { mode = 2; wi = half_wi; wj = half_wj; hh = (warp - 4) & 1; }
+		const bool do_rhs = mode == 1 && haveF && !SYRK_NO_RHS;
+		double acc[4][4][2];
+
 #pragma unroll
-		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kDmmaThreads / 32); }
-		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-	}
-	__syncthreads();
-
-	const long long nloc = wk.chunk1 - wk.chunk0;
-	const int grpA = wk.bi * (kBT / kTBoxCols), grpB = wk.bj * (kBT / kTBoxCols);
-	const unsigned tx_bytes = (unsigned) (sizeof(double) * kBT * 32 * (diag ? 1 : 2) + ((diag && haveF) ? 32 * sizeof(double) : 0));
-	// executed by ONE thread: fill stage (rel % kSStages) with chunk rel
-	auto produce = [&](long long rel) {
-		const int s = (int) (rel % kSStages);
-		SyrkTmaStage & st = stages[s];
-		const int row0 = (int) ((wk.chunk0 + rel) * 32);
-		mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-		tma_load_3d(&st.A[0][0], &tmJ, 0, row0, grpA, &full_bar[s]);
-		if (!diag) tma_load_3d(&st.B[0][0], &tmJ, 0, row0, grpB, &full_bar[s]);
-		else if (haveF) tma_load_1d(st.F, &tmF, row0, &full_bar[s]);
-	};
-
-	if (tid == 0)
-		for (long long r = 0; r < kSStages - 1 && r < nloc; r++) produce(r);
-
-	for (long long rel = 0; rel < nloc; rel++) {
-		const int s = (int) (rel % kSStages);
-		// duty thread of this iteration (rotating over the warps; an idle warp in a diagonal tile): refill the stage everybody read
-		// in iteration rel - 1 with chunk rel + kSStages - 1
-		const long long nxt = rel + kSStages - 1;
-		const int duty = diag ? 8 : (int) (rel & 15);
-		if (warp == duty && lane == 0 && nxt < nloc) {
-			if (rel >= 1) mbar_wait(&empty_bar[(int) (nxt % kSStages)], (unsigned) (((rel - 1) / kSStages) & 1));
-			produce(nxt);
-		}
-		__syncwarp();
-		mbar_wait(&full_bar[s], (unsigned) ((rel / kSStages) & 1));
-		const SyrkTmaStage & st = stages[s];
-		if (active) {
-			const double * Ab = &st.A[0][0] + (wi * 32 / kTBoxCols) * kTBoxElems;
-			const double * Bb = (diag ? &st.A[0][0] : &st.B[0][0]) + (wj * 32 / kTBoxCols) * kTBoxElems;
-			if (diagwarp) warp_tile_chunk_tma<true>(acc, Ab, Bb, lp);
-			else warp_tile_chunk_tma<false>(acc, Ab, Bb, lp);
-		} else if (rhs_col >= 0 && haveF) {
-			const double * A0 = &st.A[0][0];
+		for (int i = 0; i < 4; i++)
 #pragma unroll
-			for (int k = 0; k < 32; k++) rhs_acc = fma(A0[tma_tile_off(rhs_col, k)], st.F[k], rhs_acc);
-		}
-		__syncwarp();
-		if (lane == 0) mbar_arrive(&empty_bar[s]);
-	}
+			for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
 
-	double * tile = part_tiles + (size_t) wk.slot * kBT * kBT;
-	if (active) {
+		const long long nloc = wk.chunk1 - wk.chunk0;
+		for (long long c = 0; c < nloc; c++, g++) {
+			const int s = (int) (g % kSStages);
+			mbar_wait(&full_bar[s], (unsigned) ((g / kSStages) & 1));
+			const SyrkTmaStage & st = stages[s];
+			const double * Ab = &st.A[0][0] + (wi * 2) * kTBoxElems;
+			if (mode == 0) warp_tile_chunk_tma<false>(acc, Ab, &st.B[0][0] + (wj * 2) * kTBoxElems, lp);
+			else if (mode == 1) warp_tile_chunk_tma<true>(acc, Ab, Ab, lp, do_rhs ? st.F + 2 * (lane & 3) : nullptr, lane < 4);
+			else warp_half_tile_chunk_tma(acc, Ab, &st.A[0][0] + (wj * 2 + hh) * kTBoxElems, lp);
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty_bar[s]);
+		}
+
+		// partial tile -> workspace slot (row-major 128 x 128; a diagonal tile only defines its lower triangle)
+		double * tile = part_tiles + (size_t) wk.slot * kBT * kBT;
 #pragma unroll
 		for (int i = 0; i < 4; i++)
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				if (diagwarp && j > i) continue;
-				int p = wi * 32 + i * 8 + (lane >> 2);
-				int q = wj * 32 + j * 8 + 2 * (lane & 3);
+				if ((mode == 1 && j > i) || (mode == 2 && j > 1)) continue;
+				const int p = wi * 32 + i * 8 + (lane >> 2);
+				const int q = wj * 32 + (mode == 2 ? hh * 16 : 0) + j * 8 + 2 * (lane & 3);
 				*reinterpret_cast<double2 *>(tile + p * kBT + q) = make_double2(acc[i][j][0], acc[i][j][1]);
 			}
+		if (do_rhs && (lane & 3) == 0) {
+			double * pr = part_rhs + (size_t) wk.slot * kBT + wi * 32 + (lane >> 2);
+			pr[0] = acc[0][1][0]; pr[8] = acc[0][2][0]; pr[16] = acc[0][3][0]; pr[24] = acc[1][2][0];
+		}
 	}
-	if (rhs_col >= 0) part_rhs[(size_t) wk.slot * kBT + rhs_col] = rhs_acc;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -479,20 +539,81 @@ syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __rest
 int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed)
 {
 	PNOL_REQUIRE(ctx, n >= 1 && m >= 0, "syrk: bad shape m=%lld n=%d", m, n);
+	static const int no_f = [] { const char * e = getenv("PNOL_SYRK_NOF"); return e ? atoi(e) : 0; }();      // timing runs: J^T J only
+	if (no_f) F = nullptr;
 	const int nb = (n + kBT - 1) / kBT;
 	const int nroles = nb * (nb + 1) / 2;
 	const long long nchunks = (m + kSKC - 1) / kSKC;
+	const int grid_cap = ctx->sm_count;
 
-	// CTA budget per role, proportional to the time one K chunk takes there (busiest sub-partition)
-	int grid_cap = ctx->sm_count;
-	std::vector<int> nslots(nroles), slot0(nroles);
-	{
+	// TMA-fed stream-K kernel when the layout allows the 3-D tensor map (n a multiple of 16, 16-byte aligned J); otherwise, or with
+	// PNOL_SYRK_LEGACY=1 (A/B timing runs), the LDGSTS ring with one role per CTA
+	static const int legacy = [] { const char * e = getenv("PNOL_SYRK_LEGACY"); return e ? atoi(e) : 0; }();
+	const bool vec16 = (n % 2 == 0) && ((((size_t) J) & 15) == 0);
+	const bool haveF = F != nullptr && (((size_t) F) & 15) == 0;
+	static_assert(kSKC == 32, "the TMA kernel's chunk is 32 rows");
+	const bool use_tma = vec16 && !legacy && n % kTBoxCols == 0 && m > 0 && m < (1LL << 31) && (F == nullptr || haveF) &&
+	                     tensor_map_encoder() != nullptr;
+
+	// relative cost of one K chunk of a role: DMMA per k-step on the busiest sub-partition, 64 in an off-diagonal tile. Diagonal
+	// tiles of the TMA kernel: 34, or 38 with the J^T F tiles (measured chunk times: 34.6 and 40.6 balance the two kinds of segment);
+	// LDGSTS kernel: 36. PNOL_SYRK_WDIAG overrides (tuning runs)
+	static const double wdiag_env = [] { const char * e = getenv("PNOL_SYRK_WDIAG"); return e ? atof(e) : 0.0; }();
+	const int plan_kind = use_tma ? (haveF ? 2 : 1) : 0;
+	const double wdiag = wdiag_env > 0 ? wdiag_env : (plan_kind == 2 ? 40.6 : plan_kind == 1 ? 34.6 : 36.0);
+
+	std::vector<SyrkWork> work;
+	std::vector<int> nslots(nroles, 0), slot0(nroles, 0), cta_seg0;
+	int grid = 0;
+	if (use_tma) {
+		// stream-K: the chunks of all roles as one stream in cost units, an equal share per CTA
+		double total = 0;
+		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) total += ((bi == bj) ? wdiag : 64.0) * (double) nchunks;
+		long long units = (long long) nroles * nchunks;
+		grid = (int) (units < grid_cap ? (units > 0 ? units : 1) : grid_cap);
+		cta_seg0.assign(grid + 1, 0);
+		double cum = 0;          // cost dealt out so far
+		int r = 0, bi = 0, bj = 0;
+		long long pos = 0;       // next chunk of role r
+		for (int c = 0; c < grid; c++) {
+			cta_seg0[c] = (int) work.size();
+			const double target = total * (double) (c + 1) / (double) grid;
+			int segs_here = 0;
+			while (r < nroles && segs_here < kSyrkMaxSeg) {
+				const double cost = (bi == bj) ? wdiag : 64.0;
+				long long take;
+				if (c == grid - 1 && segs_here == kSyrkMaxSeg - 1) take = nchunks - pos;
+				else {
+					take = (long long) ((target - cum) / cost + 0.5);
+					if (c == grid - 1) take = nchunks - pos;
+					if (take > nchunks - pos) take = nchunks - pos;
+				}
+				if (take <= 0) break;
+				SyrkWork w;
+				w.bi = bi; w.bj = bj; w.slot = (int) work.size(); w.pad = 0;
+				w.chunk0 = pos; w.chunk1 = pos + take;
+				work.push_back(w);
+				if (nslots[r] == 0) slot0[r] = w.slot;
+				nslots[r]++;
+				segs_here++;
+				cum += cost * (double) take;
+				pos += take;
+				if (pos == nchunks) {
+					pos = 0; r++;
+					if (++bj > bi) { bj = 0; bi++; }
+				} else break;
+			}
+		}
+		cta_seg0[grid] = (int) work.size();
+		PNOL_REQUIRE(ctx, r == nroles, "syrk: internal: stream-K plan left work undistributed (m=%lld n=%d)", m, n);
+	} else {
+		// one role per CTA: CTA budget per role proportional to its chunk cost
 		double wsum = 0;
-		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) wsum += (bi == bj) ? 36.0 : 64.0;
+		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) wsum += (bi == bj) ? wdiag : 64.0;
 		int used = 0;
 		for (int bi = 0, r = 0; bi < nb; bi++)
 			for (int bj = 0; bj <= bi; bj++, r++) {
-				double w = (bi == bj) ? 36.0 : 64.0;   // DMMA per k-step on the busiest sub-partition
+				double w = (bi == bj) ? wdiag : 64.0;
 				int c = (int) (grid_cap * w / wsum + 0.5);
 				if (c < 1) c = 1;
 				if ((long long) c > nchunks) c = (int) (nchunks > 0 ? nchunks : 1);
@@ -505,31 +626,34 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 			if (nslots[big] <= 1) break;
 			nslots[big]--; used--;
 		}
-		int s = 0;
-		for (int r = 0; r < nroles; r++) { slot0[r] = s; s += nslots[r]; }
+		int sl = 0;
+		for (int r = 0; r < nroles; r++) { slot0[r] = sl; sl += nslots[r]; }
+		work.resize(sl);
+		for (int bi = 0, r = 0; bi < nb; bi++)
+			for (int bj = 0; bj <= bi; bj++, r++)
+				for (int k = 0; k < nslots[r]; k++) {
+					SyrkWork & w = work[slot0[r] + k];
+					w.bi = bi; w.bj = bj; w.slot = slot0[r] + k; w.pad = 0;
+					w.chunk0 = nchunks * k / nslots[r];
+					w.chunk1 = nchunks * (k + 1) / nslots[r];
+				}
+		grid = sl;
+		cta_seg0.assign(1, 0);
 	}
-	int total_slots = slot0[nroles - 1] + nslots[nroles - 1];
+	const int total_slots = (int) work.size();
 
-	std::vector<SyrkWork> work(total_slots);
-	for (int bi = 0, r = 0; bi < nb; bi++)
-		for (int bj = 0; bj <= bi; bj++, r++)
-			for (int k = 0; k < nslots[r]; k++) {
-				SyrkWork & w = work[slot0[r] + k];
-				w.bi = bi; w.bj = bj; w.slot = slot0[r] + k; w.pad = 0;
-				w.chunk0 = nchunks * k / nslots[r];
-				w.chunk1 = nchunks * (k + 1) / nslots[r];
-			}
-
-	size_t bytes_work = total_slots * sizeof(SyrkWork);
+	size_t bytes_work = (size_t) total_slots * sizeof(SyrkWork);
 	size_t bytes_roles = (size_t) 2 * nroles * sizeof(int);
+	size_t bytes_cta = cta_seg0.size() * sizeof(int);
 	size_t bytes_tiles = (size_t) total_slots * kBT * kBT * sizeof(double);
 	size_t bytes_rhs = (size_t) total_slots * kBT * sizeof(double);
 	size_t off_roles = (bytes_work + 255) & ~(size_t) 255;
+	size_t off_cta = (off_roles + bytes_roles + 255) & ~(size_t) 255;
 	PNOL_CHECK(ws_reserve(ctx, 0, bytes_tiles + bytes_rhs));
-	// the descriptor tables depend on (m, n) only: upload them once per shape (an LM run repeats one shape), so that the
+	// the descriptor tables depend on (m, n, kernel) only: upload them once per shape (an LM run repeats one shape), so that the
 	// launch does not have to wait for the stream to drain on every call
-	if (ctx->syrk_plan_m != m || ctx->syrk_plan_n != n) {
-		size_t need = off_roles + bytes_roles;
+	if (ctx->syrk_plan_m != m || ctx->syrk_plan_n != n || ctx->syrk_plan_kind != plan_kind) {
+		size_t need = off_cta + bytes_cta;
 		if (need > ctx->syrk_plan_bytes) {
 			PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			if (ctx->syrk_plan) PNOL_CUDA(ctx, cudaFree(ctx->syrk_plan));
@@ -542,23 +666,19 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 		unsigned char * plan = (unsigned char *) ctx->syrk_plan;
 		PNOL_CUDA(ctx, cudaMemcpyAsync(plan, work.data(), bytes_work, cudaMemcpyHostToDevice, ctx->stream));
 		PNOL_CUDA(ctx, cudaMemcpyAsync(plan + off_roles, roles.data(), bytes_roles, cudaMemcpyHostToDevice, ctx->stream));
+		PNOL_CUDA(ctx, cudaMemcpyAsync(plan + off_cta, cta_seg0.data(), bytes_cta, cudaMemcpyHostToDevice, ctx->stream));
 		PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors die at scope exit
-		ctx->syrk_plan_m = m; ctx->syrk_plan_n = n;
+		ctx->syrk_plan_m = m; ctx->syrk_plan_n = n; ctx->syrk_plan_kind = plan_kind;
 	}
 	unsigned char * ws = (unsigned char *) ctx->syrk_plan;
 	double * part_tiles = (double *) ctx->ws[0];
 	double * part_rhs = (double *) ((unsigned char *) ctx->ws[0] + bytes_tiles);
 	PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));
 
-	const bool vec16 = (n % 2 == 0) && ((((size_t) J) & 15) == 0);
-	size_t smem = sizeof(SyrkStage) * kSStages;
 	{
 		TimerScope ts(ctx, "syrk");
-		// TMA-fed kernel when the layout allows the 3-D tensor map (n a multiple of 16); PNOL_SYRK_LEGACY=1 forces the LDGSTS ring
-		// (A/B timing runs)
-		static const int legacy = [] { const char * e = getenv("PNOL_SYRK_LEGACY"); return e ? atoi(e) : 0; }();
 		bool done = false;
-		if (vec16 && !legacy && n % kTBoxCols == 0 && m > 0 && m < (1LL << 31) && tensor_map_encoder()) {
+		if (use_tma) {
 			CUtensorMap tmJ, tmF;
 			cuuint64_t dimJ[3] = {(cuuint64_t) kTBoxCols, (cuuint64_t) m, (cuuint64_t) (n / kTBoxCols)};
 			cuuint64_t strJ[2] = {(cuuint64_t) n * sizeof(double), (cuuint64_t) kTBoxCols * sizeof(double)};
@@ -567,7 +687,6 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 			CUresult r1 = tensor_map_encoder()(&tmJ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *) J, dimJ, strJ, boxJ, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
 			                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			CUresult r2 = CUDA_SUCCESS;
-			const bool haveF = F != nullptr && (((size_t) F) & 15) == 0;
 			if (haveF) {
 				cuuint64_t dimF[1] = {(cuuint64_t) m};
 				cuuint64_t strF[1] = {0};
@@ -576,23 +695,24 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 				r2 = tensor_map_encoder()(&tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 1, (void *) F, dimF, strF, boxF, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
 				                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			} else tmF = tmJ;
-			if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS && (F == nullptr || haveF)) {
-				size_t smem_t = sizeof(SyrkTmaStage) * kSStages + 1024;
-				auto kern = syrk_tma_kernel;
-				PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
-				PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem_t, tmJ, tmF, haveF ? 1 : 0, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
-				done = true;
-			}
+			PNOL_REQUIRE(ctx, r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "syrk: cuTensorMapEncodeTiled failed (%d, %d) for m=%lld n=%d", (int) r1, (int) r2, m, n);
+			size_t smem_t = sizeof(SyrkTmaStage) * kSStages + 1024;
+			auto kern = syrk_tma_kernel;
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
+			PNOL_LAUNCH(ctx, kern, grid, kSyrkTmaThreads, smem_t, tmJ, tmF, haveF ? 1 : 0, m, n, (const SyrkWork *) ws, (const int *) (ws + off_cta),
+			            part_tiles, part_rhs);
+			done = true;
 		}
+		size_t smem = sizeof(SyrkStage) * kSStages;
 		if (done) {
 		} else if (vec16) {
 			auto kern = syrk_kernel<true>;
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
+			PNOL_LAUNCH(ctx, kern, grid, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
 		} else {
 			auto kern = syrk_kernel<false>;
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			PNOL_LAUNCH(ctx, kern, total_slots, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
+			PNOL_LAUNCH(ctx, kern, grid, kDmmaThreads, smem, J, F, m, n, (const SyrkWork *) ws, part_tiles, part_rhs);
 		}
 	}
 	{
