@@ -87,7 +87,7 @@ extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 	cudaStreamSynchronize(ctx->stream);
 	timers_collect(ctx);
 	comm_destroy(ctx);
-	for (int s = 0; s < 4; s++) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+	for (int s = 0; s < 5; s++) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
 	if (ctx->syrk_plan) cudaFree(ctx->syrk_plan);
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	cudaStreamSynchronize(ctx->stream);
@@ -509,7 +509,8 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	DevIn<double> dx_, ddx;
 	PNOL_CHECK(dx_.init(ctx, x, n));
 	PNOL_CHECK(ddx.init(ctx, dx, n));
-	// scratch, all in workspace slot 3 (slot 0: SYRK partial tiles, slot 1: the solve's factor, slot 2: sum-of-squares partials):
+	// scratch, all in workspace slot 3 (slot 0: SYRK partial tiles, slot 1: the solve's factor, slot 2: sum-of-squares partials,
+	// slot 4: the Jacobian kernel's J^T F block partials):
 	//   A (n*n) | rhs (n) | sigma (n) | xt (n) | sigma_final (n) | sumsq (2) | info (2) | packed J^T J|J^T F (n*n + n)
 	const size_t nn = (size_t) n * n;
 	const size_t packed_count = nn + n;
@@ -519,8 +520,13 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	int * info_dev = (int *) (ss + 2);
 	double * packed = ss + 4;
 	if (!reuse_jtj) {
-		PNOL_CHECK(launch_fd_jacobian(ctx, f, dx_.get(), ddx.get(), n, J, nullptr, jac_mode));
-		PNOL_CHECK(launch_syrk(ctx, J, F, m, n, packed));
+		// J^T F: summed by the structured Jacobian kernel while it holds the rows of J (cheap there); the black-box kernel leaves
+		// it to the SYRK (extra tensor tiles). Either way it ends behind J^T J in `packed`, before the all-reduce.
+		bool jtf_done = false;
+		double * jtf = sig;      // free until the solve
+		PNOL_CHECK(launch_fd_jacobian(ctx, f, dx_.get(), ddx.get(), n, J, nullptr, jac_mode, F, jtf, &jtf_done));
+		PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed));
+		if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 		if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, packed, packed_count));
 		PNOL_CHECK(launch_lm_damp(ctx, packed, n, lambda, JTJ, A, rhs));
 		// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it

@@ -29,8 +29,8 @@ struct pnol_ctx {
 	uint64_t launches = 0;
 
 	// grow-only scratch buffers (device)
-	void * ws[4] = {nullptr, nullptr, nullptr, nullptr};
-	size_t ws_bytes[4] = {0, 0, 0, 0};
+	void * ws[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	size_t ws_bytes[5] = {0, 0, 0, 0, 0};
 	// pinned staging for small scalar read-backs
 	double * pinned = nullptr;
 	size_t pinned_doubles = 0;
@@ -237,7 +237,7 @@ int launch_alpha_pool(pnol_ctx * ctx, const pnol_functor * f, const double * xfu
 
 int launch_residual(pnol_ctx * ctx, const pnol_functor * f, const double * x, int n, double * F, double * sumsq_dev);
 int launch_fd_jacobian(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J,
-                       double * F, int mode);
+                       double * F, int mode, const double * Fw = nullptr, double * jtf_out = nullptr, bool * jtf_done = nullptr);
 
 int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed /* n*n + n */);
 int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs);
