@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: one FD Jacobian + one normal-equation assembly at the cfg5 shape and one 1M x 32
+"""Small fixed workload for ncu: LM iterations (pnol_lm_step) + one stand-alone normal-equation assembly at the cfg5 shape and one 1M x 32
 Rastrigin sweep. Run plain first, then under ncu (see profiles/README.md)."""
 import os
 import sys
@@ -15,13 +15,15 @@ ctx = capi.Context(0)
 pr = problems.lorentz_problem(m, K)
 n = pr["n"]
 f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
-Jd, Fd = ctx.malloc(m * n * 8), ctx.malloc(m * 8)
-xd, dxd = ctx.to_device(pr["x0"]), ctx.to_device(np.full(n, 1e-7))
-A, rhs = ctx.malloc(n * n * 8), ctx.malloc(n * 8)
+Jd, Fd, Ft, JTJd = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
+dx = np.full(n, 1e-7)
+ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+# one LM iteration as the LM classes and bench.py run it (Jacobian + J^T F, SYRK, damped solve, trial residual) ...
 for _ in range(2):
-    ctx.fd_jacobian(f, xd, dxd, J=Jd, F=Fd, n=n)
-    ctx.lm_normal_eq(Jd, Fd, m, n, 1e-3, A=A, rhs=rhs)
-    ctx.spd_solve(A, rhs, n, x=rhs)
+    ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-3, JTJd)
+# ... and the stand-alone normal-equation call on a given (J, F): the SYRK sums J^T F itself (extra tensor tiles)
+A, rhs = ctx.malloc(n * n * 8), ctx.malloc(n * 8)
+ctx.lm_normal_eq(Jd, Fd, m, n, 1e-3, A=A, rhs=rhs)
 B, nd = 1_000_000, 32
 pts = ctx.to_device(np.random.default_rng(0).uniform(-5.12, 5.12, size=(B, nd)))
 fo = ctx.malloc(B * 8)
