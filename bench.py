@@ -255,19 +255,16 @@ class LMDevice:
         _, ss = self.ctx.residual_eval(self.f, self.X, F=self.F, n=self.n)
         self.chi = np.sqrt(ss) ** 2
 
-    def step(self):
-        """one iteration of the while loop (Source/LevenbergMarquardtMPI.cpp:55-141), Jacobian always recomputed: the device work
-        is one pnol_lm_step call (one synchronisation), accept / reject on the host"""
-        sigma, Xn, ss, info = self.ctx.lm_step(self.f, self.X, self.dx, self.n, self.J, self.F, self.Ft, self.lam, self.JTJ)
-        chi = np.sqrt(ss) ** 2
-        if chi >= self.chi or chi != chi:
-            self.lam *= LM_PARAMS["factor"]
-            self.rejected += 1
-        else:
-            self.lam /= LM_PARAMS["factor"]
-            self.X, self.chi = Xn, chi
+    def step(self, k=1):
+        """k iterations of the while loop (Source/LevenbergMarquardtMPI.cpp:55-141), Jacobian always recomputed: per iteration the
+        device work is one pnol_lm_step (one synchronisation) and the accept / reject decision is taken on the host, in C++
+        (pnol_lm_iterate) -- no interpreter between two iterations"""
+        self.X, self.lam, self.chi, acc, rej, swapped = self.ctx.lm_iterate(self.f, self.X, self.dx, self.n, self.J, self.F, self.Ft, self.JTJ,
+                                                                            self.lam, self.chi, LM_PARAMS["factor"], k)
+        if swapped:
             self.F, self.Ft = self.Ft, self.F
-            self.accepted += 1
+        self.accepted += acc
+        self.rejected += rej
 
 
 def run_ours(args):
@@ -307,10 +304,13 @@ def run_ours(args):
 
     # ---- value: device-resident steps -----------------------------------------------------------------------------
     def run_steps(k, counter0=0):
-        for i in range(k):
+        i = 0
+        while i < k:
             if (counter0 + i) % args.restart == 0:
                 prob.start()
-            prob.step()
+            run = min(k - i, args.restart - (counter0 + i) % args.restart)      # up to the next findMin restart
+            prob.step(run)
+            i += run
 
     run_steps(args.warmup)
     dmma_peak = ctx.measure_dmma_peak()

@@ -190,6 +190,15 @@ int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const
                  double * Ftrial, double lambda, int jac_mode, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
                  double * sumsq_trial_out, int * spd_info_out);
 
+/* `iterations` LM iterations on device-resident state (J, F, Ftrial, JTJ as in pnol_lm_step), the accept / reject decision of
+ * Source/LevenbergMarquardtMPI.cpp:107-141 on the host between them: chi^2 = pow(sqrt(sum Ftrial^2), 2); chi^2 >= previous or NaN ->
+ * lambda *= factor, x and F stay; otherwise lambda /= factor, x = x_trial, F <-> Ftrial (pointer swap) and, with x_min_diff > 0, stop
+ * once ||sigma||_2 < x_min_diff (:138-140). The Jacobian is recomputed in every iteration as in the reference (:60).
+ *   x (host, n) in/out; lambda_inout, chisq_inout in/out; swapped_out: 1 when the current residuals ended in `Ftrial` */
+int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const double * dx, int n, double * J, double * F, double * Ftrial,
+                    double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
+                    int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out);
+
 /* fused variant: J is never materialised; needs a functor with a structured Jacobian */
 int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n,
                             double lambda, double * JTJ, double * A, double * rhs, double * F);

@@ -84,7 +84,7 @@ EXPORTS = [
     "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
     "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
     "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
-    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
+    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
     "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
@@ -408,6 +408,17 @@ class Context:
         self.check(self.lib.pnol_lm_step(self.h, f.handle, _ptr(x), _ptr(dx), int(n), _ptr(J), _ptr(F), _ptr(Ftrial), C.c_double(lam), int(jac_mode),
                                          int(bool(reuse_jtj)), _ptr(JTJ), _ptr(sigma), _ptr(xt), C.byref(ss), C.byref(info)))
         return sigma, xt, ss.value, info.value
+
+    def lm_iterate(self, f, x, dx, n, J, F, Ftrial, JTJ, lam, chisq, factor, iterations, x_min_diff=0.0, jac_mode=JAC_AUTO):
+        """`iterations` LM iterations on device-resident state, accept / reject on the host in C++:
+        returns (x, lambda, chisq, accepted, rejected, swapped)"""
+        x = np.array(x, dtype=np.float64)
+        lam_c, chi_c = C.c_double(lam), C.c_double(chisq)
+        acc, rej, sw = C.c_int(), C.c_int(), C.c_int()
+        self.check(self.lib.pnol_lm_iterate(self.h, f.handle, _ptr(x), _ptr(dx), int(n), _ptr(J), _ptr(F), _ptr(Ftrial), _ptr(JTJ),
+                                            C.byref(lam_c), C.byref(chi_c), C.c_double(factor), C.c_double(x_min_diff), int(iterations),
+                                            int(jac_mode), C.byref(acc), C.byref(rej), C.byref(sw)))
+        return x, lam_c.value, chi_c.value, acc.value, rej.value, sw.value
 
     def spd_solve(self, A, rhs, n, x=None):
         host = x is None

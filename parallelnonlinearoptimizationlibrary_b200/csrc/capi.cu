@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" glue of include/pnol_b200.h: context, memory, functors, and the evaluation / LM / BFGS
 // entry points (the GA entry points live in ga.cu, the communicator in comm.cu).
 #include "common.cuh"
+#include <vector>
 #include "exact_div.cuh"
 
 #include <math.h>
@@ -540,20 +541,63 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	PNOL_LAUNCH(ctx, lm_trial_point_kernel, (n + 127) / 128, 128, 0, dx_.get(), sig, info_dev, n, xt, sigf);
 	PNOL_CHECK(launch_residual(ctx, f, xt, n, Ftrial, ss));
 	if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, ss, 1));
-	// one pinned read-back: sigma | x_trial | sumsq | info
+	// one pinned read-back of the contiguous scratch [x_trial | sigma | sumsq (2) | info (2)]
 	PNOL_CHECK(pinned_reserve(ctx, 2 * (size_t) n + 4));
 	double * pin = ctx->pinned;
-	PNOL_CUDA(ctx, cudaMemcpyAsync(pin, sigf, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + n, xt, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + 2 * n, ss, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-	PNOL_CUDA(ctx, cudaMemcpyAsync(pin + 2 * n + 1, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(pin, xt, (2 * (size_t) n + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	PNOL_CHECK(finish(ctx));
-	if (sigma_out) memcpy(sigma_out, pin, (size_t) n * sizeof(double));
-	if (x_trial_out) memcpy(x_trial_out, pin + n, (size_t) n * sizeof(double));
+	if (x_trial_out) memcpy(x_trial_out, pin, (size_t) n * sizeof(double));
+	if (sigma_out) memcpy(sigma_out, pin + n, (size_t) n * sizeof(double));
 	if (sumsq_trial_out) *sumsq_trial_out = pin[2 * n];
 	int inf = 0;
-	memcpy(&inf, pin + 2 * n + 1, sizeof(int));
+	memcpy(&inf, pin + 2 * n + 2, sizeof(int));
 	if (spd_info_out) *spd_info_out = inf;
+	return PNOL_OK;
+}
+
+// A run of LM iterations on device-resident state with the accept / reject decision of Source/LevenbergMarquardtMPI.cpp:107-141 on
+// the host, in C++ (the LM classes' loop without their host-vector prologue / epilogue; bench.py's device-resident arm drives it so
+// that no interpreter sits between two iterations).
+extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const double * dx, int n, double * J, double * F,
+                               double * Ftrial, double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor,
+                               double x_min_diff, int iterations, int jac_mode, int * accepted_out, int * rejected_out,
+                               int * swapped_out)
+{
+	if (!ctx || !f) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, x && dx && lambda_inout && chisq_inout && iterations >= 0 && n >= 1, "lm_iterate: bad arguments");
+	PNOL_REQUIRE(ctx, !is_device_ptr(x), "lm_iterate: x is the host's in/out parameter vector");
+	std::vector<double> sigma(n), xt(n);
+	double lambda = *lambda_inout, chisq = *chisq_inout;
+	int acc = 0, rej = 0, swapped = 0;
+	double * Fc = F, * Ft = Ftrial;
+	for (int it = 0; it < iterations; it++) {
+		double ss = 0;
+		int info = 0;
+		PNOL_CHECK(pnol_lm_step(ctx, f, x, dx, n, J, Fc, Ft, lambda, jac_mode, 0, JTJ, sigma.data(), xt.data(), &ss, &info));
+		const double chi_prev = chisq;
+		const double chi = pow(sqrt(ss), 2);                     // pow(vector2Norm(F),2)  (:108)
+		if (chi >= chi_prev || chi != chi) {                     // (:110) X and F stay, lambda grows (:118-129)
+			lambda = lambda * lambda_factor;
+			rej++;
+		} else {                                                 // (:132-141)
+			lambda = lambda / lambda_factor;
+			chisq = chi;
+			for (int i = 0; i < n; i++) x[i] = xt[i];
+			double * t = Fc; Fc = Ft; Ft = t;                    // the trial residuals become F (pointer swap instead of the copy at :91-94)
+			swapped ^= 1;
+			acc++;
+			if (x_min_diff > 0) {
+				double s2 = 0;
+				for (int i = 0; i < n; i++) s2 = s2 + sigma[i] * sigma[i];
+				if (sqrt(s2) < x_min_diff) break;
+			}
+		}
+	}
+	*lambda_inout = lambda;
+	*chisq_inout = chisq;
+	if (accepted_out) *accepted_out = acc;
+	if (rejected_out) *rejected_out = rej;
+	if (swapped_out) *swapped_out = swapped;                     // 1: the current residuals are in `Ftrial`
 	return PNOL_OK;
 }
 

@@ -382,3 +382,43 @@ def test_lm_step_equals_the_separate_calls(ctx):
     assert np.array_equal(s2, ctx.spd_solve(A2, packed[n * n:], n))
     for p in (Jd, Fd, Ft, JTJd):
         ctx.free(p)
+
+
+def test_lm_iterate_equals_stepping_with_the_decision_in_python(ctx):
+    # pnol_lm_iterate = pnol_lm_step + the accept / reject rule of Source/LevenbergMarquardtMPI.cpp:107-141 in C++
+    pr = problems.lorentz_problem(2000, 8)
+    n, m = pr["n"], pr["m"]
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    dx = np.full(n, 1e-7)
+    factor, iters = 10.0, 9
+
+    def fresh():
+        J, F, Ft, JTJ = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
+        _, ss = ctx.residual_eval(f, pr["x0"], F=F, n=n)
+        return J, F, Ft, JTJ, np.sqrt(ss) ** 2
+
+    J, F, Ft, JTJ, chi = fresh()
+    X, lam, acc, rej = pr["x0"].copy(), 1e-3, 0, 0
+    for _ in range(iters):
+        sigma, Xn, ss, info = ctx.lm_step(f, X, dx, n, J, F, Ft, lam, JTJ)
+        c = np.sqrt(ss) ** 2
+        if c >= chi or c != c:
+            lam, rej = lam * factor, rej + 1
+        else:
+            lam, X, chi, acc = lam / factor, Xn, c, acc + 1
+            F, Ft = Ft, F
+    Fpy = ctx.to_host(F, m)
+    for p in (J, F, Ft, JTJ):
+        ctx.free(p)
+
+    J, F, Ft, JTJ, chi0 = fresh()
+    X2, lam2, chi2, acc2, rej2, swapped = ctx.lm_iterate(f, pr["x0"], dx, n, J, F, Ft, JTJ, 1e-3, chi0, factor, iters)
+    assert (acc2, rej2) == (acc, rej) and acc > 0 and swapped == acc % 2
+    assert np.array_equal(X2, X) and lam2 == lam and chi2 == chi
+    assert np.array_equal(ctx.to_host(Ft if swapped else F, m), Fpy)
+    # the stopping rule: with a huge x_min_diff the run ends after the first accepted step
+    X3, _, _, acc3, rej3, _ = ctx.lm_iterate(f, pr["x0"], dx, n, J, Ft if swapped else F, F if swapped else Ft, JTJ, 1e-3, chi2, factor, iters,
+                                             x_min_diff=1e30)
+    assert acc3 <= 1
+    for p in (J, F, Ft, JTJ):
+        ctx.free(p)
