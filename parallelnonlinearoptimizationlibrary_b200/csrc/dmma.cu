@@ -487,6 +487,193 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SYRK on CTA PAIRS for two tile rows (128 < n <= 256), J^T J only: J is read from HBM ONCE.
+// The stream-K kernel above gives every tile role its own CTAs, so a row of J is fetched by the CTAs of (0,0), (1,0) and (1,1):
+// 16.3 GB for an 8.2 GB Jacobian (tensor-bound, so the time does not show it). Here a cluster of two CTAs owns a row range and each
+// chunk of 32 full rows (64 KB) lands in BOTH CTAs' shared memory through two multicast TMA copies (CTA r issues column groups
+// 8 r .. 8 r + 7). CTA r accumulates the diagonal tile (r, r) -- same warp deal as above: 34 DMMA per k-step and sub-partition --
+// and rows 64 r .. 64 r + 63 of the off-diagonal tile (1, 0) -- one 32 x 16 piece per warp: 32 more -- so every sub-partition of
+// every SM carries 66 DMMA per k-step and the row ranges are simply equal.
+// Ring protocol: full[s] (1 arrival + 64 KB of transactions: the own copy and the peer's) as before; empty[s] counts the 32 DMMA
+// warps of BOTH CTAs, because a CTA's copy also overwrites the peer's stage (remote arrivals through mapa / shared::cluster).
+// ---------------------------------------------------------------------------------------------------
+struct SyrkPairStage {
+	double T[2 * kBT / kTBoxCols][kTBoxElems];        // 16 sub-tiles of 32 rows x 16 columns
+};
+
+__device__ __forceinline__ unsigned pair_cluster_ctarank()
+{
+	unsigned r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void pair_cluster_sync()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one arrival on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster. Default (CTA-scope release) semantics
+// as in CUTLASS' ClusterBarrier::arrive(cta_id): the arrival only says "my reads of the stage are done" -- they are, their values
+// fed the DMMA issued before it -- and a cluster-scope release costs a MEMBAR.GPU per warp and chunk.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t * bar, unsigned rank)
+{
+	asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n"
+	             ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_multicast(void * smem_dst, const CUtensorMap * map, int c0, int c1, int c2, uint64_t * bar,
+                                                      unsigned short cta_mask)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;\n"
+	             ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+	               "r"((unsigned) __cvta_generic_to_shared(bar)), "h"(cta_mask) : "memory");
+}
+
+// 4 x 2 DMMA tiles of a k-step loop over one chunk: A sub-tile pair Ab (32 columns), B sub-tile Bb (16 columns)
+__device__ __forceinline__ void pair_half_tile(double (&acc)[4][2][2], const double * __restrict__ Ab, const double * __restrict__ Bb,
+                                               const int (&lp)[2][2], int t)
+{
+	const int rb = (t >> 1) * 8 * kTBoxCols;
+	double a[4], b[2];
+#pragma unroll
+	for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+#pragma unroll
+	for (int j = 0; j < 2; j++) b[j] = Bb[rb + lp[j][t & 1]];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 2; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSyrkTmaThreads, 1)
+syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int nclusters, double * __restrict__ part_tiles)
+{
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	SyrkPairStage * stages = reinterpret_cast<SyrkPairStage *>(smem_raw);
+	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned rank = pair_cluster_ctarank();
+	const int cl = blockIdx.x >> 1;
+	const long long chunk0 = nchunks * cl / nclusters, chunk1 = nchunks * (cl + 1) / nclusters;
+	const int nloc = (int) (chunk1 - chunk0);
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2 * kSyrkRingWarps); }
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	pair_cluster_sync();      // both CTAs' barriers exist before anybody copies into or arrives on the peer
+
+	if (warp >= kDmmaThreads / 32) {
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+		if (warp == kDmmaThreads / 32 && lane == 0) {
+			// producer: this CTA's half of every chunk, multicast to both CTAs
+			for (int g = 0; g < nloc; g++) {
+				const int s = g % kSStages;
+				if (g >= kSStages) mbar_wait(&empty_bar[s], (unsigned) (((g / kSStages) - 1) & 1));
+				mbar_arrive_expect_tx(&full_bar[s], (unsigned) sizeof(SyrkPairStage));
+				tma_load_3d_multicast(&stages[s].T[8 * rank][0], &tmJ, 0, (int) ((chunk0 + g) * 32), (int) (8 * rank), &full_bar[s], (unsigned short) 3);
+			}
+		}
+		__syncwarp();      // the producer's warp meets again before the (warp-aligned) cluster barrier below
+	} else {
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+		int lp[2][2];
+		{
+			const int g = lane >> 2, j2 = 2 * (lane & 3);
+#pragma unroll
+			for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+				for (int pp = 0; pp < 2; pp++) lp[ib][pp] = (j2 + pp) * kTBoxCols + (((ib * 4 + (g >> 1)) ^ (j2 + pp)) << 1) + (g & 1);
+		}
+		// off-diagonal piece of this warp: rows (of the output tile (1,0)) 64 rank + 32 rg .. + 31, columns 16 cg .. + 15
+		const int rg = warp & 1, cg = warp >> 1;
+		const int offA = (8 + 4 * (int) rank + 2 * rg) * kTBoxElems, offB = cg * kTBoxElems;
+		const int dbase = 8 * (int) rank;                 // first sub-tile of the diagonal tile's columns
+		double accO[4][2][2];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 2; j++) { accO[i][j][0] = 0; accO[i][j][1] = 0; }
+		double * tileO = part_tiles + (size_t) (nclusters + cl) * kBT * kBT;
+		double * tileD = part_tiles + (size_t) ((rank ? 2 * nclusters : 0) + cl) * kBT * kBT;
+
+		if (warp < 4) {
+			// diagonal warp tile (wi = wj = warp): 10 DMMA, A fragments double as B fragments
+			double acc[4][4][2];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+			const int offD = (dbase + 2 * warp) * kTBoxElems;
+			for (int g = 0; g < nloc; g++) {
+				const int s = g % kSStages;
+				mbar_wait(&full_bar[s], (unsigned) ((g / kSStages) & 1));
+				const double * T0 = &stages[s].T[0][0];
+#pragma unroll
+				for (int t = 0; t < 8; t++) {
+					const int rb = (t >> 1) * 8 * kTBoxCols;
+					double a[4];
+#pragma unroll
+					for (int i = 0; i < 4; i++) a[i] = T0[offD + (i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+#pragma unroll
+					for (int i = 0; i < 4; i++)
+#pragma unroll
+						for (int j = 0; j <= i; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], a[j]);
+					pair_half_tile(accO, T0 + offA, T0 + offB, lp, t);
+				}
+				__syncwarp();
+				if (lane == 0) { mbar_arrive(&empty_bar[s]); mbar_arrive_cluster(&empty_bar[s], rank ^ 1u); }
+			}
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j <= i; j++) {
+					const int p = warp * 32 + i * 8 + (lane >> 2), q = warp * 32 + j * 8 + 2 * (lane & 3);
+					*reinterpret_cast<double2 *>(tileD + p * kBT + q) = make_double2(acc[i][j][0], acc[i][j][1]);
+				}
+		} else {
+			// half of a full warp tile of the diagonal tile: 8 DMMA
+			const int ht = (warp - 4) >> 1, hh = (warp - 4) & 1;
+			const int wi = ht < 1 ? 1 : (ht < 3 ? 2 : 3);
+			const int wj = ht - wi * (wi - 1) / 2;
+			const int offDa = (dbase + 2 * wi) * kTBoxElems, offDb = (dbase + 2 * wj + hh) * kTBoxElems;
+			double acc[4][2][2];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 2; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+			for (int g = 0; g < nloc; g++) {
+				const int s = g % kSStages;
+				mbar_wait(&full_bar[s], (unsigned) ((g / kSStages) & 1));
+				const double * T0 = &stages[s].T[0][0];
+#pragma unroll
+				for (int t = 0; t < 8; t++) {
+					pair_half_tile(acc, T0 + offDa, T0 + offDb, lp, t);
+					pair_half_tile(accO, T0 + offA, T0 + offB, lp, t);
+				}
+				__syncwarp();
+				if (lane == 0) { mbar_arrive(&empty_bar[s]); mbar_arrive_cluster(&empty_bar[s], rank ^ 1u); }
+			}
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 2; j++) {
+					const int p = wi * 32 + i * 8 + (lane >> 2), q = wj * 32 + hh * 16 + j * 8 + 2 * (lane & 3);
+					*reinterpret_cast<double2 *>(tileD + p * kBT + q) = make_double2(acc[i][j][0], acc[i][j][1]);
+				}
+		}
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 2; j++) {
+				const int p = 64 * (int) rank + 32 * rg + i * 8 + (lane >> 2), q = 16 * cg + j * 8 + 2 * (lane & 3);
+				*reinterpret_cast<double2 *>(tileO + p * kBT + q) = make_double2(accO[i][j][0], accO[i][j][1]);
+			}
+	}
+	// nobody leaves while the peer may still copy into this CTA's stages or arrive on its barriers
+	pair_cluster_sync();
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -559,13 +746,25 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	// tiles of the TMA kernel: 34, or 38 with the J^T F tiles (measured chunk times: 34.6 and 40.6 balance the two kinds of segment);
 	// LDGSTS kernel: 36. PNOL_SYRK_WDIAG overrides (tuning runs)
 	static const double wdiag_env = [] { const char * e = getenv("PNOL_SYRK_WDIAG"); return e ? atof(e) : 0.0; }();
-	const int plan_kind = use_tma ? (haveF ? 2 : 1) : 0;
+	// two tile rows and no F: the CTA-pair kernel (J read once); PNOL_SYRK_NO_PAIR=1 keeps the stream-K kernel (A/B runs)
+	static const int no_pair = [] { const char * e = getenv("PNOL_SYRK_NO_PAIR"); return e ? atoi(e) : 0; }();
+	const bool use_pair = use_tma && nb == 2 && F == nullptr && !no_pair && ctx->sm_count >= 2;
+	const int plan_kind = use_pair ? 3 : use_tma ? (haveF ? 2 : 1) : 0;
 	const double wdiag = wdiag_env > 0 ? wdiag_env : (plan_kind == 2 ? 40.6 : plan_kind == 1 ? 34.6 : 36.0);
 
 	std::vector<SyrkWork> work;
 	std::vector<int> nslots(nroles, 0), slot0(nroles, 0), cta_seg0;
 	int grid = 0;
-	if (use_tma) {
+	int nclusters = 0;
+	if (use_pair) {
+		// one cluster of two CTAs per equal row range; slots: role (0,0) <- rank 0, role (1,0) <- both ranks, role (1,1) <- rank 1
+		nclusters = (int) (nchunks < ctx->sm_count / 2 ? nchunks : ctx->sm_count / 2);
+		grid = 2 * nclusters;
+		for (int r = 0; r < 3; r++) { slot0[r] = r * nclusters; nslots[r] = nclusters; }
+		work.resize(3 * nclusters);      // slot count only; the kernel derives its rows from the cluster index
+		for (size_t k = 0; k < work.size(); k++) { work[k].bi = work[k].bj = 0; work[k].slot = (int) k; work[k].pad = 0; work[k].chunk0 = work[k].chunk1 = 0; }
+		cta_seg0.assign(1, 0);
+	} else if (use_tma) {
 		// stream-K: the chunks of all roles as one stream in cost units, an equal share per CTA
 		double total = 0;
 		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) total += ((bi == bj) ? wdiag : 64.0) * (double) nchunks;
@@ -678,7 +877,21 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	{
 		TimerScope ts(ctx, "syrk");
 		bool done = false;
-		if (use_tma) {
+		if (use_pair) {
+			CUtensorMap tmJ;
+			cuuint64_t dimJ[3] = {(cuuint64_t) kTBoxCols, (cuuint64_t) m, (cuuint64_t) (n / kTBoxCols)};
+			cuuint64_t strJ[2] = {(cuuint64_t) n * sizeof(double), (cuuint64_t) kTBoxCols * sizeof(double)};
+			cuuint32_t boxJ[3] = {kTBoxCols, 32, kBT / kTBoxCols};
+			cuuint32_t es3[3] = {1, 1, 1};
+			CUresult r1 = tensor_map_encoder()(&tmJ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *) J, dimJ, strJ, boxJ, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			PNOL_REQUIRE(ctx, r1 == CUDA_SUCCESS, "syrk: cuTensorMapEncodeTiled failed (%d) for m=%lld n=%d", (int) r1, m, n);
+			size_t smem_p = sizeof(SyrkPairStage) * kSStages + 1024;
+			auto kern = syrk_pair_kernel;
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_p));
+			PNOL_LAUNCH(ctx, kern, grid, kSyrkTmaThreads, smem_p, tmJ, nchunks, nclusters, part_tiles);
+			done = true;
+		} else if (use_tma) {
 			CUtensorMap tmJ, tmF;
 			cuuint64_t dimJ[3] = {(cuuint64_t) kTBoxCols, (cuuint64_t) m, (cuuint64_t) (n / kTBoxCols)};
 			cuuint64_t strJ[2] = {(cuuint64_t) n * sizeof(double), (cuuint64_t) kTBoxCols * sizeof(double)};

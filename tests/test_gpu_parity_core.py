@@ -216,6 +216,31 @@ def test_lm_normal_eq(ctx, m, n):
     assert np.array_equal(np.diag(A), (1 + lam) * np.diag(JTJ))
 
 
+@pytest.mark.parametrize("m,n", [(1, 32), (31, 16), (33, 128), (64, 256), (4737, 256), (100_000, 48), (7000, 272), (5000, 512),
+                                 (300_000, 256)])
+def test_lm_normal_eq_stream_k_shapes(ctx, m, n):
+    # shapes that stress the TMA / stream-K SYRK: fewer chunks than CTAs, ragged last chunk (rows beyond m are the TMA's zero
+    # fill), partial 128-column tiles (n = 48, 272), 6 and 10 tile roles, CTAs that cross role boundaries (m = 300k); with and
+    # without F (the LM step runs it without). Reference: numpy (BLAS) in double, bar 1e-12 norm-wise
+    rng = np.random.default_rng(7 * m + n)
+    J = rng.normal(size=(m, n)) * (1 + 0.05 * np.arange(n))
+    F = rng.normal(size=m)
+    JTJ, A, rhs = ctx.lm_normal_eq(J, F, m, n, 0.25)
+    JTJw, rhsw = J.T @ J, -(J.T @ F)
+    assert rel(JTJ, JTJw) < 1e-12 and np.array_equal(JTJ, JTJ.T)
+    assert rel(rhs, rhsw) < 1e-12
+    assert np.array_equal(np.diag(A), 1.25 * np.diag(JTJ))
+    Jd = ctx.to_device(J)
+    JTJ2 = ctx.malloc(n * n * 8)
+    A2, rhs2 = ctx.malloc(n * n * 8), ctx.malloc(n * 8)
+    ctx.lm_normal_eq(Jd, None, m, n, 0.25, JTJ=JTJ2, A=A2, rhs=rhs2)          # J^T J only (two tile rows: the CTA-pair kernel)
+    got = ctx.to_host(JTJ2, n * n).reshape(n, n)
+    assert rel(got, JTJw) < 1e-12 and np.array_equal(got, got.T)
+    assert np.array_equal(ctx.to_host(rhs2, n), np.zeros(n))
+    for p_ in (Jd, JTJ2, A2, rhs2):
+        ctx.free(p_)
+
+
 @pytest.mark.parametrize("n", [1, 3, 16, 32, 33, 100, 256, 300])
 def test_spd_solve(ctx, n):
     rng = np.random.default_rng(n)
