@@ -498,8 +498,15 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__
 // Ring protocol: full[s] (1 arrival + 64 KB of transactions: the own copy and the peer's) as before; empty[s] counts the 32 DMMA
 // warps of BOTH CTAs, because a CTA's copy also overwrites the peer's stage (remote arrivals through mapa / shared::cluster).
 // ---------------------------------------------------------------------------------------------------
+#ifndef SYRK_PAIR_ROWS
+#define SYRK_PAIR_ROWS 32
+#define SYRK_PAIR_STAGES 3
+#endif
+constexpr int kPairRows = SYRK_PAIR_ROWS;            // rows of J per chunk (a multiple of 8: the swizzle's row group)
+constexpr int kPairStages = SYRK_PAIR_STAGES;
+constexpr int kPairSub = kPairRows * kTBoxCols;      // one sub-tile: kPairRows rows x 16 columns
 struct SyrkPairStage {
-	double T[2 * kBT / kTBoxCols][kTBoxElems];        // 16 sub-tiles of 32 rows x 16 columns
+	double T[2 * kBT / kTBoxCols][kPairSub];          // 16 sub-tiles
 };
 
 __device__ __forceinline__ unsigned pair_cluster_ctarank()
@@ -535,7 +542,7 @@ __device__ __forceinline__ void pair_half_tile(double (&acc)[4][2][2], const dou
 	const int rb = (t >> 1) * 8 * kTBoxCols;
 	double a[4], b[2];
 #pragma unroll
-	for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+	for (int i = 0; i < 4; i++) a[i] = Ab[(i >> 1) * kPairSub + rb + lp[i & 1][t & 1]];
 #pragma unroll
 	for (int j = 0; j < 2; j++) b[j] = Bb[rb + lp[j][t & 1]];
 #pragma unroll
@@ -549,7 +556,7 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 {
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	SyrkPairStage * stages = reinterpret_cast<SyrkPairStage *>(smem_raw);
-	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
+	__shared__ uint64_t full_bar[kPairStages], empty_bar[kPairStages];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned rank = pair_cluster_ctarank();
@@ -558,7 +565,7 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 	const int nloc = (int) (chunk1 - chunk0);
 	if (tid == 0) {
 #pragma unroll
-		for (int s = 0; s < kSStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2 * kSyrkRingWarps); }
+		for (int s = 0; s < kPairStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2 * kSyrkRingWarps); }
 		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 	}
 	pair_cluster_sync();      // both CTAs' barriers exist before anybody copies into or arrives on the peer
@@ -568,10 +575,10 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 		if (warp == kDmmaThreads / 32 && lane == 0) {
 			// producer: this CTA's half of every chunk, multicast to both CTAs
 			for (int g = 0; g < nloc; g++) {
-				const int s = g % kSStages;
-				if (g >= kSStages) mbar_wait(&empty_bar[s], (unsigned) (((g / kSStages) - 1) & 1));
+				const int s = g % kPairStages;
+				if (g >= kPairStages) mbar_wait(&empty_bar[s], (unsigned) (((g / kPairStages) - 1) & 1));
 				mbar_arrive_expect_tx(&full_bar[s], (unsigned) sizeof(SyrkPairStage));
-				tma_load_3d_multicast(&stages[s].T[8 * rank][0], &tmJ, 0, (int) ((chunk0 + g) * 32), (int) (8 * rank), &full_bar[s], (unsigned short) 3);
+				tma_load_3d_multicast(&stages[s].T[8 * rank][0], &tmJ, 0, (int) ((chunk0 + g) * kPairRows), (int) (8 * rank), &full_bar[s], (unsigned short) 3);
 			}
 		}
 		__syncwarp();      // the producer's warp meets again before the (warp-aligned) cluster barrier below
@@ -587,7 +594,7 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 		}
 		// off-diagonal piece of this warp: rows (of the output tile (1,0)) 64 rank + 32 rg .. + 31, columns 16 cg .. + 15
 		const int rg = warp & 1, cg = warp >> 1;
-		const int offA = (8 + 4 * (int) rank + 2 * rg) * kTBoxElems, offB = cg * kTBoxElems;
+		const int offA = (8 + 4 * (int) rank + 2 * rg) * kPairSub, offB = cg * kPairSub;
 		const int dbase = 8 * (int) rank;                 // first sub-tile of the diagonal tile's columns
 		double accO[4][2][2];
 #pragma unroll
@@ -604,17 +611,17 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 			for (int i = 0; i < 4; i++)
 #pragma unroll
 				for (int j = 0; j < 4; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
-			const int offD = (dbase + 2 * warp) * kTBoxElems;
+			const int offD = (dbase + 2 * warp) * kPairSub;
 			for (int g = 0; g < nloc; g++) {
-				const int s = g % kSStages;
-				mbar_wait(&full_bar[s], (unsigned) ((g / kSStages) & 1));
+				const int s = g % kPairStages;
+				mbar_wait(&full_bar[s], (unsigned) ((g / kPairStages) & 1));
 				const double * T0 = &stages[s].T[0][0];
 #pragma unroll
-				for (int t = 0; t < 8; t++) {
+				for (int t = 0; t < kPairRows / 4; t++) {
 					const int rb = (t >> 1) * 8 * kTBoxCols;
 					double a[4];
 #pragma unroll
-					for (int i = 0; i < 4; i++) a[i] = T0[offD + (i >> 1) * kTBoxElems + rb + lp[i & 1][t & 1]];
+					for (int i = 0; i < 4; i++) a[i] = T0[offD + (i >> 1) * kPairSub + rb + lp[i & 1][t & 1]];
 #pragma unroll
 					for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -636,18 +643,18 @@ syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int
 			const int ht = (warp - 4) >> 1, hh = (warp - 4) & 1;
 			const int wi = ht < 1 ? 1 : (ht < 3 ? 2 : 3);
 			const int wj = ht - wi * (wi - 1) / 2;
-			const int offDa = (dbase + 2 * wi) * kTBoxElems, offDb = (dbase + 2 * wj + hh) * kTBoxElems;
+			const int offDa = (dbase + 2 * wi) * kPairSub, offDb = (dbase + 2 * wj + hh) * kPairSub;
 			double acc[4][2][2];
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
 				for (int j = 0; j < 2; j++) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
 			for (int g = 0; g < nloc; g++) {
-				const int s = g % kSStages;
-				mbar_wait(&full_bar[s], (unsigned) ((g / kSStages) & 1));
+				const int s = g % kPairStages;
+				mbar_wait(&full_bar[s], (unsigned) ((g / kPairStages) & 1));
 				const double * T0 = &stages[s].T[0][0];
 #pragma unroll
-				for (int t = 0; t < 8; t++) {
+				for (int t = 0; t < kPairRows / 4; t++) {
 					pair_half_tile(acc, T0 + offDa, T0 + offDb, lp, t);
 					pair_half_tile(accO, T0 + offA, T0 + offB, lp, t);
 				}
@@ -758,7 +765,8 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	int nclusters = 0;
 	if (use_pair) {
 		// one cluster of two CTAs per equal row range; slots: role (0,0) <- rank 0, role (1,0) <- both ranks, role (1,1) <- rank 1
-		nclusters = (int) (nchunks < ctx->sm_count / 2 ? nchunks : ctx->sm_count / 2);
+		const long long pchunks = (m + kPairRows - 1) / kPairRows;
+		nclusters = (int) (pchunks < ctx->sm_count / 2 ? pchunks : ctx->sm_count / 2);
 		grid = 2 * nclusters;
 		for (int r = 0; r < 3; r++) { slot0[r] = r * nclusters; nslots[r] = nclusters; }
 		work.resize(3 * nclusters);      // slot count only; the kernel derives its rows from the cluster index
@@ -881,15 +889,15 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 			CUtensorMap tmJ;
 			cuuint64_t dimJ[3] = {(cuuint64_t) kTBoxCols, (cuuint64_t) m, (cuuint64_t) (n / kTBoxCols)};
 			cuuint64_t strJ[2] = {(cuuint64_t) n * sizeof(double), (cuuint64_t) kTBoxCols * sizeof(double)};
-			cuuint32_t boxJ[3] = {kTBoxCols, 32, kBT / kTBoxCols};
+			cuuint32_t boxJ[3] = {kTBoxCols, kPairRows, kBT / kTBoxCols};
 			cuuint32_t es3[3] = {1, 1, 1};
 			CUresult r1 = tensor_map_encoder()(&tmJ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *) J, dimJ, strJ, boxJ, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
 			                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			PNOL_REQUIRE(ctx, r1 == CUDA_SUCCESS, "syrk: cuTensorMapEncodeTiled failed (%d) for m=%lld n=%d", (int) r1, m, n);
-			size_t smem_p = sizeof(SyrkPairStage) * kSStages + 1024;
+			size_t smem_p = sizeof(SyrkPairStage) * kPairStages + 1024;
 			auto kern = syrk_pair_kernel;
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_p));
-			PNOL_LAUNCH(ctx, kern, grid, kSyrkTmaThreads, smem_p, tmJ, nchunks, nclusters, part_tiles);
+			PNOL_LAUNCH(ctx, kern, grid, kSyrkTmaThreads, smem_p, tmJ, (m + kPairRows - 1) / kPairRows, nclusters, part_tiles);
 			done = true;
 		} else if (use_tma) {
 			CUtensorMap tmJ, tmF;
