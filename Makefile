@@ -31,7 +31,7 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h) $(w
 
 $(LIBDIR)/libpnol_b200.so: $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJS) -ldl
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJS) -ldl -lpthread
 
 $(BUILD)/host_%.o: $(HOSTSRC)/%.cpp $(wildcard include/*.h) $(wildcard include/pnol/*)
 	@mkdir -p $(BUILD)

@@ -2,6 +2,7 @@
 // entry points (the GA entry points live in ga.cu, the communicator in comm.cu).
 #include "common.cuh"
 #include <vector>
+#include <thread>
 #include "exact_div.cuh"
 
 #include <math.h>
@@ -89,6 +90,9 @@ extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 	timers_collect(ctx);
 	comm_destroy(ctx);
 	for (int s = 0; s < 5; s++) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+	if (ctx->stage_pinned) cudaFreeHost(ctx->stage_pinned);
+	for (int t = 0; t < 4; t++) if (ctx->stage_streams[t]) cudaStreamDestroy(ctx->stage_streams[t]);
+	for (int e = 0; e < 8; e++) if (ctx->stage_events[e]) cudaEventDestroy(ctx->stage_events[e]);
 	if (ctx->syrk_plan) cudaFree(ctx->syrk_plan);
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	cudaStreamSynchronize(ctx->stream);
@@ -125,12 +129,100 @@ extern "C" int pnol_free(pnol_ctx * ctx, void * dev_ptr)
 	PNOL_CUDA(ctx, cudaFreeAsync(dev_ptr, ctx->stream));
 	return PNOL_OK;
 }
+// ---------------------------------------------------------------------------------------------------
+// Large copies between PAGEABLE host memory and the device. cudaMemcpy stages such a copy through the driver's pinned buffers with
+// one host thread (~10 GB/s here), which made the host-vector API (LevMarq::findMin: data columns up, F0 / FOpt down, 128 MB per
+// call at m = 4M) cost 0.9 ms per LM iteration. Here four threads each move every fourth 4 MB chunk through their own pair of
+// pinned buffers and their own stream, so the host-side memcpy of one chunk overlaps the DMA of the others.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t kStageChunk = (size_t) 4 << 20;
+constexpr int kStageThreads = 4;
+constexpr size_t kStageMinBytes = (size_t) 8 << 20;
+
+static bool is_pageable_host(const void * p)
+{
+	cudaPointerAttributes a;
+	cudaError_t e = cudaPointerGetAttributes(&a, p);
+	if (e != cudaSuccess) { cudaGetLastError(); return true; }
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_init(pnol_ctx * ctx)
+{
+	if (ctx->stage_pinned) return PNOL_OK;
+	PNOL_CUDA(ctx, cudaHostAlloc(&ctx->stage_pinned, kStageChunk * 2 * kStageThreads, cudaHostAllocDefault));
+	for (int t = 0; t < kStageThreads; t++) PNOL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_streams[t], cudaStreamNonBlocking));
+	for (int e = 0; e < 2 * kStageThreads; e++) PNOL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_events[e], cudaEventDisableTiming));
+	return PNOL_OK;
+}
+
+// dst / src: one of them pageable host memory, the other device memory; the context's stream is idle (the caller synchronised)
+static int staged_copy(pnol_ctx * ctx, void * dst, const void * src, size_t bytes, bool h2d)
+{
+	PNOL_CHECK(stage_init(ctx));
+	cudaError_t errs[kStageThreads];
+	auto worker = [&](int t) {
+		cudaError_t e = cudaSetDevice(ctx->device);
+		unsigned char * pin = (unsigned char *) ctx->stage_pinned + (size_t) t * 2 * kStageChunk;
+		cudaStream_t st = ctx->stage_streams[t];
+		cudaEvent_t * ev = &ctx->stage_events[2 * t];
+		size_t prev_off = 0, prev_len = 0;
+		for (size_t i = 0; e == cudaSuccess; i++) {
+			const size_t off = ((size_t) t + i * kStageThreads) * kStageChunk;
+			const bool have = off < bytes;
+			const size_t len = have ? (bytes - off < kStageChunk ? bytes - off : kStageChunk) : 0;
+			const int b = (int) (i & 1);
+			unsigned char * buf = pin + (size_t) b * kStageChunk;
+			if (h2d) {
+				if (!have) break;
+				if (i >= 2) e = cudaEventSynchronize(ev[b]);      // the DMA out of this buffer two chunks ago
+				memcpy(buf, (const unsigned char *) src + off, len);
+				if (e == cudaSuccess) e = cudaMemcpyAsync((unsigned char *) dst + off, buf, len, cudaMemcpyHostToDevice, st);
+				if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+			} else {
+				if (have) {
+					e = cudaMemcpyAsync(buf, (const unsigned char *) src + off, len, cudaMemcpyDeviceToHost, st);
+					if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+				}
+				if (i >= 1 && prev_len && e == cudaSuccess) {       // the previous chunk has landed in the other buffer
+					e = cudaEventSynchronize(ev[b ^ 1]);
+					memcpy((unsigned char *) dst + prev_off, pin + (size_t) (b ^ 1) * kStageChunk, prev_len);
+				}
+				prev_off = off; prev_len = len;
+				if (!have) break;
+			}
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		errs[t] = e;
+	};
+	std::thread th[kStageThreads - 1];
+	for (int t = 1; t < kStageThreads; t++) th[t - 1] = std::thread(worker, t);
+	worker(0);
+	for (int t = 1; t < kStageThreads; t++) th[t - 1].join();
+	for (int t = 0; t < kStageThreads; t++)
+		if (errs[t] != cudaSuccess) { PNOL_SET_ERR(ctx, "staged copy: %s", cudaGetErrorString(errs[t])); return PNOL_ERR_CUDA; }
+	return PNOL_OK;
+}
+
+// host <-> device copy that is complete on return (any pointer kinds)
+int copy_now(pnol_ctx * ctx, void * dst, const void * src, size_t bytes)
+{
+	if (!bytes) return PNOL_OK;
+	if (bytes >= kStageMinBytes) {
+		const bool dst_dev = is_device_ptr(dst), src_dev = is_device_ptr(src);
+		if (dst_dev != src_dev && is_pageable_host(dst_dev ? src : dst)) {
+			PNOL_CHECK(finish(ctx));                             // whatever produced / still uses the device side
+			return staged_copy(ctx, dst, src, bytes, dst_dev);
+		}
+	}
+	PNOL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+	return finish(ctx);
+}
+
 extern "C" int pnol_memcpy(pnol_ctx * ctx, void * dst, const void * src, size_t bytes)
 {
 	if (!ctx) return PNOL_ERR_INVALID;
-	if (!bytes) return PNOL_OK;
-	PNOL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
-	return finish(ctx);
+	return copy_now(ctx, dst, src, bytes);
 }
 extern "C" int pnol_memset(pnol_ctx * ctx, void * dev_ptr, int value, size_t bytes)
 {
@@ -202,8 +294,7 @@ extern "C" int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * des
 		void * d = nullptr;
 		size_t bytes = (size_t) (desc->m > 0 ? desc->m : 1) * sizeof(double);
 		cudaError_t e = cudaMallocAsync(&d, bytes, ctx->stream);
-		if (e == cudaSuccess && desc->m > 0)
-			e = cudaMemcpyAsync(d, desc->columns[c], (size_t) desc->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess && desc->m > 0 && copy_now(ctx, d, desc->columns[c], (size_t) desc->m * sizeof(double)) != PNOL_OK) e = cudaErrorUnknown;
 		if (e != cudaSuccess) {
 			PNOL_SET_ERR(ctx, "functor column upload: %s", cudaGetErrorString(e));
 			pnol_functor_destroy(f);

@@ -124,3 +124,15 @@ def test_lm_with_a_singular_normal_matrix(ctx):
             ctx.spd_solve(A, rhs, 8)
     finally:
         hostapi.detach()
+
+
+def test_large_pageable_copies_round_trip(ctx):
+    # copies of >= 8 MB between pageable host memory and the device go through the threaded, chunked staging path (capi.cu:
+    # staged_copy): whole chunks, a ragged tail, fewer chunks than threads, and the plain path below the threshold
+    rng = np.random.default_rng(11)
+    for nbytes in (8 << 20, (8 << 20) + 8, (36 << 20) + 4096 + 8, 4 << 20, (64 << 20)):
+        a = rng.integers(0, 2 ** 62, size=nbytes // 8, dtype=np.int64)
+        p = ctx.to_device(a)
+        b = ctx.to_host(p, a.shape, dtype=np.int64)
+        assert np.array_equal(a, b)
+        ctx.free(p)
