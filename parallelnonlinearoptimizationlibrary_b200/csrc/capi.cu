@@ -91,8 +91,8 @@ extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 	comm_destroy(ctx);
 	for (int s = 0; s < 5; s++) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
 	if (ctx->stage_pinned) cudaFreeHost(ctx->stage_pinned);
-	for (int t = 0; t < 4; t++) if (ctx->stage_streams[t]) cudaStreamDestroy(ctx->stage_streams[t]);
-	for (int e = 0; e < 8; e++) if (ctx->stage_events[e]) cudaEventDestroy(ctx->stage_events[e]);
+	for (int t = 0; t < 8; t++) if (ctx->stage_streams[t]) cudaStreamDestroy(ctx->stage_streams[t]);
+	for (int e = 0; e < 16; e++) if (ctx->stage_events[e]) cudaEventDestroy(ctx->stage_events[e]);
 	if (ctx->syrk_plan) cudaFree(ctx->syrk_plan);
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	cudaStreamSynchronize(ctx->stream);
@@ -136,7 +136,9 @@ extern "C" int pnol_free(pnol_ctx * ctx, void * dev_ptr)
 // pinned buffers and their own stream, so the host-side memcpy of one chunk overlaps the DMA of the others.
 // ---------------------------------------------------------------------------------------------------
 constexpr size_t kStageChunk = (size_t) 4 << 20;
-constexpr int kStageThreads = 4;
+constexpr int kStageMaxThreads = 8;
+// threads actually used: PNOL_COPY_THREADS (1..8), default 4
+static const int kStageThreads = [] { const char * e = getenv("PNOL_COPY_THREADS"); int t = e ? atoi(e) : 4; return t < 1 ? 1 : (t > kStageMaxThreads ? kStageMaxThreads : t); }();
 constexpr size_t kStageMinBytes = (size_t) 8 << 20;
 
 static bool is_pageable_host(const void * p)
@@ -150,9 +152,9 @@ static bool is_pageable_host(const void * p)
 static int stage_init(pnol_ctx * ctx)
 {
 	if (ctx->stage_pinned) return PNOL_OK;
-	PNOL_CUDA(ctx, cudaHostAlloc(&ctx->stage_pinned, kStageChunk * 2 * kStageThreads, cudaHostAllocDefault));
-	for (int t = 0; t < kStageThreads; t++) PNOL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_streams[t], cudaStreamNonBlocking));
-	for (int e = 0; e < 2 * kStageThreads; e++) PNOL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_events[e], cudaEventDisableTiming));
+	PNOL_CUDA(ctx, cudaHostAlloc(&ctx->stage_pinned, kStageChunk * 2 * kStageMaxThreads, cudaHostAllocDefault));
+	for (int t = 0; t < kStageMaxThreads; t++) PNOL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stage_streams[t], cudaStreamNonBlocking));
+	for (int e = 0; e < 2 * kStageMaxThreads; e++) PNOL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_events[e], cudaEventDisableTiming));
 	return PNOL_OK;
 }
 
@@ -160,7 +162,7 @@ static int stage_init(pnol_ctx * ctx)
 static int staged_copy(pnol_ctx * ctx, void * dst, const void * src, size_t bytes, bool h2d)
 {
 	PNOL_CHECK(stage_init(ctx));
-	cudaError_t errs[kStageThreads];
+	cudaError_t errs[kStageMaxThreads];
 	auto worker = [&](int t) {
 		cudaError_t e = cudaSetDevice(ctx->device);
 		unsigned char * pin = (unsigned char *) ctx->stage_pinned + (size_t) t * 2 * kStageChunk;
@@ -195,7 +197,7 @@ static int staged_copy(pnol_ctx * ctx, void * dst, const void * src, size_t byte
 		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 		errs[t] = e;
 	};
-	std::thread th[kStageThreads - 1];
+	std::thread th[kStageMaxThreads];
 	for (int t = 1; t < kStageThreads; t++) th[t - 1] = std::thread(worker, t);
 	worker(0);
 	for (int t = 1; t < kStageThreads; t++) th[t - 1].join();

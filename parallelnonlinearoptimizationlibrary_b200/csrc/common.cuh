@@ -36,8 +36,8 @@ struct pnol_ctx {
 	size_t pinned_doubles = 0;
 	// pinned staging + copy streams of the threaded host <-> device copy of large pageable buffers (capi.cu: staged_copy)
 	void * stage_pinned = nullptr;
-	cudaStream_t stage_streams[4] = {nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t stage_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaStream_t stage_streams[8] = {};
+	cudaEvent_t stage_events[16] = {};
 
 	// SYRK work plan of the last (m, n) shape (device copy of the descriptor tables; see launch_syrk)
 	void * syrk_plan = nullptr;
