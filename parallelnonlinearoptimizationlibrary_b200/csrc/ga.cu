@@ -183,22 +183,20 @@ sort_hist_kernel(const unsigned long long * __restrict__ keys, long long n, int 
 	}
 }
 
-// per pass: is one digit value holding every key? (skip[p] = 1) -- single block
-__global__ void sort_skip_kernel(const unsigned * __restrict__ counts, int nblocks, long long n, int * __restrict__ skip)
+// per pass: is one digit value holding every key? (skip[p] = 1; skip[] zeroed by the caller). One warp per (pass, digit) counter
+// row: the first version summed the 2048 x nblocks counters in ONE block, 8 rows per thread -- 0.30 ms per sort at 1M keys, a
+// fifth of a GA generation.
+__global__ void __launch_bounds__(256)
+sort_skip_kernel(const unsigned * __restrict__ counts, int nblocks, long long n, int * __restrict__ skip)
 {
-	__shared__ unsigned long long tot[8][256];
-	for (int e = threadIdx.x; e < 8 * 256; e += blockDim.x) {
-		unsigned long long s = 0;
-		const unsigned * c = counts + (size_t) e * nblocks;
-		for (int b = 0; b < nblocks; b++) s += c[b];
-		(&tot[0][0])[e] = s;
-	}
-	__syncthreads();
-	if (threadIdx.x < 8) {
-		int sk = 0;
-		for (int d = 0; d < 256; d++) if (tot[threadIdx.x][d] == (unsigned long long) n) sk = 1;
-		skip[threadIdx.x] = sk;
-	}
+	const int e = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);      // (pass, digit) = (e >> 8, e & 255)
+	const int lane = threadIdx.x & 31;
+	if (e >= 8 * 256) return;
+	const unsigned * c = counts + (size_t) e * nblocks;
+	unsigned long long s = 0;
+	for (int b = lane; b < nblocks; b += 32) s += c[b];
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if (lane == 0 && s == (unsigned long long) n) skip[e >> 8] = 1;
 }
 
 __global__ void __launch_bounds__(kSortWarps * 32)
@@ -294,7 +292,8 @@ static int radix_sort_pairs(pnol_ctx * ctx, unsigned long long * keys, unsigned 
 	if (n <= 1) return PNOL_OK;
 	int nblocks = (int) ((n + kSortTile - 1) / kSortTile);
 	PNOL_LAUNCH(ctx, sort_hist_kernel, nblocks, 256, 0, keys, n, nblocks, sc.counts);
-	PNOL_LAUNCH(ctx, sort_skip_kernel, 1, 256, 0, sc.counts, nblocks, n, sc.skip);
+	PNOL_CUDA(ctx, cudaMemsetAsync(sc.skip, 0, 8 * sizeof(int), ctx->stream));
+	PNOL_LAUNCH(ctx, sort_skip_kernel, 8 * 256 * 32 / 256, 256, 0, sc.counts, nblocks, n, sc.skip);
 	int skip[8];
 	PNOL_CUDA(ctx, cudaMemcpyAsync(skip, sc.skip, sizeof skip, cudaMemcpyDeviceToHost, ctx->stream));
 	PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
