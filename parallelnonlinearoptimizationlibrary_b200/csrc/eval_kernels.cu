@@ -126,6 +126,11 @@ __device__ __forceinline__ void ldg_f64x4(const double * p, double (&v)[4])
 	asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
+__device__ __forceinline__ void ldg_f64x4p(const double * p, double * v)
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
 template <class F>
 __global__ void __launch_bounds__(128)
 eval_batch_rowwise_kernel(FunctorParams P, const double * __restrict__ pts, long long B, int n, long long ld,
@@ -144,6 +149,35 @@ eval_batch_rowwise_kernel(FunctorParams P, const double * __restrict__ pts, long
 		v = v + t0; v = v + t1; v = v + t2; v = v + t3;
 #pragma unroll
 		for (int q = 0; q < 4; q++) cur[q] = nxt[q];
+	}
+	f_out[b] = v;
+}
+
+// same, n a multiple of 16: four 256-bit loads (16 genes) in flight per thread ahead of the arithmetic, so that the memory system
+// keeps working through the FP64-heavy terms (the kernel's FP64 issue time and its HBM time are about equal; with one load ahead
+// they overlapped badly). Same order of additions, hence the same bits.
+template <class F>
+__global__ void __launch_bounds__(128)
+eval_batch_rowwise16_kernel(FunctorParams P, const double * __restrict__ pts, long long B, int n, long long ld,
+                            const unsigned char * __restrict__ indicator, double * __restrict__ f_out)
+{
+	const long long b = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	if (indicator && !indicator[b]) return;
+	const double * row = pts + b * ld;
+	double v = F::sep_init(P, n);
+	double cur[16], nxt[16];
+#pragma unroll
+	for (int q = 0; q < 4; q++) ldg_f64x4p(row + 4 * q, cur + 4 * q);
+	for (int k = 0; k < n; k += 16) {
+		if (k + 16 < n) {
+#pragma unroll
+			for (int q = 0; q < 4; q++) ldg_f64x4p(row + k + 16 + 4 * q, nxt + 4 * q);
+		}
+#pragma unroll
+		for (int q = 0; q < 16; q++) v = v + F::sep_term(P, cur[q]);
+#pragma unroll
+		for (int q = 0; q < 16; q++) cur[q] = nxt[q];
 	}
 	f_out[b] = v;
 }
@@ -168,7 +202,11 @@ template <class F> struct SeparableLaunch<F, true> {
 		// PNOL_SWEEP_G = 4 / 8 / 16 forces the warp-tile kernel with that prefetch depth (tuning runs).
 		static const int g = [] { const char * e = getenv("PNOL_SWEEP_G"); return e ? atoi(e) : 0; }();
 		if (g == 0 && n % 4 == 0 && ld % 4 == 0 && (((size_t) pts) & 31) == 0) {
-			PNOL_LAUNCH(ctx, eval_batch_rowwise_kernel<F>, (unsigned) ((B + 127) / 128), 128, 0, f->params, pts, B, n, ld, indicator, f_out);
+			static const int deep = [] { const char * e = getenv("PNOL_SWEEP_DEEP"); return e ? atoi(e) : 1; }();      // 0: one load ahead (A/B runs)
+			if (deep && n % 16 == 0)
+				PNOL_LAUNCH(ctx, eval_batch_rowwise16_kernel<F>, (unsigned) ((B + 127) / 128), 128, 0, f->params, pts, B, n, ld, indicator, f_out);
+			else
+				PNOL_LAUNCH(ctx, eval_batch_rowwise_kernel<F>, (unsigned) ((B + 127) / 128), 128, 0, f->params, pts, B, n, ld, indicator, f_out);
 			*done = true;
 			return PNOL_OK;
 		}
