@@ -1,16 +1,20 @@
 // dmma.cu -- the dense FP64 contractions on the tensor cores (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05
 // has no FP64 kind, so the warp-level DMMA is the Blackwell FP64 tensor path -- SURVEY.md 7.4, Appendix C).
 //
-//  * syrk_kernel   : packed[JTJ | JTr] partials of J^T J (lower-triangle tiles only) and J^T F, split-K over the
-//                    rows of J with persistent CTAs; replaces matrixTranspose + matrixMultiply(JT,J,JTJ) +
-//                    matrixVectorMultiply(JT,F,rhs) of Source/LevenbergMarquardtMPI.cpp:64-65,83.
-//  * syrk_finish   : fixed-order reduction of the partials (deterministic), mirroring to the upper triangle.
-//  * gemm_nn_kernel: C = A B for the literal updateHessianInv (Source/BFGS_with_linesearch.cpp:421-422).
+//  J^T J (| J^T F) -- replaces matrixTranspose + matrixMultiply(JT,J,JTJ) + matrixVectorMultiply(JT,F,rhs) of
+//  Source/LevenbergMarquardtMPI.cpp:64-65,83 -- lower-triangle 128 x 128 tiles only, split-K over the rows of J, partial tiles
+//  summed in a fixed order by syrk_finish (deterministic), mirrored to the upper triangle. Three kernels, chosen in launch_syrk:
+//  * syrk_pair_kernel : two tile rows (128 < n <= 256), no F -- the LM step's case. Clusters of two CTAs, every 32-row chunk of J
+//                       multicast by the TMA into both CTAs: J is read from HBM once. 0.95 of the DMMA peak at m = 4M, n = 256.
+//  * syrk_tma_kernel  : any n that is a multiple of 16, with or without F. TMA-fed, stream-K segments over the tile roles,
+//                       producer warp (setmaxnreg), J^T F as extra DMMA tiles in the diagonal warps.
+//  * syrk_kernel      : everything else (odd n, unaligned J): LDGSTS stage ring, one tile role per CTA.
+//  gemm_nn_kernel: C = A B for the literal updateHessianInv (Source/BFGS_with_linesearch.cpp:421-422).
 //
-// Tiling: CTA tile 128 x 128 (16 warps, warp tile 32 x 32 = 4 x 4 DMMA tiles, 32 FP64 accumulators per thread),
-// K chunk of 32 rows staged with cp.async into a 3-stage shared-memory ring (~200 KB). Operand rows are padded to a pitch
-// = 4 (mod 16) doubles so that the DMMA fragment loads (4 k-rows x 8 columns per warp) hit 16 distinct 8-byte
-// banks per half-warp. For SYRK the A and B fragments come from the SAME staged rows of J.
+// Tiling: CTA tile 128 x 128 (16 warps, warp tile 32 x 32 = 4 x 4 DMMA tiles, 32 FP64 accumulators per thread), K chunk of 32 rows
+// in a 3-stage shared-memory ring (~200 KB). LDGSTS kernels: operand rows padded to a pitch = 4 (mod 16) doubles so that the DMMA
+// fragment loads (4 k-rows x 8 columns per warp) hit 16 distinct 8-byte banks per half-warp; TMA kernels: dense 32 x 16 sub-tiles
+// with SWIZZLE_128B. For SYRK the A and B fragments come from the SAME staged rows of J.
 #include "common.cuh"
 
 #include <cuda.h>
