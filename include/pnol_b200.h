@@ -298,6 +298,10 @@ int pnol_timer_get(pnol_ctx * ctx, const char * name, double * total_ms, long lo
 int pnol_timer_reset(pnol_ctx * ctx);
 /* self test: number of (x, d) pairs out of `pairs` pseudo-random / adversarial ones for which the reciprocal-based
  * exact division of the Jacobian kernels (csrc/exact_div.cuh) differs from x / d. Must return 0 mismatches. */
+/* host-only self-test of the J^T J kernel's stream-K work plan for m x n on sm_count CTAs (with_f: J^T F summed as well): 0 when
+ * every K chunk of every tile role is covered exactly once, in order, with contiguous slots per role, at most 8 segments per CTA and
+ * CTA shares within one chunk of the mean; otherwise the number of the violated rule. Needs no device. */
+int pnol_selftest_syrk_plan(long long m, int n, int sm_count, int with_f);
 int pnol_selftest_exact_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches);
 /* the same for the branch-free cores the speculative row kernels use (div_core, div_exact_core), over their validity range */
 int pnol_selftest_fast_div(pnol_ctx * ctx, long long pairs, unsigned long long seed, unsigned long long * mismatches);

@@ -89,7 +89,7 @@ EXPORTS = [
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
     "pnol_ga_check_identical", "pnol_measure_dmma_peak", "pnol_measure_copy_bandwidth", "pnol_timer_enable",
-    "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div", "pnol_selftest_fast_div",
+    "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div", "pnol_selftest_fast_div", "pnol_selftest_syrk_plan",
 ]
 
 _lib = None

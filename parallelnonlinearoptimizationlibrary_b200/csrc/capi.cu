@@ -694,6 +694,12 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 	return PNOL_OK;
 }
 
+// host-only: invariants of the SYRK's stream-K work plan for a shape (no device needed; see syrk_plan_selftest in dmma.cu)
+extern "C" int pnol_selftest_syrk_plan(long long m, int n, int sm_count, int with_f)
+{
+	return syrk_plan_selftest(m, n, sm_count, with_f);
+}
+
 extern "C" int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double,
                                        double *, double *, double *, double *)
 {

@@ -734,6 +734,116 @@ syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __rest
 	(void) nb;
 }
 
+// stream-K plan (host): the K chunks of all tile roles as one stream in cost units (64 per chunk of an off-diagonal role, wdiag
+// per chunk of a diagonal one), an equal share of the stream per CTA. Out: the segments in stream order (slot = index, so a role's
+// slots are contiguous: slot0 / nslots), the first segment of every CTA (cta_seg0[grid + 1]) and the grid. A CTA holds at most
+// kSyrkMaxSeg segments (it only crosses that many role boundaries when the roles are tiny). Returns false if chunks were left over.
+// pnol_selftest_syrk_plan checks the invariants on the host (tests/test_abi.py, no GPU needed).
+static bool syrk_streamk_plan(long long nchunks, int nb, int grid_cap, double wdiag, std::vector<SyrkWork> & work,
+                              std::vector<int> & cta_seg0, std::vector<int> & slot0, std::vector<int> & nslots, int & grid)
+{
+	const int nroles = nb * (nb + 1) / 2;
+	work.clear();
+	slot0.assign(nroles, 0);
+	nslots.assign(nroles, 0);
+	double total = 0;
+	for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) total += ((bi == bj) ? wdiag : 64.0) * (double) nchunks;
+	long long units = (long long) nroles * nchunks;
+	grid = (int) (units < grid_cap ? (units > 0 ? units : 1) : grid_cap);
+	cta_seg0.assign(grid + 1, 0);
+	double cum = 0;          // cost dealt out so far
+	int r = 0, bi = 0, bj = 0;
+	long long pos = 0;       // next chunk of role r
+	for (int c = 0; c < grid; c++) {
+		cta_seg0[c] = (int) work.size();
+		const double target = total * (double) (c + 1) / (double) grid;
+		int segs_here = 0;
+		while (r < nroles && segs_here < kSyrkMaxSeg) {
+			const double cost = (bi == bj) ? wdiag : 64.0;
+			long long take;
+			if (c == grid - 1 && segs_here == kSyrkMaxSeg - 1) take = nchunks - pos;
+			else {
+				take = (long long) ((target - cum) / cost + 0.5);
+				if (c == grid - 1) take = nchunks - pos;
+				if (take > nchunks - pos) take = nchunks - pos;
+			}
+			if (take <= 0) break;
+			SyrkWork w;
+			w.bi = bi; w.bj = bj; w.slot = (int) work.size(); w.pad = 0;
+			w.chunk0 = pos; w.chunk1 = pos + take;
+			work.push_back(w);
+			if (nslots[r] == 0) slot0[r] = w.slot;
+			nslots[r]++;
+			segs_here++;
+			cum += cost * (double) take;
+			pos += take;
+			if (pos == nchunks) {
+				pos = 0; r++;
+				if (++bj > bi) { bj = 0; bi++; }
+			} else break;
+		}
+	}
+	cta_seg0[grid] = (int) work.size();
+	return r == nroles;
+}
+
+// With many more tile roles than CTAs (n in the thousands) a CTA's share would cross more than kSyrkMaxSeg role boundaries: the
+// grid is doubled (several waves) until the plan holds all the work.
+static bool syrk_streamk_plan_any(long long nchunks, int nb, int grid_cap, double wdiag, std::vector<SyrkWork> & work,
+                                  std::vector<int> & cta_seg0, std::vector<int> & slot0, std::vector<int> & nslots, int & grid)
+{
+	for (int cap = grid_cap, tries = 0; tries < 16; cap *= 2, tries++)
+		if (syrk_streamk_plan(nchunks, nb, cap, wdiag, work, cta_seg0, slot0, nslots, grid)) return true;
+	return false;
+}
+
+// host-only check of the plan for (m, n) on `sm_count` CTAs: 0 = every chunk of every role is covered exactly once, in order, a
+// role's slots are contiguous, no CTA holds more than kSyrkMaxSeg segments and the CTAs' shares differ by at most one chunk of
+// cost from the mean; otherwise the number of the violated rule
+int syrk_plan_selftest(long long m, int n, int sm_count, int with_f)
+{
+	if (m < 1 || n < 1 || sm_count < 1) return -1;
+	const int nb = (n + kBT - 1) / kBT, nroles = nb * (nb + 1) / 2;
+	const long long nchunks = (m + 31) / 32;
+	const double wdiag = with_f ? 40.6 : 34.6;
+	std::vector<SyrkWork> work;
+	std::vector<int> cta_seg0, slot0, nslots;
+	int grid = 0;
+	if (!syrk_streamk_plan_any(nchunks, nb, sm_count, wdiag, work, cta_seg0, slot0, nslots, grid)) return 1;
+	if (grid < 1 || (int) cta_seg0.size() != grid + 1 || cta_seg0[grid] != (int) work.size()) return 2;
+	if (grid > sm_count && nroles <= sm_count * (kSyrkMaxSeg - 1)) return 2;      // more waves only when the roles demand it
+	// stream order: roles in (bi, bj) order, chunks ascending and gap-free
+	int r = 0, bi = 0, bj = 0;
+	long long pos = 0;
+	for (size_t k = 0; k < work.size(); k++) {
+		const SyrkWork & w = work[k];
+		if (w.slot != (int) k || w.chunk1 <= w.chunk0) return 3;
+		if (w.bi != bi || w.bj != bj || w.chunk0 != pos) return 4;
+		if ((int) k < slot0[r] || (int) k >= slot0[r] + nslots[r]) return 5;
+		pos = w.chunk1;
+		if (pos > nchunks) return 6;
+		if (pos == nchunks) { pos = 0; r++; if (++bj > bi) { bj = 0; bi++; } }
+	}
+	if (r != nroles || pos != 0) return 7;
+	int sum_slots = 0;
+	for (int q = 0; q < nroles; q++) { if (nslots[q] < 1) return 8; sum_slots += nslots[q]; }
+	if (sum_slots != (int) work.size()) return 9;
+	double total = 0, worst = 0;
+	std::vector<double> share(grid, 0.0);
+	for (int c = 0; c < grid; c++) {
+		if (cta_seg0[c + 1] < cta_seg0[c] || cta_seg0[c + 1] - cta_seg0[c] > kSyrkMaxSeg) return 10;
+		for (int k = cta_seg0[c]; k < cta_seg0[c + 1]; k++)
+			share[c] += ((work[k].bi == work[k].bj) ? wdiag : 64.0) * (double) (work[k].chunk1 - work[k].chunk0);
+		total += share[c];
+	}
+	for (int c = 0; c < grid; c++) { double d = share[c] - total / grid; if (d < 0) d = -d; if (d > worst) worst = d; }
+	// shares are cut at whole chunks: within one off-diagonal chunk of the mean, unless tiny roles filled a CTA's segment list
+	bool capped = false;
+	for (int c = 0; c < grid; c++) if (cta_seg0[c + 1] - cta_seg0[c] == kSyrkMaxSeg) capped = true;
+	if (!capped && worst > 64.0 + 1e-6) return 11;
+	return 0;
+}
+
 int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed)
 {
 	PNOL_REQUIRE(ctx, n >= 1 && m >= 0, "syrk: bad shape m=%lld n=%d", m, n);
@@ -777,46 +887,8 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 		for (size_t k = 0; k < work.size(); k++) { work[k].bi = work[k].bj = 0; work[k].slot = (int) k; work[k].pad = 0; work[k].chunk0 = work[k].chunk1 = 0; }
 		cta_seg0.assign(1, 0);
 	} else if (use_tma) {
-		// stream-K: the chunks of all roles as one stream in cost units, an equal share per CTA
-		double total = 0;
-		for (int bi = 0; bi < nb; bi++) for (int bj = 0; bj <= bi; bj++) total += ((bi == bj) ? wdiag : 64.0) * (double) nchunks;
-		long long units = (long long) nroles * nchunks;
-		grid = (int) (units < grid_cap ? (units > 0 ? units : 1) : grid_cap);
-		cta_seg0.assign(grid + 1, 0);
-		double cum = 0;          // cost dealt out so far
-		int r = 0, bi = 0, bj = 0;
-		long long pos = 0;       // next chunk of role r
-		for (int c = 0; c < grid; c++) {
-			cta_seg0[c] = (int) work.size();
-			const double target = total * (double) (c + 1) / (double) grid;
-			int segs_here = 0;
-			while (r < nroles && segs_here < kSyrkMaxSeg) {
-				const double cost = (bi == bj) ? wdiag : 64.0;
-				long long take;
-				if (c == grid - 1 && segs_here == kSyrkMaxSeg - 1) take = nchunks - pos;
-				else {
-					take = (long long) ((target - cum) / cost + 0.5);
-					if (c == grid - 1) take = nchunks - pos;
-					if (take > nchunks - pos) take = nchunks - pos;
-				}
-				if (take <= 0) break;
-				SyrkWork w;
-				w.bi = bi; w.bj = bj; w.slot = (int) work.size(); w.pad = 0;
-				w.chunk0 = pos; w.chunk1 = pos + take;
-				work.push_back(w);
-				if (nslots[r] == 0) slot0[r] = w.slot;
-				nslots[r]++;
-				segs_here++;
-				cum += cost * (double) take;
-				pos += take;
-				if (pos == nchunks) {
-					pos = 0; r++;
-					if (++bj > bi) { bj = 0; bi++; }
-				} else break;
-			}
-		}
-		cta_seg0[grid] = (int) work.size();
-		PNOL_REQUIRE(ctx, r == nroles, "syrk: internal: stream-K plan left work undistributed (m=%lld n=%d)", m, n);
+		const bool complete = syrk_streamk_plan_any(nchunks, nb, grid_cap, wdiag, work, cta_seg0, slot0, nslots, grid);
+		PNOL_REQUIRE(ctx, complete, "syrk: internal: stream-K plan left work undistributed (m=%lld n=%d)", m, n);
 	} else {
 		// one role per CTA: CTA budget per role proportional to its chunk cost
 		double wsum = 0;

@@ -70,3 +70,21 @@ def test_no_cpu_fallback():
     hostapi.detach()
     with pytest.raises(capi.PnolError):
         hostapi.gradient("rosenbrock", np.ones(4), np.full(4, 1e-6))
+
+
+def test_syrk_stream_k_plan_invariants():
+    # host logic of the J^T J kernel's work distribution (dmma.cu: syrk_streamk_plan), checked without a device: every K chunk of
+    # every tile role exactly once and in order, contiguous slots per role, at most 8 segments per CTA, shares within one chunk
+    lib = capi.load_library()
+    lib.pnol_selftest_syrk_plan.restype = C.c_int
+    lib.pnol_selftest_syrk_plan.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(5)
+    shapes = [(1, 16), (31, 16), (32, 16), (33, 128), (4737, 256), (100_000, 48), (7000, 272), (5000, 512), (300_000, 256),
+              (4_000_000, 256), (500_000, 256), (4_000_000, 16), (1_000_003, 640), (2_000_000_000, 32), (100_000, 4096),
+              (50_000, 8192), (777, 16384)]
+    shapes += [(int(rng.integers(1, 3_000_000)), int(16 * rng.integers(1, 45))) for _ in range(200)]
+    for m, n in shapes:
+        for sms in (1, 2, 7, 132, 148):
+            for with_f in (0, 1):
+                assert lib.pnol_selftest_syrk_plan(m, n, sms, with_f) == 0, (m, n, sms, with_f)
+    assert lib.pnol_selftest_syrk_plan(0, 16, 148, 0) == -1

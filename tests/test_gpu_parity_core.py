@@ -217,12 +217,13 @@ def test_lm_normal_eq(ctx, m, n):
 
 
 @pytest.mark.parametrize("m,n", [(1, 32), (31, 16), (33, 128), (64, 256), (4737, 256), (100_000, 48), (7000, 272), (5000, 512),
-                                 (300_000, 256), (2000, 144), (513, 192), (40, 240)])
+                                 (300_000, 256), (2000, 144), (513, 192), (40, 240), (700, 4096), (300, 8192)])
 def test_lm_normal_eq_stream_k_shapes(ctx, m, n):
     # shapes that stress the TMA / stream-K SYRK: fewer chunks than CTAs, ragged last chunk (rows beyond m are the TMA's zero
     # fill), partial 128-column tiles (n = 48, 272), 6 and 10 tile roles, CTAs that cross role boundaries (m = 300k); with and
     # without F (the LM step runs it without; with two tile rows -- n = 144 ... 256 -- that is the CTA-pair kernel, also with
-    # fewer chunks than clusters). Reference: numpy (BLAS) in double, bar 1e-12 norm-wise
+    # fewer chunks than clusters); n = 4096 / 8192: 528 / 2080 tile roles on 148 CTAs (several segments per CTA, two waves).
+    # Reference: numpy (BLAS) in double, bar 1e-12 norm-wise
     rng = np.random.default_rng(7 * m + n)
     J = rng.normal(size=(m, n)) * (1 + 0.05 * np.arange(n))
     F = rng.normal(size=m)
