@@ -377,8 +377,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__
                 const SyrkWork * __restrict__ segs, const int * __restrict__ cta_seg0, double * __restrict__ part_tiles,
                 double * __restrict__ part_rhs)
 {
-	extern __shared__ __align__(1024) unsigned char smem_raw[];
-	SyrkTmaStage * stages = reinterpret_cast<SyrkTmaStage *>(smem_raw);
+	extern __shared__ __align__(1024) unsigned char smem_tma[];      // (own name: the LDGSTS kernels declare theirs 16-byte aligned)
+	SyrkTmaStage * stages = reinterpret_cast<SyrkTmaStage *>(smem_tma);
 	__shared__ uint64_t full_bar[kSStages], empty_bar[kSStages];
 	__shared__ SyrkWork sseg[kSyrkMaxSeg];
 
@@ -558,8 +558,8 @@ __device__ __forceinline__ void pair_half_tile(double (&acc)[4][2][2], const dou
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSyrkTmaThreads, 1)
 syrk_pair_kernel(const __grid_constant__ CUtensorMap tmJ, long long nchunks, int nclusters, double * __restrict__ part_tiles)
 {
-	extern __shared__ __align__(1024) unsigned char smem_raw[];
-	SyrkPairStage * stages = reinterpret_cast<SyrkPairStage *>(smem_raw);
+	extern __shared__ __align__(1024) unsigned char smem_tma[];
+	SyrkPairStage * stages = reinterpret_cast<SyrkPairStage *>(smem_tma);
 	__shared__ uint64_t full_bar[kPairStages], empty_bar[kPairStages];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
