@@ -35,6 +35,7 @@ using namespace std;
 #include "BFGS_bnd_linesearch.hpp"
 #include "BFGS_bnd_linesearch_MPI_SW.hpp"
 #include "Box_boundary_functions.hpp"
+#include "SimplexSearch.hpp"
 
 #include "oracle_objectives.h"
 
@@ -329,6 +330,23 @@ static void setStreamFromArgs()
 	else shimStreamSetCounter( (unsigned long long) argi("seed", 12345), argd("scale", 1.0) );
 }
 
+// SimplexSearch::findMin of the verbatim reference (Source/SimplexSearch.cpp:13-226); its srand(time(0)) is harmless, the start
+// simplex comes from timeRand() = the host-supplied stream of the shim
+static int cmdSimplex()
+{
+	Objective * obj = makeScalar( arg("obj") );
+	vector<double> X = readf64( arg("x") );
+	setStreamFromArgs();
+	SimplexSearch s; s.setObjPtr( *obj );
+	s.setSimplexParams( argd("alpha", 1.0), argd("gamma", 2.0), argd("rho", 0.5), argd("sigma", 0.5), (int) argi("maxiter", 10000),
+			argd("initrandmax", 1.0), argd("xmindiff", 1e-7), false );
+	double f0 = 0, fOpt = 0;
+	s.findMin( X, f0, fOpt );
+	writef64( "X", X ); writeScalar( "f0", f0 ); writeScalar( "fOpt", fOpt );
+	writeScalar( "stream_pos", (double) shimStreamPosition() );
+	return 0;
+}
+
 static int cmdGA()
 {
 	Objective * obj = makeScalar( arg("obj") );
@@ -483,6 +501,7 @@ int main( int argc, char ** argv )
 	else if( cmd == "updhinv" ) rc = cmdUpdHinv();
 	else if( cmd == "bfgs" || cmd == "bfgs_mpi" || cmd == "bfgs_bnd" || cmd == "bfgs_bnd_sw" ) rc = cmdBfgs(cmd);
 	else if( cmd == "ga" ) rc = cmdGA();
+	else if( cmd == "simplex" ) rc = cmdSimplex();
 	else if( cmd == "popsort" || cmd == "checkbounds" || cmd == "checkidentical" ) rc = cmdGAStage(cmd);
 	else if( cmd == "box" ) rc = cmdBox();
 	else if( cmd == "bench_lm" ){ cout.rdbuf(0); rc = cmdBenchLM(); }

@@ -17,6 +17,7 @@
 #include "pnol/GeneticAlgorithm.hpp"
 #include "pnol/GeneticAlgorithmMPI.hpp"
 #include "pnol/Box_boundary_functions.hpp"
+#include "pnol/SimplexSearch.hpp"
 
 namespace {
 
@@ -255,6 +256,25 @@ int pnolhost_bfgs( const char * variant, const char * objective, double * X, int
 		if( f0 ) *f0 = a;
 		if( fOpt ) *fOpt = b;
 		if( iters ) *iters = it;
+	} );
+}
+
+// SimplexSearch::findMin on one of the example objectives. p[7] = alpha gamma rho sigma maxIter initRandMax xMinDiff; the start simplex
+// draws from the stream set with pnolhost_set_stream(). report[2] = iterations, stream position
+int pnolhost_simplex( const char * objective, double * X, int n, const double * p, int verbose, double * f0, double * fOpt, double * report )
+{
+	return guarded( [&] {
+		CoutSilencer quiet( verbose == 0 );
+		std::unique_ptr<Objective> obj = makeScalar( objective );
+		vector<double> Xv( X, X + n );
+		SimplexSearch alg; alg.setObjPtr( *obj );
+		alg.setSimplexParams( p[0], p[1], p[2], p[3], (int) p[4], p[5], p[6], verbose != 0 );
+		double a = 0, b = 0;
+		alg.findMin( Xv, a, b );
+		memcpy( X, Xv.data(), n*sizeof(double) );
+		if( f0 ) *f0 = a;
+		if( fOpt ) *fOpt = b;
+		if( report ) { report[0] = alg.iterations(); report[1] = (double) alg.streamPosition(); }
 	} );
 }
 

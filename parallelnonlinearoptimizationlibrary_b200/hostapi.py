@@ -206,6 +206,16 @@ def ga(objective, x0, xlb, xub, npop, maxgen, elite_frac=0.1, cross_frac=0.3, el
                 sizes=tuple(int(v) for v in rep[3:7]))
 
 
+def simplex(objective, x0, alpha=1.0, gamma=2.0, rho=0.5, sigma=0.5, maxiter=10000, init_rand_max=1.0, xmindiff=1e-7, verbose=0):
+    """SimplexSearch::findMin on an example objective; the start simplex draws from the stream of set_stream()"""
+    Xv = _f64(x0).copy()
+    p = _f64([alpha, gamma, rho, sigma, maxiter, init_rand_max, xmindiff])
+    f0, fopt = C.c_double(), C.c_double()
+    rep = np.zeros(2)
+    _check(lib().pnolhost_simplex(objective.encode(), _p(Xv), Xv.size, _p(p), int(verbose), C.byref(f0), C.byref(fopt), _p(rep)))
+    return dict(X=Xv, f0=f0.value, fOpt=fopt.value, iterations=int(rep[0]), stream_pos=int(rep[1]))
+
+
 def check_box_bounds(x, xlb, xub):
     Xv, lb, ub = _f64(x).copy(), _f64(xlb), _f64(xub)
     _check(lib().pnolhost_check_box_bounds(_p(Xv), _p(lb), _p(ub), Xv.size))

@@ -16,7 +16,7 @@ HOST_EXPORTS = ["pnolhost_last_error", "pnolhost_attach", "pnolhost_detach", "pn
                 "pnolhost_set_jac_mode", "pnolhost_set_jacobian_cache", "pnolhost_set_stream", "pnolhost_lm_lorentz", "pnolhost_lm_problem_create", "pnolhost_lm_problem_run", "pnolhost_lm_problem_destroy",
                 "pnolhost_lm_example",
                 "pnolhost_gradient", "pnolhost_gradient_recur", "pnolhost_hessian", "pnolhost_obj_eval", "pnolhost_jacobian_example",
-                "pnolhost_bfgs", "pnolhost_ga", "pnolhost_check_box_bounds", "pnolhost_compute_alpha_bnd"]
+                "pnolhost_bfgs", "pnolhost_ga", "pnolhost_simplex", "pnolhost_check_box_bounds", "pnolhost_compute_alpha_bnd"]
 
 
 def header_symbols():

@@ -90,3 +90,21 @@ def test_ga_stages():
     assert np.array_equal(Xb, g(c, "boundsX")) and np.array_equal(ib, g(c, "boundsInd")) and pb == int(g(c, "boundsPos")[0])
     Xi, ii, pi = O.ga_check_identical(g(c, "X"), g(c, "lb"), g(c, "ub"), dict(seed=5, scale=1.0))
     assert np.array_equal(Xi, g(c, "identX")) and np.array_equal(ii, g(c, "identInd")) and pi == int(g(c, "identPos")[0])
+
+
+def test_simplex_golden_is_what_the_verbatim_reference_produces():
+    # tests/golden/simplex_golden.npz against a fresh run of the reference's SimplexSearch::findMin (needs oracle/_ref)
+    import sys
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/pnol_ref_cli not built (needs /root/reference)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_simplex_golden as M
+    G2 = np.load(os.path.join(here, "golden", "simplex_golden.npz"))
+    for name, (obj, x0, kw, stream) in M.CASES.items():
+        r = M.run_reference(obj, x0, kw, stream)
+        for k in ("X", "f0", "fOpt", "stream_pos"):
+            assert np.array_equal(r[k], G2[name + "/" + k]), (name, k)
+    # known answers of the reference's example drivers: Rosenbrock -> 1, Booth -> (1, 3), Goldstein-Price -> (0, -1) with f = 3
+    assert np.allclose(G2["rosenbrock4/X"], 1.0, atol=1e-6) and np.allclose(G2["booth/X"], [1.0, 3.0], atol=1e-6)
+    assert np.allclose(G2["goldstein/X"], [0.0, -1.0], atol=1e-6) and abs(G2["goldstein/fOpt"][0] - 3.0) < 1e-9
