@@ -9,7 +9,7 @@
  *   - PowerObject multiplies repeatedly instead of calling pow(x, power) with a run-time exponent;
  *   - ExpCurve* use pnol::exp_hd (include/pnol/pnol_math.h) instead of libm exp; their DATA are still generated with
  *     libm exp/pow on the host exactly as the reference constructors do.
- * PowerObjectSlow (a deliberately slow busy-loop, :236-265) is not reproduced.
+ * PowerObjectSlow (:236-265) keeps its name and values; its deliberately slow busy-loop is not reproduced.
  */
 #ifndef PNOL_EXAMPLEOBJECTIVES_HPP_
 #define PNOL_EXAMPLEOBJECTIVES_HPP_
@@ -54,6 +54,10 @@ class PowerObject : public pnol::FunctorObjective<pnol::PowerFunctor> {
 	int getPower(){ return (int) P.ints[0]; }
 	PowerObject(){ P.ints[0] = 2; }
 };
+
+// Source/ExampleObjectives.hpp:238-271: PowerObject behind a busy loop ("slow computation for no reason") that the reference uses to
+// make testGAParallel's evaluations expensive. The values are PowerObject's; a device functor has nothing to wait for.
+class PowerObjectSlow : public PowerObject {};
 
 namespace pnol {
 // residual model backed by functor R with host-owned data columns

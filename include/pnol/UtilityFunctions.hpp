@@ -59,5 +59,35 @@ inline void print2DVector(const std::vector<std::vector<double> > & A)
 {
 	for (size_t i = 0; i < A.size(); i++) print1DVector(A[i]);
 }
+inline void setIdentity(std::vector<std::vector<double> > & A)
+{
+	for (size_t i = 0; i < A.size(); i++)
+		for (size_t j = 0; j < A[i].size(); j++) A[i][j] = (i == j) ? 1.0 : 0.0;
+}
+// small host inverse for user code (the reference's example driver testHessian calls it, Source/Examples.cpp:296):
+// Gauss-Jordan with partial pivoting on [A | I]. The algorithms here never call it -- an initial inverse Hessian is
+// solved on the device (pnol::InverseHessian::setFromInverseOfFDHessian).
+inline void matrixInverse(const std::vector<std::vector<double> > & A, std::vector<std::vector<double> > & Ainv)
+{
+	size_t n = A.size();
+	std::vector<std::vector<double> > M(A);
+	Ainv.assign(n, std::vector<double>(n, 0.0));
+	for (size_t i = 0; i < n; i++) Ainv[i][i] = 1.0;
+	for (size_t c = 0; c < n; c++)
+	{
+		size_t piv = c;
+		for (size_t r = c + 1; r < n; r++) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+		M[c].swap(M[piv]); Ainv[c].swap(Ainv[piv]);
+		double d = M[c][c];
+		for (size_t j = 0; j < n; j++) { M[c][j] = M[c][j] / d; Ainv[c][j] = Ainv[c][j] / d; }
+		for (size_t r = 0; r < n; r++)
+		{
+			if (r == c) continue;
+			double f = M[r][c];
+			if (f == 0.0) continue;
+			for (size_t j = 0; j < n; j++) { M[r][j] = M[r][j] - f * M[c][j]; Ainv[r][j] = Ainv[r][j] - f * Ainv[c][j]; }
+		}
+	}
+}
 
 #endif

@@ -37,7 +37,10 @@ using namespace std;
 #include "Box_boundary_functions.hpp"
 #include "SimplexSearch.hpp"
 
+#include "Examples.hpp"
 #include "oracle_objectives.h"
+
+static std::streambuf * gKeepCout = 0;
 
 double computeAlphaBnd( vector <double> & X, vector <double> & Xlb, vector <double> & Xub, vector <double> & p );
 
@@ -306,7 +309,15 @@ static int cmdBfgs( const string & variant )
 	{
 		vector<double> Xlb = argvec( "xlb", n, -5 ), Xub = argvec( "xub", n, 5 );
 		double alphaTol = argd("alphatol", 1e-10), alphaMult = argd("alphamult", 2);
-		if( variant == "bfgs_bnd" )
+		if( variant == "bfgsbnd_mpi" )
+		{
+			// Source/BFGS_with_bnd_linsearch_MPI.cpp:14-80; pool width = mini-MPI rank count. Its progress prints go to stdout.
+			BFGSBnd_MPI b; b.setObjPtr( *obj );
+			b.setParams( c1, c2, argd("alphamin", 1e-16), argd("maxalphamult", 4), alphaGuess, maxIterLS, dXGrad, dXHess, maxIter, xMinDiff, minGrad,
+					argd("fsteptol", 1e-5), initHess, argi("verbose", 0) != 0 );
+			b.findMinBnd( X, Xlb, Xub, f0, fOpt );
+		}
+		else if( variant == "bfgs_bnd" )
 		{
 			BFGS_Bnd b; b.setObjPtr( *obj );
 			b.setParams( c1, c2, dalpha, alphaGuess, alphaTol, alphaMult, maxIterLS, argd("bndtol", 1e-5), dXGrad, dXHess, maxIter, xMinDiff, minGrad, initHess, 0 );
@@ -320,6 +331,35 @@ static int cmdBfgs( const string & variant )
 		}
 	}
 	writef64( "X", X ); writeScalar( "f0", f0 ); writeScalar( "fOpt", fOpt );
+	return 0;
+}
+
+// the reference's own example drivers (Source/Examples.cpp), for side-by-side runs with oracle/_ref/pnol_examples_dropin
+static int cmdExample()
+{
+	string d = arg("name");
+	int rank = 0;
+	MPI_Comm_rank( MPI_COMM_WORLD, &rank );
+	if( rank == 0 ) cout.rdbuf( gKeepCout );          // the drivers print from every rank; keep the root's
+	shimStreamSetCounter( (unsigned long long) argi("seed", 12345), argd("scale", 1.0 - 1.0/1048576.0) );
+	if( d == "testBFGSBndMPISW" ) testBFGSBndMPISW();
+	else if( d == "testBFGSBnd" ) testBFGSBnd();
+	else if( d == "testBFGSBnd_MPI" ) testBFGSBnd_MPI();
+	else if( d == "testLMExpMPI" ) testLMExpMPI();
+	else if( d == "testBFGS_MPI" ) testBFGS_MPI();
+	else if( d == "testBFGS_booth" ) testBFGS_booth();
+	else if( d == "testBFGS" ) testBFGS();
+	else if( d == "testHessian" ) testHessian();
+	else if( d == "testGAParallel" ) testGAParallel();
+	else if( d == "testGA" ) testGA();
+	else if( d == "testLMExp" ) testLMExp();
+	else if( d == "testLMCubicLinearCoef" ) testLMCubicLinearCoef();
+	else if( d == "testSimplexSearch" ) testSimplexSearch();
+	else if( d == "testCreateObject" ) testCreateObject();
+	else if( d == "testGradientEvaluation" ) testGradientEvaluation();
+	else if( d == "testGradientApproxMultMPI" ) testGradientApproxMultMPI();
+	else if( d == "testGradientApproxMultMPIRecur" ) testGradientApproxMultMPIRecur();
+	else return 2;
 	return 0;
 }
 
@@ -490,6 +530,7 @@ int main( int argc, char ** argv )
 	MPI_Comm_rank( MPI_COMM_WORLD, &gRank );
 	// the reference prints progress unconditionally in places; keep stdout of non-root ranks quiet
 	std::streambuf * keep = cout.rdbuf();
+	gKeepCout = keep;
 	if( arg("quiet", "1") == "1" && cmd.compare(0, 5, "bench") != 0 ) cout.rdbuf(0);
 	int rc = 0;
 	if( cmd == "fdgrad" ) rc = cmdFdGrad();
@@ -499,11 +540,12 @@ int main( int argc, char ** argv )
 	else if( cmd == "fdjac" ) rc = cmdFdJac();
 	else if( cmd == "lm" ) rc = cmdLM();
 	else if( cmd == "updhinv" ) rc = cmdUpdHinv();
-	else if( cmd == "bfgs" || cmd == "bfgs_mpi" || cmd == "bfgs_bnd" || cmd == "bfgs_bnd_sw" ) rc = cmdBfgs(cmd);
+	else if( cmd == "bfgs" || cmd == "bfgs_mpi" || cmd == "bfgs_bnd" || cmd == "bfgs_bnd_sw" || cmd == "bfgsbnd_mpi" ) rc = cmdBfgs(cmd);
 	else if( cmd == "ga" ) rc = cmdGA();
 	else if( cmd == "simplex" ) rc = cmdSimplex();
 	else if( cmd == "popsort" || cmd == "checkbounds" || cmd == "checkidentical" ) rc = cmdGAStage(cmd);
 	else if( cmd == "box" ) rc = cmdBox();
+	else if( cmd == "example" ) rc = cmdExample();
 	else if( cmd == "bench_lm" ){ cout.rdbuf(0); rc = cmdBenchLM(); }
 	else if( cmd == "bench_ga_eval" ){ cout.rdbuf(0); rc = cmdBenchGAEval(); }
 	else { fprintf(stderr, "ref_cli: unknown command %s\n", cmd.c_str()); rc = 2; }

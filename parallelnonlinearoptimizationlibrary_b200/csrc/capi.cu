@@ -387,6 +387,9 @@ static int recur_assemble(pnol_ctx * ctx, const double * xr, int nr, const doubl
 	*xfull = (double *) ctx->ws[1];
 	*pos = (int *) (*xfull + nfull);
 	int * found = *pos + nfull;
+	// -1 = "no slot": a caller may pass more reduced entries than const_ind leaves free (BFGSBnd_MPI keeps iterating on the full
+	// vector after every variable has been frozen, Source/BFGS_with_bnd_linsearch_MPI.cpp:808-810)
+	PNOL_CUDA(ctx, cudaMemsetAsync(*pos, 0xFF, (size_t) nfull * sizeof(int), ctx->stream));
 	PNOL_CHECK(launch_assemble_recur(ctx, dxr.get(), nr, dcx.get(), dci.get(), nfull, *xfull, *pos, found));
 	return PNOL_OK;
 }

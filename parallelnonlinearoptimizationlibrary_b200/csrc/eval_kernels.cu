@@ -285,8 +285,10 @@ fd_points_kernel(FunctorParams P, const double * __restrict__ xfull, int nfull, 
 	__syncthreads();
 	int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < i1) {
+		// pos[i] < 0: reduced variable i has no slot in the full point (more reduced entries than free variables: the reference's
+		// objEvalRecur never reads it, Source/PNOL_Objective.cpp:311-323), so its stencil point is the base point itself
 		int pi = pos ? pos[i] : i;
-		PerturbAcc acc{xs, pi, xs[pi] + dx[i]};   // XdX[i] = XdX[i] + dX[i]  (Source/PNOL_Objective.cpp:27)
+		PerturbAcc acc{xs, pi, pi >= 0 ? xs[pi] + dx[i] : 0.0};   // XdX[i] = XdX[i] + dX[i]  (Source/PNOL_Objective.cpp:27)
 		fdx_out[i] = F::eval(P, acc, nfull);
 	} else if (i == i1 && f0_out) {
 		PtrAcc acc{xs};
@@ -329,7 +331,7 @@ int launch_fd_quotient(pnol_ctx * ctx, const double * fdx, const double * f0, co
 
 // Active-set assembly (Objective::objEvalRecur, Source/PNOL_Objective.cpp:303-323): the full point takes
 // const_x[j] where const_ind[j], else the next reduced variable. Also emits pos[i] (full index of reduced
-// variable i). Single block; a serial scan over chunks of blockDim entries.
+// variable i; the caller presets pos to -1, which stays for reduced entries beyond the number of free variables). Single block; a serial scan over chunks of blockDim entries.
 __global__ void assemble_recur_kernel(const double * __restrict__ xr, int nr,
                                       const double * __restrict__ const_x, const unsigned char * __restrict__ const_ind,
                                       int nfull, double * __restrict__ xfull, int * __restrict__ pos,

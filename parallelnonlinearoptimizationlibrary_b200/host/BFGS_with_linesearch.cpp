@@ -43,6 +43,8 @@ void InverseHessian::toHost( vector<vector<double> > & D ) const
 {
 	vector<double> flat( (size_t) n_*n_ );
 	D_.download( flat.data(), flat.size() );
+	D.resize( n_ );
+	for( int i = 0; i < n_; i++ ) D[i].resize( n_ );
 	for( int i = 0; i < n_; i++ ) for( int j = 0; j < n_; j++ ) D[i][j] = flat[(size_t) i*n_ + j];
 }
 

@@ -84,6 +84,11 @@ void BFGS_MPI::findMin( vector <double> & X, double & f0, double & fOpt )
 	}
 	iterationsDone = iter;
 	fOpt = F;
+	if( verbose == true )                                                    // (:130-138)
+	{
+		cout << endl << "Completed bfgs. f0 = " << f0 << ", fOpt = " << fOpt << " with variable:" << endl;
+		cout << "X = "; print1DVector( X );
+	}
 }
 
 // Source/BFGS_with_linesearch_MPI.cpp:226-492

@@ -1,6 +1,7 @@
 // SimplexSearch.cpp -- the Nelder-Mead controller of Source/SimplexSearch.cpp:13-349 on the host; every objective evaluation is a
 // pnol_eval_batch on the objective's device twin (one point, or all n + 1 vertices in one launch).
 #include "pnol/SimplexSearch.hpp"
+#include "pnol/UtilityFunctions.hpp"
 
 #include <cmath>
 #include <iostream>
@@ -170,7 +171,10 @@ void SimplexSearch::findMin( vector <double> & X, double & f0, double & fOpt )
 	fOpt = fvec[0];
 	for( int j = 0; j < Ndim; j++ ) X[j] = xvec[0][j];
 	if( verbose == true )
-		std::cout << "Completed simplex search. f0 = " << f0 << ", fOpt = " << fOpt << std::endl;
+	{
+		std::cout << "Completed simplex search. f0 = " << f0 << ", fOpt = " << fOpt << " with variable:" << std::endl;
+		std::cout << "X = "; print1DVector( X );
+	}
 }
 
 // Selection of the minimum Nd + 1 times, the taken entry overwritten with twice the largest value (:283-309). Two quirks of the

@@ -14,6 +14,7 @@
 #include "pnol/BFGS_with_linesearch_MPI.hpp"
 #include "pnol/BFGS_bnd_linesearch_MPI_SW.hpp"
 #include "pnol/BFGS_bnd_linesearch.hpp"
+#include "pnol/BFGS_with_bnd_linesearch_MPI.hpp"
 #include "pnol/GeneticAlgorithm.hpp"
 #include "pnol/GeneticAlgorithmMPI.hpp"
 #include "pnol/Box_boundary_functions.hpp"
@@ -209,9 +210,10 @@ int pnolhost_jacobian_example( const char * name, const double * X, const double
 	} );
 }
 
-// BFGS family. variant: "bfgs" | "bfgs_mpi" | "bfgs_bnd_sw". params (doubles):
+// BFGS family. variant: "bfgs" | "bfgs_mpi" | "bfgs_bnd" | "bfgs_bnd_sw" | "bfgsbnd_mpi". params (doubles):
 //   bfgs        : c1 c2 dalpha alphaGuess maxIterLS dXGrad dXHess maxIter xMinDiff minGrad2Norm initHessFD
 //   bfgs_mpi    : c1 c2 maxAlphaMult alphaGuess maxIterLS dXGrad dXHess maxIter xMinDiff minGrad2Norm initHessFD
+//   bfgsbnd_mpi : c1 c2 alphaMin maxAlphaMult alphaGuess maxIterLS dXGrad dXHess maxIter xMinDiff minGrad2Norm FStepTolerance initHessFD
 //   bfgs_bnd / bfgs_bnd_sw : c1 c2 dalpha alphaGuess alphaTol alphaMult maxIterLS bndTol dXGrad dXHess maxIter xMinDiff minGrad2Norm initHessFD
 int pnolhost_bfgs( const char * variant, const char * objective, double * X, int n, const double * p, const double * xlb, const double * xub,
 		int poolWidth, int verbose, double * f0, double * fOpt, int * iters )
@@ -248,6 +250,14 @@ int pnolhost_bfgs( const char * variant, const char * objective, double * X, int
 		{
 			BFGS_Bnd alg; alg.setObjPtr( *obj );
 			alg.setParams( p[0], p[1], p[2], p[3], p[4], p[5], (int) p[6], p[7], p[8], p[9], p[10], p[11], p[12], p[13] != 0, verbose );
+			vector<double> lb( xlb, xlb + n ), ub( xub, xub + n );
+			alg.findMinBnd( Xv, lb, ub, a, b ); it = alg.iterations();
+		}
+		else if( v == "bfgsbnd_mpi" )
+		{
+			BFGSBnd_MPI alg; alg.setObjPtr( *obj );
+			alg.setParams( p[0], p[1], p[2], p[3], p[4], (int) p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[12] != 0, verbose != 0 );
+			if( poolWidth > 0 ) alg.setPoolWidth( poolWidth );
 			vector<double> lb( xlb, xlb + n ), ub( xub, xub + n );
 			alg.findMinBnd( Xv, lb, ub, a, b ); it = alg.iterations();
 		}

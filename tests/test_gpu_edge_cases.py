@@ -70,6 +70,33 @@ def test_one_parameter_gradient_and_hessian(ctx):
     assert np.array_equal(ctx.fd_hessian(f, x, np.array([1e-3])), O.fd_hessian(of, x, np.array([1e-3])))
 
 
+@pytest.mark.parametrize("nfree", [0, 1, 3])
+def test_recur_gradient_with_more_reduced_entries_than_free_variables(ctx, nfree):
+    # BFGSBnd_MPI keeps calling the Recur stencils with the FULL vector after variables (even all of them) have been frozen
+    # (Source/BFGS_with_bnd_linsearch_MPI.cpp:808-810): objEvalRecur reads only as many reduced entries as there are free slots
+    # (Source/PNOL_Objective.cpp:311-323), the others never reach the objective and their gradient entries are exactly 0
+    n = 6
+    rng = np.random.default_rng(40 + nfree)
+    constx = rng.uniform(-1, 1, n)
+    ind = np.ones(n, dtype=np.uint8)
+    ind[:nfree] = 0
+    xr = rng.uniform(-1, 1, n)                                 # n reduced entries for nfree free slots
+    dxr = np.full(n, 1e-6)
+    for kind in (capi.F_ROSENBROCK, capi.F_RASTRIGIN):
+        f, of = ctx.functor(kind), O.OFunctor(kind)
+        g, f0 = ctx.fd_gradient_recur(f, xr, dxr, constx, ind)
+        gw, f0w = O.fd_gradient_recur(of, xr, dxr, constx, ind)
+        assert f0 == f0w and np.array_equal(g, gw) and np.all(g[nfree:] == 0.0)
+        assert ctx.eval_recur(f, xr, constx, ind) == O.eval_recur(of, xr, constx, ind)
+    # the same situation through the alpha pool: only the free slots move along p
+    f, of = ctx.functor(capi.F_ROSENBROCK), O.OFunctor(capi.F_ROSENBROCK)
+    p = rng.normal(size=n)
+    alpha = np.array([0.0, 0.1, 0.5, 1.0])
+    phi, _, bad = ctx.alpha_pool(f, xr, p, alpha, 0.0, want_dphi=False, const_x=constx, const_ind=ind)
+    want = [O.eval_recur(of, xr + a * p, constx, ind) for a in alpha]
+    assert bad == 0 and np.array_equal(phi, np.array(want))
+
+
 def test_invalid_arguments_return_status_codes(ctx):
     lib = ctx.lib
     f = ctx.functor(capi.F_ROSENBROCK)
