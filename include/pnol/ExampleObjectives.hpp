@@ -39,6 +39,9 @@ template <class F> class FunctorObjective : public Objective {
 	{
 		return dev.get( F::kKind, vector<double>( P.scalars, P.scalars + PNOL_MAX_SCALARS ), vector<long long>( P.ints, P.ints + PNOL_MAX_INTS ) );
 	}
+	void noteDeviceEvaluations( long long count ) { evals += (int) count; }
+	// host objEval calls + points evaluated on the device twin: for a serial algorithm the number the reference prints
+	// ("Optimization used ... function evaluations"); the reference's MPI classes count per rank, this is the total
 	double getEvals(){ return evals; }
 };
 }

@@ -33,6 +33,9 @@ class Objective {
 
 	// device twin of objEval: a functor of include/pnol/functors.hpp bound to the runtime's context
 	virtual pnol_functor * deviceFunctor() { return nullptr; }
+	// the stencils and algorithms report here how many points they evaluated on the device twin, so that stateful objectives can
+	// keep the counters the reference's fixtures keep in objEval (`evals++`, Source/ExampleObjectives.hpp:89)
+	virtual void noteDeviceEvaluations( long long count ) { (void) count; }
 
 	// forward-difference gradient (Source/PNOL_Objective.cpp:12-34)
 	void gradientApproximation( vector <double> & X, vector <double> & dX, vector <double> & dFdX );

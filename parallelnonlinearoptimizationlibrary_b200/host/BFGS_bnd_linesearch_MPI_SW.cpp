@@ -490,6 +490,7 @@ void BFGS_Bnd_MPI_SW::evaluateAlphaPoolAndDerivatives( vector <double> & alphaPo
 	int bad = 0;
 	rt.check( pnol_alpha_pool( rt.ctx(), f, X.data(), p.data(), (int) X.size(), alphaPool.data(), N, dalpha, nullptr,
 			constantX.data(), ind.data(), (int) constantX.size(), phiPool.data(), dphidalphaPool.data(), &bad ) );
+	objPtr->noteDeviceEvaluations( 2LL*N );                                  // lineSearchObj + lineSearchFDDerivative per entry (:629-640)
 	for( int i = 0; i < N; i++ )
 		if( phiPool[i] == 1e10 )
 		{

@@ -159,6 +159,7 @@ void BFGSBnd_MPI::evalAlphaPoolMPI( vector <double> & alphaPool, vector <double>
 	rt.check( pnol_alpha_pool( rt.ctx(), f, X.data(), p.data(), (int) X.size(), alphaPool.data(), N, 0.0, nullptr,
 			constantX.data(), ind.data(), (int) constantX.size(), phiPool.data(), nullptr, &bad ) );
 	poolLaunches = poolLaunches + 1;
+	objPtr->noteDeviceEvaluations( N );
 	if( bad > 0 )
 		throw pnol::Error( PNOL_ERR_NONFINITE, "BFGSBnd_MPI: line search crashed (objective returned NaN or inf on the alpha pool)" );
 }

@@ -126,6 +126,7 @@ void BFGS::evalPhiAndSlope( double alpha, vector <double> & X, vector <double> &
 	int bad = 0;
 	rt.check( pnol_alpha_pool( rt.ctx(), f, X.data(), p.data(), (int) X.size(), &alpha, 1, dalpha, nullptr, nullptr, nullptr,
 			(int) X.size(), &phi, &dphi, &bad ) );
+	if( bad == 0 ) objPtr->noteDeviceEvaluations( 2 );                        // phi and the point of its forward-difference slope
 	if( bad > 0 )
 	{
 		// the serial reference lets NaN/inf flow into its comparisons; reproduce that by re-evaluating on the host

@@ -22,6 +22,7 @@ void BFGS_MPI::evalAlphaPoolMPI( vector <double> & alphaPool, vector <double> & 
 	int bad = 0;
 	rt.check( pnol_alpha_pool( rt.ctx(), f, X.data(), p.data(), (int) X.size(), alphaPool.data(), (int) phiPool.size(), 0.0, nullptr,
 			nullptr, nullptr, (int) X.size(), phiPool.data(), nullptr, &bad ) );
+	objPtr->noteDeviceEvaluations( (long long) phiPool.size() );
 	if( bad > 0 )
 		for( size_t i = 0; i < phiPool.size(); i++ )
 			if( phiPool[i] == 1e10 ) phiPool[i] = lineSearchObj( alphaPool[i], X, p );

@@ -63,6 +63,7 @@ void gaFindMinBnd( Objective * objPtr, int Npop, int maxGenerations, double elit
 		rt.check( pnol_ga_init( ga, X.data(), &f0 ) );                         // (:55-81)
 		pnol_ga_status st;
 		rt.check( pnol_ga_status_get( ga, &st ) );
+		objPtr->noteDeviceEvaluations( Npop );                                // initial population (:76)
 		if( verbose )
 			cout << "Computing genetic algorithm with population Nelite = " << st.n_elite << ", NeliteMut = " << st.n_elite_mut
 			     << ", Ncross = " << st.n_cross << ", Nrand = " << st.n_rand << endl;
@@ -70,6 +71,7 @@ void gaFindMinBnd( Objective * objPtr, int Npop, int maxGenerations, double elit
 		{
 			rt.check( pnol_ga_generation( ga ) );
 			rt.check( pnol_ga_status_get( ga, &st ) );
+			objPtr->noteDeviceEvaluations( Npop - st.n_elite );               // elites keep their value (:108-118, :220)
 			if( verbose ) cout << "At generation = " << st.generation << " minimum of f = " << st.f_best << endl;
 		}
 		// store result (:255-259): the best individual is row 0 of the sorted population
@@ -104,6 +106,9 @@ static void evaluateRows( Objective * objPtr, vector<vector<double> > & Xpop, ve
 	for( size_t i = 0; i < ind.size(); i++ ) ind[i] = evaluateIndicator[i] ? 1 : 0;
 	int n = Xpop.empty() ? 0 : (int) Xpop[0].size();
 	rt.check( pnol_eval_batch( rt.ctx(), f, flat.data(), (long long) Xpop.size(), n, n, ind.data(), F.data() ) );
+	long long evaluated = 0;
+	for( size_t i = 0; i < ind.size(); i++ ) evaluated += ind[i];
+	objPtr->noteDeviceEvaluations( evaluated );
 }
 
 // Source/GeneticAlgorithmMPI.cpp:283-414

@@ -26,6 +26,7 @@ void Objective::gradientApproximation( vector <double> & X, vector <double> & dX
 	pnol::Runtime & rt = pnol::Runtime::instance();
 	pnol_functor * f = requireFunctor( "Objective::gradientApproximation" );
 	rt.check( pnol_fd_gradient( rt.ctx(), f, X.data(), dX.data(), (int) X.size(), dFdX.data(), nullptr ) );
+	noteDeviceEvaluations( (long long) X.size() + 1 );                        // N + 1 points (:19-32)
 }
 
 // Source/PNOL_Objective.cpp:88-159: the reference deals the N+1 evaluations out to MPI ranks and sums; the values are
@@ -43,6 +44,7 @@ void Objective::hessianApproximation( vector <double> & X, vector <double> & dX,
 	int N = (int) X.size();
 	vector<double> flat( (size_t) N*N );
 	rt.check( pnol_fd_hessian( rt.ctx(), f, X.data(), dX.data(), N, flat.data() ) );
+	noteDeviceEvaluations( 3LL*N*(N + 1)/2 + 1 );                            // what the reference evaluates (:47-71); the kernels reuse f_i
 	for( int i = 0; i < N; i++ )
 		for( int j = 0; j < N; j++ )
 			H[i][j] = flat[(size_t) i*N + j];
@@ -72,6 +74,7 @@ void Objective::gradientApproximationRecur( vector <double> & X, vector <double>
 	for( size_t i = 0; i < ind.size(); i++ ) ind[i] = constantIndicator[i] ? 1 : 0;
 	rt.check( pnol_fd_gradient_recur( rt.ctx(), f, X.data(), dX.data(), (int) X.size(), constantX.data(), ind.data(),
 			(int) constantX.size(), dFdX.data(), nullptr ) );
+	noteDeviceEvaluations( (long long) X.size() + 1 );                        // (:345-358)
 }
 
 // Source/PNOL_Objective.cpp:366-459

@@ -50,6 +50,7 @@ double SimplexSearch::evaluateVariableArray( double * x, vector <double> & X )
 	double fval = 0;
 	const int n = (int) X.size();
 	rt.check( pnol_eval_batch( rt.ctx(), f, X.data(), 1, n, n, nullptr, &fval ) );
+	objPtr->noteDeviceEvaluations( 1 );
 	return fval;
 }
 
@@ -71,6 +72,7 @@ void SimplexSearch::evaluateVariableSet( double ** xvec, int Nsimplex, vector <d
 		pts = packed.data();
 	}
 	rt.check( pnol_eval_batch( rt.ctx(), f, pts, Nsimplex, n, n, nullptr, fvec ) );
+	objPtr->noteDeviceEvaluations( Nsimplex );
 	// the reference evaluates the vertices one after the other through X (:262-264): X holds the last one afterwards
 	for( int j = 0; j < n; j++ ) X[j] = xvec[Nsimplex - 1][j];
 }

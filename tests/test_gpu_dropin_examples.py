@@ -111,6 +111,9 @@ def test_bfgs_family_drivers_end_where_the_reference_ends(run, driver, xkey, xto
     assert abs(fa - fb) <= ftol * max(abs(fb), 1e-6), (fa, fb)
     if driver == "testBFGSBnd_MPI":
         assert a[0] == -1.0 and abs(fa - 4.0) < 1e-6
+    if driver == "testBFGSBnd":
+        # serial class, same path: getEvals() (host objEval calls + points evaluated on the device twin) is the reference's count
+        assert scalar(ours, "Optimization used") == scalar(ref, "Optimization used") == 397
 
 
 def test_simplex_search_driver(run):
@@ -119,3 +122,4 @@ def test_simplex_search_driver(run):
     assert scalar(ours, "f0 =") == scalar(ref, "f0 =") and abs(fa - fb) < 1e-4       # both print 5-6 significant digits
     a, b = vectors(ours, "X = ")[-1], vectors(ref, "X = ")[-1]                     # the reference prints 5 digits
     assert np.allclose(a, b, atol=2e-5)
+    assert scalar(ours, "Optimization used") == scalar(ref, "Optimization used")  # same number of objective evaluations
