@@ -52,6 +52,10 @@ class Runtime {
 	// (Source/LevenbergMarquardtMPI.cpp:60 after :120-129); false reproduces that work, the results are the same.
 	bool jacobianCache() const { return jacCache_; }
 	void setJacobianCache(bool on) { jacCache_ = on; }
+	// LM: keep the whole Jacobian in HBM (default), or sum the normal equations over row blocks and never store J
+	// (work space 512 MB instead of m*n*8 bytes; same iterates up to the summation order of J^T J)
+	bool storeJacobian() const { return storeJ_; }
+	void setStoreJacobian(bool on) { storeJ_ = on; }
 	void check(int status) const;             // throws pnol::Error with pnol_last_error() text
   private:
 	Runtime();
@@ -64,6 +68,7 @@ class Runtime {
 	int hinvMode_;
 	int jacMode_;
 	bool jacCache_;
+	bool storeJ_ = true;
 };
 
 // RAII device functor (the device twin an Objective / MultiObjective hands to the algorithms)

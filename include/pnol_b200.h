@@ -181,7 +181,8 @@ int pnol_lm_damp(pnol_ctx * ctx, const double * JTJ, int n, double lambda, doubl
  * FD Jacobian at x -> J^T J | J^T F (+ all-reduce over the ranks) -> Marquardt damping -> Cholesky solve -> x_trial = x + sigma ->
  * Ftrial = F(x_trial) and its sum of squares (+ all-reduce). The accept / reject decision stays with the caller as in the reference.
  *   x, dx       host or device, n
- *   J           device, m x n work space (m = rows of the functor); F device: residuals at x; Ftrial device: receives F(x_trial)
+ *   J           device, m x n work space (m = rows of the functor), or NULL: the normal equations are then summed over row blocks
+ *               and J is never stored (see pnol_lm_normal_eq_fused); F device: residuals at x; Ftrial device: receives F(x_trial)
  *   JTJ         device, n*n + n doubles: receives J^T J followed by -J^T F. reuse_jtj != 0: J^T J / rhs are taken from it instead of
  *               being recomputed (x unchanged after a rejected step), only the damping is redone with the new lambda
  *   sigma_out, x_trial_out (host, n), sumsq_trial_out, spd_info_out (host): the step, the trial point, sum Ftrial^2 over all
@@ -199,7 +200,13 @@ int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const do
                     double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
                     int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out);
 
-/* fused variant: J is never materialised; needs a functor with a structured Jacobian */
+/* SURVEY.md 8(f) item 2 -- the normal equations without J in HBM: the rows are walked in blocks (512 MB of J per block by default,
+ * $PNOL_FUSED_MB), each block's Jacobian is written to a scratch buffer, read back by the SYRK and its J^T J | J^T F added to the
+ * running sum in row order (deterministic; equal to pnol_fd_jacobian + pnol_lm_normal_eq up to summation order). Work space 512 MB
+ * instead of m*n*8 bytes: the memory-footprint mode (9 % slower than the stored-J path at m = 4M, n = 256; both are FP64-bound). Any
+ * residual functor (structured or black-box Jacobian). F (optional, host or device, m doubles) receives the residuals at x;
+ * JTJ / A / rhs as in pnol_lm_normal_eq. Replaces Source/LevenbergMarquardtMPI.cpp:60-85 in one call. pnol_lm_step / pnol_lm_iterate
+ * take the same path when their J argument is NULL. */
 int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n,
                             double lambda, double * JTJ, double * A, double * rhs, double * F);
 

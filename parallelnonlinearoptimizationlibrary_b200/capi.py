@@ -400,6 +400,18 @@ class Context:
                                               _ptr(A), _ptr(rhs)))
         return JTJ, A, rhs
 
+    def lm_normal_eq_fused(self, f, x, dx, n, lam, JTJ=None, A=None, rhs=None, F=None, want_F=True):
+        """normal equations straight from the residual model, J never stored (walked in row blocks):
+        returns (JTJ, A, rhs, F)"""
+        x, dx = _f64(x), _f64(dx)
+        if JTJ is None and A is None and rhs is None:
+            JTJ, A, rhs = np.empty((n, n)), np.empty((n, n)), np.empty(n)
+        if F is None and want_F:
+            F = np.empty(f.m, dtype=np.float64)
+        self.check(self.lib.pnol_lm_normal_eq_fused(self.h, f.handle, _ptr(x), _ptr(dx), int(n), C.c_double(lam), _ptr(JTJ), _ptr(A),
+                                                    _ptr(rhs), _ptr(F)))
+        return JTJ, A, rhs, F
+
     def lm_step(self, f, x, dx, n, J, F, Ftrial, lam, JTJ, jac_mode=JAC_AUTO, reuse_jtj=False):
         """one LM iteration's device work, one synchronisation: returns (sigma, x_trial, sumsq_trial, spd_info)"""
         x, dx = _f64(x), _f64(dx)

@@ -594,13 +594,16 @@ __global__ void lm_trial_point_kernel(const double * __restrict__ x, const doubl
 	xt[i] = x[i] + s;                       // X[i] = X[i] + sigma[i]   (:97-100)
 }
 
+static int normal_eq_blocks(pnol_ctx * ctx, const pnol_functor * f, const double * x_dev, const double * dx_dev, int n, int jac_mode,
+                            const double * F_known, double * F_out, double * total);
+
 extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J, const double * F,
                             double * Ftrial, double lambda, int jac_mode, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
                             double * sumsq_trial_out, int * spd_info_out)
 {
 	if (!ctx || !f) return PNOL_ERR_INVALID;
-	PNOL_REQUIRE(ctx, x && dx && J && F && Ftrial && JTJ && n >= 1, "lm_step: bad arguments");
-	PNOL_REQUIRE(ctx, is_device_ptr(J) && is_device_ptr(F) && is_device_ptr(Ftrial) && is_device_ptr(JTJ), "lm_step: J, F, Ftrial and JTJ must be device memory");
+	PNOL_REQUIRE(ctx, x && dx && F && Ftrial && JTJ && n >= 1, "lm_step: bad arguments");
+	PNOL_REQUIRE(ctx, (!J || is_device_ptr(J)) && is_device_ptr(F) && is_device_ptr(Ftrial) && is_device_ptr(JTJ), "lm_step: J, F, Ftrial and JTJ must be device memory");
 	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_step: the functor is not a residual model");
 	const long long m = f->params.m;
 	DevIn<double> dx_, ddx;
@@ -619,11 +622,16 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	if (!reuse_jtj) {
 		// J^T F: summed by the structured Jacobian kernel while it holds the rows of J (cheap there); the black-box kernel leaves
 		// it to the SYRK (extra tensor tiles). Either way it ends behind J^T J in `packed`, before the all-reduce.
-		bool jtf_done = false;
-		double * jtf = sig;      // free until the solve
-		PNOL_CHECK(launch_fd_jacobian(ctx, f, dx_.get(), ddx.get(), n, J, nullptr, jac_mode, F, jtf, &jtf_done));
-		PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed));
-		if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		if (!J) {
+			// no J buffer given: the normal equations are summed over row blocks, J is never stored (normal_eq_blocks)
+			PNOL_CHECK(normal_eq_blocks(ctx, f, dx_.get(), ddx.get(), n, jac_mode, F, nullptr, packed));
+		} else {
+			bool jtf_done = false;
+			double * jtf = sig;      // free until the solve
+			PNOL_CHECK(launch_fd_jacobian(ctx, f, dx_.get(), ddx.get(), n, J, nullptr, jac_mode, F, jtf, &jtf_done));
+			PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed));
+			if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		}
 		if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, packed, packed_count));
 		PNOL_CHECK(launch_lm_damp(ctx, packed, n, lambda, JTJ, A, rhs));
 		// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it
@@ -703,12 +711,96 @@ extern "C" int pnol_selftest_syrk_plan(long long m, int n, int sm_count, int wit
 	return syrk_plan_selftest(m, n, sm_count, with_f);
 }
 
-extern "C" int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double,
-                                       double *, double *, double *, double *)
+__global__ void packed_accumulate_kernel(double * __restrict__ acc, const double * __restrict__ add, long long count)
 {
-	if (!ctx) return PNOL_ERR_INVALID;
-	PNOL_SET_ERR(ctx, "fused Jacobian -> JTJ kernel is not built yet (SURVEY.md 8(f) item 2)");
-	return PNOL_ERR_NO_FUNCTOR;
+	long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) acc[i] = acc[i] + add[i];
+}
+
+// the normal equations without J in HBM. The rows are walked in blocks: the Jacobian kernel writes a block
+// of J (512 MB by default, PNOL_FUSED_MB overrides) into a scratch buffer, the SYRK reads it back, the block's J^T J | J^T F is
+// added to the running sum: work space 512 MB instead of m*n*8 bytes (8.19 GB at m = 4M, n = 256), so m is no longer limited by
+// the 180 GB of HBM. It is the memory-footprint mode, not a faster one: both kernels are bound by the FP64 unit, not by HBM
+// (DESIGN.md section 5.1), and every block pays the SYRK's ramp-up and reduction. Measured at m = 4M, n = 256
+// (profiles/r01_fused_sweep.txt): 35.6 / 21.9 / 15.2 / 13.2 / 12.1 / 11.5 / 10.9 ms per call with 16 / 32 / 64 / 128 / 256 / 512 /
+// 1024 MB blocks against 10.56 ms for the stored-J path -- blocks small enough to stay in the L2 are the slowest.
+// The block sums are added in row order, so the result is deterministic; it differs from the stored-J path in summation order only.
+//   F_known (device, m) != nullptr: the residuals at x are known (LM step): J^T F comes from the structured Jacobian kernel when it
+//                                   can provide it, else from the SYRK, as in pnol_lm_step;
+//   F_known == nullptr:             the residuals are computed with the Jacobian and written to F_out (device, m) when wanted.
+// `total` (device, n*n + n) receives J^T J followed by J^T F of this rank's rows (no all-reduce here).
+static int normal_eq_blocks(pnol_ctx * ctx, const pnol_functor * f, const double * x_dev, const double * dx_dev, int n, int jac_mode,
+                            const double * F_known, double * F_out, double * total)
+{
+	const long long m = f->params.m;
+	const char * env_mb = getenv("PNOL_FUSED_MB");       // read per call: tests walk several block sizes in one process
+	double block_mb = env_mb ? atof(env_mb) : 512.0;    // fractions allowed (tests: 0.1 MB -> the 1024-row minimum)
+	if (!(block_mb > 0.0)) block_mb = 512.0;
+	long long rows = (long long) (block_mb * 1048576.0) / ((long long) n * (long long) sizeof(double));
+	rows = rows / 1024 * 1024;                      // keeps every block of J and F 8 KB-aligned (TMA, double2 stores)
+	if (rows < 1024) rows = 1024;
+	if (rows > m) rows = m > 0 ? m : 1;
+	const size_t nn = (size_t) n * n, packed_count = nn + n;
+	// scratch (stream-ordered pool): block of J | residuals of the block | block sum | J^T F of the block
+	const size_t j_count = (size_t) rows * n;
+	double * scratch = nullptr;
+	PNOL_CUDA(ctx, cudaMallocAsync(&scratch, (j_count + (size_t) rows + packed_count + (size_t) n + 64) * sizeof(double), ctx->stream));
+	double * Jb = scratch, * Fb = Jb + j_count, * part = Fb + rows, * jtf = part + packed_count;
+	int st = PNOL_OK;
+	if (cudaMemsetAsync(total, 0, packed_count * sizeof(double), ctx->stream) != cudaSuccess) st = PNOL_ERR_CUDA;
+	for (long long r0 = 0; r0 < m && st == PNOL_OK; r0 += rows) {
+		const long long nr = (m - r0 < rows) ? (m - r0) : rows;
+		pnol_functor view = *f;                     // the same model on rows [r0, r0 + nr): data columns advanced, row count cut
+		for (int c = 0; c < f->n_columns && c < PNOL_MAX_COLUMNS; c++)
+			if (view.params.col[c]) view.params.col[c] = f->params.col[c] + r0;
+		view.params.m = nr;
+		if (F_known) {
+			bool jtf_done = false;
+			st = launch_fd_jacobian(ctx, &view, x_dev, dx_dev, n, Jb, nullptr, jac_mode, F_known + r0, jtf, &jtf_done);
+			if (st == PNOL_OK) st = launch_syrk(ctx, Jb, jtf_done ? nullptr : F_known + r0, nr, n, part);
+			if (st == PNOL_OK && jtf_done &&
+			    cudaMemcpyAsync(part + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) st = PNOL_ERR_CUDA;
+		} else {
+			double * Fr = F_out ? F_out + r0 : Fb;
+			st = launch_fd_jacobian(ctx, &view, x_dev, dx_dev, n, Jb, Fr, jac_mode);
+			if (st == PNOL_OK) st = launch_syrk(ctx, Jb, Fr, nr, n, part);
+		}
+		if (st == PNOL_OK) {
+			packed_accumulate_kernel<<<(unsigned) ((packed_count + 255) / 256), 256, 0, ctx->stream>>>(total, part, (long long) packed_count);
+			ctx->launches++;
+			if (cudaGetLastError() != cudaSuccess) st = PNOL_ERR_CUDA;
+		}
+	}
+	cudaFreeAsync(scratch, ctx->stream);
+	if (st == PNOL_ERR_CUDA && ctx->err.empty()) PNOL_SET_ERR(ctx, "normal_eq_blocks: CUDA error in the block loop");
+	return st;
+}
+
+extern "C" int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n,
+                                       double lambda, double * JTJ, double * A, double * rhs, double * F)
+{
+	if (!ctx || !f) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, x && dx && n >= 1, "lm_normal_eq_fused: bad arguments");
+	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_normal_eq_fused: the functor is not a residual model");
+	const long long m = f->params.m;
+	DevIn<double> dx_, ddx; DevOut<double> oJTJ, oA, orhs, oF;
+	PNOL_CHECK(dx_.init(ctx, x, n));
+	PNOL_CHECK(ddx.init(ctx, dx, n));
+	PNOL_CHECK(oJTJ.init(ctx, JTJ, (size_t) n * n));
+	PNOL_CHECK(oA.init(ctx, A, (size_t) n * n));
+	PNOL_CHECK(orhs.init(ctx, rhs, (size_t) n));
+	PNOL_CHECK(oF.init(ctx, F, (size_t) m));
+	const size_t packed_count = (size_t) n * n + n;
+	PNOL_CHECK(ws_reserve(ctx, 3, packed_count * sizeof(double)));
+	double * total = (double *) ctx->ws[3];
+	PNOL_CHECK(normal_eq_blocks(ctx, f, dx_.get(), ddx.get(), n, PNOL_JAC_AUTO, nullptr, oF.get(), total));
+	if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, total, packed_count));
+	PNOL_CHECK(launch_lm_damp(ctx, total, n, lambda, oJTJ.get(), oA.get(), orhs.get()));
+	PNOL_CHECK(oJTJ.commit());
+	PNOL_CHECK(oA.commit());
+	PNOL_CHECK(orhs.commit());
+	PNOL_CHECK(oF.commit());
+	return finish(ctx);
 }
 
 extern "C" int pnol_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info)

@@ -26,7 +26,8 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 		throw Error( PNOL_ERR_INVALID, "LevMarq::findMin: F0 / FOpt must be pre-sized to the number of residuals" );
 
 	// Storage (:27-38): J and the residual vectors live on the device; there is no JT copy. JTJ holds J^T J followed by -J^T F.
-	DeviceArray J( (size_t) Ndata*Nparam ), F( Ndata ), Ftrial( Ndata ), JTJ( (size_t) Nparam*Nparam + Nparam );
+	// With Runtime::setStoreJacobian(false) no J is allocated: pnol_lm_step sums the normal equations over row blocks.
+	DeviceArray J( rt.storeJacobian() ? (size_t) Ndata*Nparam : 0 ), F( Ndata ), Ftrial( Ndata ), JTJ( (size_t) Nparam*Nparam + Nparam );
 	DeviceArray dXdev( Nparam );
 	vector <double> dX( Nparam, dXGrad );
 	vector <double> sigma( Nparam, 0 );
@@ -52,7 +53,7 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 		// A zero / negative pivot (e.g. a zero column of J) comes back as a NaN step: the reference's luSolve would return
 		// inf/NaN there and the step would be rejected through the NaN test at :110. Same outcome here.
 		int info = 0;
-		rt.check( pnol_lm_step( ctx, f, X.data(), dXdev.data(), Nparam, J.data(), F.data(), Ftrial.data(), lambda, rt.jacobianMode(),
+		rt.check( pnol_lm_step( ctx, f, X.data(), dXdev.data(), Nparam, rt.storeJacobian() ? J.data() : nullptr, F.data(), Ftrial.data(), lambda, rt.jacobianMode(),
 				jacobianCurrent ? 1 : 0, JTJ.data(), sigma.data(), Xtrial.data(), &sumsq, &info ) );
 		jacobianCurrent = rt.jacobianCache();
 

@@ -60,6 +60,7 @@ int pnolhost_detach() { return guarded( [&] { pnol::Runtime::instance().reset();
 int pnolhost_set_pool_width( int w ) { pnol::Runtime::instance().setPoolWidth( w ); return PNOL_OK; }
 int pnolhost_set_hinv_mode( int m ) { pnol::Runtime::instance().setHessianUpdateMode( m ); return PNOL_OK; }
 int pnolhost_set_jacobian_cache( int on ) { pnol::Runtime::instance().setJacobianCache( on != 0 ); return PNOL_OK; }
+int pnolhost_set_store_jacobian( int on ) { pnol::Runtime::instance().setStoreJacobian( on != 0 ); return PNOL_OK; }
 int pnolhost_set_jac_mode( int m ) { pnol::Runtime::instance().setJacobianMode( m ); return PNOL_OK; }
 int pnolhost_set_stream( const double * values, unsigned long long n_values, unsigned long long seed, double scale )
 {

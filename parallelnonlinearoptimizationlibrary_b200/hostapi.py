@@ -74,6 +74,11 @@ def set_jacobian_cache(on):
     lib().pnolhost_set_jacobian_cache(int(bool(on)))
 
 
+def set_store_jacobian(on):
+    """False: LM never stores J (normal equations summed over row blocks, pnol::Runtime::setStoreJacobian)"""
+    lib().pnolhost_set_store_jacobian(int(bool(on)))
+
+
 _stream_keep = None
 
 

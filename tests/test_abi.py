@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "pnol_b200.h")
 
 HOST_EXPORTS = ["pnolhost_last_error", "pnolhost_attach", "pnolhost_detach", "pnolhost_set_pool_width", "pnolhost_set_hinv_mode",
-                "pnolhost_set_jac_mode", "pnolhost_set_jacobian_cache", "pnolhost_set_stream", "pnolhost_lm_lorentz", "pnolhost_lm_problem_create", "pnolhost_lm_problem_run", "pnolhost_lm_problem_destroy",
+                "pnolhost_set_jac_mode", "pnolhost_set_jacobian_cache", "pnolhost_set_store_jacobian", "pnolhost_set_stream", "pnolhost_lm_lorentz", "pnolhost_lm_problem_create", "pnolhost_lm_problem_run", "pnolhost_lm_problem_destroy",
                 "pnolhost_lm_example",
                 "pnolhost_gradient", "pnolhost_gradient_recur", "pnolhost_hessian", "pnolhost_obj_eval", "pnolhost_jacobian_example",
                 "pnolhost_bfgs", "pnolhost_ga", "pnolhost_simplex", "pnolhost_check_box_bounds", "pnolhost_compute_alpha_bnd"]

@@ -114,6 +114,16 @@ def test_invalid_arguments_return_status_codes(ctx):
         ctx.functor(999)
     with pytest.raises(capi.PnolError):
         ctx.functor(capi.F_LORENTZ_SUM, (4.0,), (), (), 10)          # data columns missing
+    # the sum-of-Lorentzians model adds its terms in a balanced binary tree: K = n / 2 must be a power of two
+    pr = problems.lorentz_problem(64, 4)
+    fl = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), 64)
+    for bad_n in (6, 7, 10):
+        with pytest.raises(capi.PnolError, match="not 2"):
+            ctx.residual_eval(fl, np.ones(bad_n))
+        with pytest.raises(capi.PnolError, match="not 2"):
+            ctx.fd_jacobian(fl, np.ones(bad_n), np.full(bad_n, 1e-7))
+        with pytest.raises(capi.PnolError, match="not 2"):
+            ctx.lm_normal_eq_fused(fl, np.ones(bad_n), np.full(bad_n, 1e-7), bad_n, 0.1)
     with pytest.raises(capi.PnolError):
         ctx.ga_create(f, 4, np.zeros(4), np.ones(4), 1, 5, dict(seed=1, scale=0.5))    # npop < 2
     with pytest.raises(capi.PnolError):

@@ -193,3 +193,21 @@ def test_lm_problem_handle_matches_one_shot_call(host):
     assert np.array_equal(Xa, b["X"]) and np.array_equal(Xa, one["X"]) and np.array_equal(Fa, one["F"])
     assert np.array_equal(b["F0"], g(c, "F0")) and rel(Xa, g(c, "X")) < RTOL
     prob.close()
+
+
+@pytest.mark.parametrize("case", ["lm_lorentz_K8", "lm_lorentz_K16"])
+def test_lm_without_a_stored_jacobian(host, case, monkeypatch):
+    # pnol::Runtime::setStoreJacobian(false): LevMarqMPI allocates no J, pnol_lm_step sums J^T J | J^T F over
+    # row blocks (0.1 MB of J here = the 1024-row minimum, so that the m = 2000 fit takes two blocks). Same iterates as the reference to the 1e-9 bar,
+    # F0 bit-exact, and equal to the stored-J run up to the summation order of the normal equations
+    monkeypatch.setenv("PNOL_FUSED_MB", "0.1")
+    args = (g(case, "t"), g(case, "y"), float(g(case, "w")), g(case, "x0"), 0.001, 10.0, 1e-7, int(g(case, "iters")), 0.0)
+    stored = host.lm_lorentz(*args)
+    host.set_store_jacobian(False)
+    try:
+        r = host.lm_lorentz(*args)
+    finally:
+        host.set_store_jacobian(True)
+    assert np.array_equal(r["F0"], g(case, "F0"))
+    assert rel(r["X"], g(case, "X")) < RTOL and rel(r["X"], stored["X"]) < RTOL
+    assert r["iterations"] == stored["iterations"]

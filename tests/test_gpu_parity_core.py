@@ -216,6 +216,36 @@ def test_lm_normal_eq(ctx, m, n):
     assert np.array_equal(np.diag(A), (1 + lam) * np.diag(JTJ))
 
 
+@pytest.mark.parametrize("m,K,mb", [(5000, 8, 0.1), (5000, 8, 64), (9001, 128, 1), (70_000, 16, 1), (1500, 512, 0.1), (1, 8, 1)])
+def test_lm_normal_eq_fused_equals_the_two_kernel_path(ctx, m, K, mb, monkeypatch):
+    # J never stored -- the rows are walked in blocks (PNOL_FUSED_MB of J per block; 1 MB here so that small
+    # problems take several blocks (5, 1, 9, 18, 2, 1 here), the ragged last one included; K = 512 has no structured kernel: black-box Jacobian per block).
+    # F bit-exact vs the residual kernel and the oracle; J^T J / rhs vs the stored-J path to 1e-12 (block sums added in row order)
+    monkeypatch.setenv("PNOL_FUSED_MB", str(mb))
+    pr = problems.lorentz_problem(m, K)
+    n = pr["n"]
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    of = O.OFunctor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    dx = np.full(n, 1e-7)
+    lam = 0.01
+    JTJ, A, rhs, F = ctx.lm_normal_eq_fused(f, pr["x0"], dx, n, lam)
+    J, F2 = ctx.fd_jacobian(f, pr["x0"], dx)
+    assert np.array_equal(F, F2) and np.array_equal(F, O.residual(of, pr["x0"]))
+    JTJ2, A2, rhs2 = ctx.lm_normal_eq(J, F2, m, n, lam)
+    assert rel(JTJ, JTJ2) < 1e-12 and np.array_equal(JTJ, JTJ.T)
+    assert rel(A, A2) < 1e-12 and np.array_equal(np.diag(A), (1 + lam) * np.diag(JTJ))
+    scale = np.linalg.norm(J, axis=0) * np.linalg.norm(F2)          # rhs_j = -J_j . F: bar relative to |J_j| |F|
+    assert np.max(np.abs(rhs - rhs2) / scale) < 1e-12
+    JTJw, Aw, rhsw = O.lm_normal_eq(J, F2, lam)
+    assert rel(JTJ, JTJw) < 1e-12 and np.max(np.abs(rhs - rhsw) / scale) < 1e-12
+    # device-resident outputs, residuals not wanted
+    JTJd, Ad, rhsd = ctx.malloc(n * n * 8), ctx.malloc(n * n * 8), ctx.malloc(n * 8)
+    ctx.lm_normal_eq_fused(f, pr["x0"], dx, n, lam, JTJ=JTJd, A=Ad, rhs=rhsd, want_F=False)
+    assert np.array_equal(ctx.to_host(JTJd, n * n).reshape(n, n), JTJ) and np.array_equal(ctx.to_host(rhsd, n), rhs)
+    for p in (JTJd, Ad, rhsd):
+        ctx.free(p)
+
+
 @pytest.mark.parametrize("m,n", [(1, 32), (31, 16), (33, 128), (64, 256), (4737, 256), (100_000, 48), (7000, 272), (5000, 512),
                                  (300_000, 256), (2000, 144), (513, 192), (40, 240), (700, 4096), (300, 8192)])
 def test_lm_normal_eq_stream_k_shapes(ctx, m, n):
