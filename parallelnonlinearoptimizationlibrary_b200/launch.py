@@ -26,8 +26,15 @@ def row_shard(m, world, rank):
 
 
 def column_shard(n, world, rank):
-    """FD-gradient coordinates [lo, hi) of `rank` (contiguous blocks, all-gathered in rank order)."""
-    return row_shard(n, world, rank)
+    """FD-gradient coordinates [lo, hi) of `rank`, as pnol_fd_gradient deals them out (csrc/capi.cu, fd_gradient_common): equal
+    blocks of ceil(n / world) coordinates, the last ones cut at n (possibly empty), so that one all-gather of fixed-size blocks in
+    rank order rebuilds the gradient. The reference deals the coordinates round-robin and sums (Source/PNOL_Objective.cpp:110-148)."""
+    n, world, rank = int(n), int(world), int(rank)
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank %d of %d" % (rank, world))
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
 
 
 def init_process_group(backend=None):

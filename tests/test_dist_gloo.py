@@ -1,7 +1,8 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU layout (parallelnonlinearoptimizationlibrary_b200/launch.py)
 -- row / individual shards, the rendezvous that distributes the NCCL unique id, max-over-ranks timing -- and the algebra
 the sharding relies on: the sum over ranks of the per-shard J^T J | J^T r | chi^2 equals the unsharded normal equations, so a
-row-sharded LM run reproduces the single-rank iterates (checked with the CPU oracle standing in for the kernels)."""
+row-sharded LM run reproduces the single-rank iterates (checked with the CPU oracle standing in for the kernels); the coordinate-block split of the FD gradient and the individual-sharded GA
+fitness sweep, each with its all-gather, are bit-identical to the unsharded results."""
 import os
 import socket
 import sys
@@ -63,8 +64,51 @@ def _worker(rank, world, port, out_dir):
             lam /= 10
             X, F, chi = Xn, Fn, chin
     np.save(os.path.join(out_dir, "X%d.npy" % rank), X)
+    # 4. FD gradient split by coordinate blocks: every rank evaluates its block of stencil points, one all-gather of
+    #    fixed-size blocks in rank order rebuilds the gradient -- bit-identical to the unsharded stencil
+    import torch
+    fr = O.OFunctor(1)                  # Rosenbrock
+    ng = 11                             # not divisible by the world size
+    xg, dxg = np.linspace(-1.5, 2.0, ng), np.full(ng, 1e-6)
+    g_all, f0 = O.fd_gradient(fr, xg, dxg)
+    clo, chi_ = launch.column_shard(ng, world, rank)
+    per = (ng + world - 1) // world
+    mine = torch.zeros(per, dtype=torch.float64)
+    for i in range(clo, chi_):          # this rank's stencil points only
+        xp = xg.copy()
+        xp[i] = xp[i] + dxg[i]
+        mine[i - clo] = (O.obj_eval(fr, xp) - f0) / dxg[i]
+    blocks = [torch.zeros(per, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(blocks, mine)
+    g = torch.cat(blocks).numpy()[:ng]
+    assert np.array_equal(g, g_all)
+    # 5. GA fitness sweep sharded by individuals, all-gather of F (every other GA stage is replicated): bit-identical F on every rank
+    fa = O.OFunctor(5)                  # Rastrigin
+    npop, ngene = 101, 8
+    pop = np.random.default_rng(11).uniform(-5.12, 5.12, size=(npop, ngene))
+    plo, phi = launch.row_shard(npop, world, rank)
+    perp = (npop + world - 1) // world
+    minef = torch.zeros(perp, dtype=torch.float64)
+    minef[:phi - plo] = torch.from_numpy(O.eval_batch(fa, pop[plo:phi]))
+    fblocks = [torch.zeros(perp, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(fblocks, minef)
+    F_all = np.concatenate([fblocks[r].numpy()[:launch.row_shard(npop, world, r)[1] - launch.row_shard(npop, world, r)[0]] for r in range(world)])
+    assert np.array_equal(F_all, O.eval_batch(fa, pop))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_column_shards_are_equal_blocks_in_rank_order():
+    from parallelnonlinearoptimizationlibrary_b200 import launch
+    for n in (1, 2, 10, 11, 256, 4096, 4097):
+        for world in (1, 2, 3, 4, 8):
+            per = (n + world - 1) // world
+            edges = [launch.column_shard(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            assert all(b - a == per for a, b in edges if b < n)          # full blocks everywhere before the cut
+    with pytest.raises(ValueError):
+        launch.column_shard(10, 2, 2)
 
 
 def test_row_shards_cover_everything():
