@@ -41,3 +41,17 @@ for _ in range(5):
     ctx.lm_normal_eq(Jd, Fd, m, n, 1e-3, JTJ=JTJ, A=A, rhs=rhs)
 ctx.sync()
 print("stored m=%d n=%d  J = %.2f GB: %.3f ms per call" % (m, n, m * n * 8 / 1e9, (time.perf_counter() - t0) / 5 * 1e3))
+# one whole LM iteration (pnol_lm_step: normal equations, damped solve, trial residuals, one host synchronisation) with and without a J buffer
+Ft, JTJp = ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
+ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+os.environ["PNOL_FUSED_MB"] = os.environ.get("STEP_MB", "512")
+for label, Jarg in (("stored J", Jd), ("no J, %s MB blocks" % os.environ["PNOL_FUSED_MB"], None)):
+    for _ in range(2):
+        ctx.lm_step(f, pr["x0"], dx, n, Jarg, Fd, Ft, 1e-3, JTJp)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.lm_step(f, pr["x0"], dx, n, Jarg, Fd, Ft, 1e-3, JTJp)
+    ctx.sync()
+    dt = (time.perf_counter() - t0) / 10
+    print("lm_step m=%d n=%d  %-24s %.3f ms per iteration = %.1f LM iterations/s" % (m, n, label + ":", dt * 1e3, 1.0 / dt))
