@@ -88,3 +88,24 @@ def test_syrk_stream_k_plan_invariants():
             for with_f in (0, 1):
                 assert lib.pnol_selftest_syrk_plan(m, n, sms, with_f) == 0, (m, n, sms, with_f)
     assert lib.pnol_selftest_syrk_plan(0, 16, 148, 0) == -1
+
+
+def test_reference_examples_compile_against_the_plugin_headers_and_fail_loudly_without_a_gpu():
+    # oracle/_ref/pnol_examples_dropin = the reference's own Source/Examples.cpp, unmodified, compiled against include/pnol and linked
+    # to the two product libraries (oracle/dropin_examples.cpp; `make -C oracle dropin` where /root/reference exists). That it exists
+    # says the plugin API is source-compatible with every class and helper the reference's drivers use; without a device a driver
+    # that needs the hot path must stop with the library's error, not fall back to the CPU.
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "oracle", "_ref", "pnol_examples_dropin")
+    if os.path.isdir("/root/reference/Source"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"])
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/pnol_examples_dropin not built (needs /root/reference)")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the drivers run (tests/test_gpu_dropin_examples.py)")
+    for driver in ("testBFGS", "testLMExpMPI", "testGA", "testBFGSBnd_MPI", "testSimplexSearch", "testGradientEvaluation"):
+        r = subprocess.run([exe, driver], capture_output=True, text=True, timeout=60, cwd=ROOT)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr, (driver, r.returncode, r.stderr[-300:])
+    r = subprocess.run([exe, "noSuchDriver"], capture_output=True, text=True, timeout=60, cwd=ROOT)
+    assert r.returncode == 2
