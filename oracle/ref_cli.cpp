@@ -462,6 +462,31 @@ static int cmdBox()
 	return 0;
 }
 
+// The alpha-pool evaluation of the pooled line searches through the reference's own class:
+// BFGS_Bnd_MPI_SW::evaluateAlphaPoolAndDerivatives (Source/BFGS_bnd_linesearch_MPI_SW.cpp:599-699; phi and its forward-difference
+// slope per entry, dealt over the ranks, 1e10 sentinel for NaN / inf) with an optional active set (constx / ind of the full length)
+static int cmdAlphaPool()
+{
+	Objective * obj = makeScalar( arg("obj") );
+	vector<double> X = readf64( arg("x") ), p = readf64( arg("p") ), alphaPool = readf64( arg("alpha") );
+	int n = (int) X.size();
+	vector<double> constantX( n, 0 );
+	vector<bool> constantIndicator( n, false );
+	if( !arg("constx").empty() )
+	{
+		constantX = readf64( arg("constx") );
+		vector<double> ind = readf64( arg("ind") );
+		constantIndicator.assign( constantX.size(), false );
+		for( size_t i = 0; i < ind.size(); i++ ) constantIndicator[i] = ind[i] != 0;
+	}
+	vector<double> phiPool( alphaPool.size(), 0 ), dphiPool( alphaPool.size(), 0 );
+	BFGS_Bnd_MPI_SW b; b.setObjPtr( *obj );
+	b.setParams( 1e-4, 0.9, argd("dalpha", 1e-6), 1, 1e-20, 2, 50, 1e-5, 1e-6, 1e-3, 100, 1e-5, 1e-5, 0, 0 );
+	b.evaluateAlphaPoolAndDerivatives( alphaPool, X, p, constantX, constantIndicator, phiPool, dphiPool );
+	writef64( "phi", phiPool ); writef64( "dphi", dphiPool );
+	return 0;
+}
+
 // CPU baseline: one LM iteration's hot path (Jacobian + normal equations + solve + trial residual) on the
 // Lorentz-sum model through the reference's own code, timed with MPI_Wtime on rank 0.
 static int cmdBenchLM()
@@ -545,6 +570,7 @@ int main( int argc, char ** argv )
 	else if( cmd == "simplex" ) rc = cmdSimplex();
 	else if( cmd == "popsort" || cmd == "checkbounds" || cmd == "checkidentical" ) rc = cmdGAStage(cmd);
 	else if( cmd == "box" ) rc = cmdBox();
+	else if( cmd == "alphapool" ) rc = cmdAlphaPool();
 	else if( cmd == "example" ) rc = cmdExample();
 	else if( cmd == "bench_lm" ){ cout.rdbuf(0); rc = cmdBenchLM(); }
 	else if( cmd == "bench_ga_eval" ){ cout.rdbuf(0); rc = cmdBenchGAEval(); }

@@ -137,3 +137,24 @@ def test_bfgsbnd_mpi_golden_is_what_the_verbatim_reference_produces():
         r = M.run_reference(obj, x0, lb, ub, P, iters, extra)
         for k in ("X", "f0", "fOpt"):
             assert np.array_equal(r[k], G2[name + "/" + k]), (name, k)
+
+
+def test_alpha_pool_oracle_against_the_committed_reference_outputs():
+    # tests/golden/alphapool_golden.npz = BFGS_Bnd_MPI_SW::evaluateAlphaPoolAndDerivatives of the verbatim reference (4 ranks): the
+    # oracle's phi / slope / sentinel bit for bit, with and without an active set; fresh-run comparison where oracle/_ref exists
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_alphapool_golden as M
+    G2 = np.load(os.path.join(here, "golden", "alphapool_golden.npz"))
+    for name, c in M.cases().items():
+        assert np.array_equal(G2[name + "/x"], c["x"]) and np.array_equal(G2[name + "/p"], c["p"])
+        f = O.OFunctor(c["kind"], (), c["ints"])
+        phi, dphi, bad = O.alpha_pool(f, c["x"], c["p"], c["alpha"], c["dalpha"], const_x=c["constx"], const_ind=c["ind"])
+        assert np.array_equal(phi, G2[name + "/phi"]), name
+        assert np.array_equal(dphi, G2[name + "/dphi"], equal_nan=True), name
+        assert bad == int(np.sum(G2[name + "/phi"] == 1e10))
+        if O.have_ref():
+            r = M.run_reference(c, nprocs=2)
+            assert np.array_equal(r["phi"], G2[name + "/phi"]) and np.array_equal(r["dphi"], G2[name + "/dphi"], equal_nan=True)
+    assert np.all(G2["rosenbrock6_overflow/phi"] == 1e10)

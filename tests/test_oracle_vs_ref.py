@@ -128,6 +128,32 @@ def test_update_hinv(n):
     assert np.array_equal(r["D"].reshape(n, n), O.update_hinv(D, g, s))
 
 
+@pytest.mark.parametrize("P", [1, 3])
+def test_alpha_pool_against_the_reference_class(P):
+    # BFGS_Bnd_MPI_SW::evaluateAlphaPoolAndDerivatives (Source/BFGS_bnd_linesearch_MPI_SW.cpp:599-699) through the verbatim build:
+    # phi and the forward-difference slope of every pool entry, without and with an active set, and the 1e10 sentinel
+    rng = np.random.default_rng(3)
+    n = 9
+    x, p = rng.uniform(-1.5, 1.5, n), rng.normal(size=n)
+    alpha = np.array([0.0, 1e-3, 0.1, 0.37, 1.0, 2.5])
+    r = O.ref_cli("alphapool", arrays=dict(x=x, p=p, alpha=alpha), obj="rosenbrock", dalpha=1e-6, nprocs=P)
+    phi, dphi, bad = O.alpha_pool(O.OFunctor(ROSEN), x, p, alpha, 1e-6)
+    assert bad == 0 and np.array_equal(r["phi"], phi) and np.array_equal(r["dphi"], dphi)
+    nf = 12
+    ind = np.zeros(nf)
+    ind[[2, 5, 9]] = 1
+    constx = rng.uniform(-1, 1, nf)
+    xr = rng.uniform(-1, 1, n)
+    r = O.ref_cli("alphapool", arrays=dict(x=xr, p=p, alpha=alpha, constx=constx, ind=ind), obj="rastrigin", dalpha=1e-6, nprocs=P)
+    phi, dphi, bad = O.alpha_pool(O.OFunctor(RAST), xr, p, alpha, 1e-6, const_x=constx, const_ind=ind)
+    assert bad == 0 and np.array_equal(r["phi"], phi) and np.array_equal(r["dphi"], dphi)
+    xb = x.copy()
+    xb[0] = 1e200                                      # f overflows: every entry comes back as the sentinel
+    r = O.ref_cli("alphapool", arrays=dict(x=xb, p=p, alpha=alpha), obj="rosenbrock", dalpha=1e-6, nprocs=P)
+    phi, dphi, bad = O.alpha_pool(O.OFunctor(ROSEN), xb, p, alpha, 1e-6)
+    assert bad == alpha.size and np.all(phi == 1e10) and np.array_equal(r["phi"], phi)
+
+
 def test_box_helpers():
     rng = np.random.default_rng(0)
     n = 50
