@@ -1,5 +1,6 @@
 """ctypes binding of lib/libpnol_b200_host.so: the host C++ mirror of the reference's plugin API (include/pnol/*.hpp --
-LevMarqMPI, BFGS, BFGS_MPI, BFGS_Bnd_MPI_SW, GeneticAlgorithm[MPI], Objective / MultiObjective stencils) driven through
+LevMarq[MPI], BFGS, BFGS_MPI, BFGS_Bnd, BFGS_Bnd_MPI_SW, BFGSBnd_MPI, GeneticAlgorithm[MPI], SimplexSearch, Objective /
+MultiObjective stencils) driven through
 the small C face of host/host_capi.cpp. Tests and bench.py use it to call exactly what a C++ user of the reference API
 calls (`alg.setObjPtr(obj); alg.setParams(...); alg.findMin(...)`). No CPU fallback: every call ends in CUDA kernels."""
 import ctypes as C
