@@ -1,0 +1,156 @@
+// host_logic_device.cpp -- TEST INFRASTRUCTURE, never shipped, never loaded by the product (the product's libraries are
+// lib/libpnol_b200.so + lib/libpnol_b200_host.so and have no CPU path).
+//
+// The part of the C-ABI (include/pnol_b200.h) that the BFGS family, SimplexSearch and the scalar-objective stencils of the host
+// C++ mirror call, answered by the CPU oracle (pnol_oracle.cpp) instead of CUDA kernels. tests/test_host_logic_cpu.py links the
+// UNMODIFIED host sources (parallelnonlinearoptimizationlibrary_b200/host/*.cpp) against this file into a test-only library and runs
+// the reference's control flow on a box without a GPU: with the oracle's arithmetic (= the oracle shim's: sequential sums, the
+// literal two-product updateHessianInv) under them, the host controllers reproduce the verbatim reference's iterates BIT FOR BIT,
+// which isolates every difference seen on the GPU to the summation order of the device's dense algebra. Entry points of the LM /
+// GA paths are not provided here (they return an error): those loops are restated in the oracle itself.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../include/pnol_b200.h"
+
+extern "C" {
+// pnol_oracle.cpp
+double oracle_obj_eval(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m, const double * X, int n);
+void oracle_eval_batch(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                       const double * pts, long long B, int n, long long ld, const unsigned char * indicator, double * f_out);
+void oracle_fd_gradient(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                        const double * X, const double * dX, int N, double * dFdX, double * f0);
+double oracle_eval_recur(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                         const double * X, int N, const double * constantX, const unsigned char * ind, int Nparam);
+void oracle_fd_gradient_recur(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                              const double * X, const double * dX, int N, const double * constantX, const unsigned char * ind,
+                              int Nparam, double * dFdX, double * f0);
+void oracle_fd_hessian(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                       const double * X, const double * dX, int N, double * B);
+void oracle_alpha_pool(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                       const double * X, const double * p, int n, const double * alpha, int npool, double dalpha,
+                       const unsigned char * eval_ind, const double * constantX, const unsigned char * const_ind, int nfull,
+                       double * phi, double * dphi, int * bad);
+void oracle_update_hinv(double * D, const double * g, const double * s, int n);
+void oracle_matvec_neg(const double * D, const double * g, int n, double * p);
+void oracle_lu_solve(const double * A, const double * b, int n, double * x);
+int oracle_check_box_bounds(double * X, const double * Xlb, const double * Xub, int n);
+double oracle_compute_alpha_bnd(const double * X, const double * Xlb, const double * Xub, const double * p, int Nprm);
+double oracle_stream_uniform(uint64_t seed, uint64_t k, double scale);
+}
+
+struct pnol_ctx { std::string err; };
+struct pnol_functor { pnol_functor_desc d; };
+struct pnol_ga { int unused; };
+
+#define FARGS(f) (f)->d.kind, (f)->d.scalars, (f)->d.ints, (f)->d.columns, (f)->d.m
+
+static int unavailable(pnol_ctx * ctx, const char * what)
+{
+	if (ctx) ctx->err = std::string(what) + ": not provided by the CPU stand-in of the host-logic tests (oracle/host_logic_device.cpp)";
+	return PNOL_ERR_NO_FUNCTOR;
+}
+
+extern "C" {
+
+int pnol_ctx_create(pnol_ctx ** ctx, int) { *ctx = new pnol_ctx; return PNOL_OK; }
+void pnol_ctx_destroy(pnol_ctx * ctx) { delete ctx; }
+const char * pnol_last_error(pnol_ctx * ctx) { return ctx ? ctx->err.c_str() : ""; }
+int pnol_comm_rank(pnol_ctx *) { return 0; }
+
+// "device" memory is host memory here
+int pnol_malloc(pnol_ctx *, void ** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? PNOL_OK : PNOL_ERR_CUDA; }
+int pnol_free(pnol_ctx *, void * p) { std::free(p); return PNOL_OK; }
+int pnol_memcpy(pnol_ctx *, void * dst, const void * src, size_t bytes) { std::memmove(dst, src, bytes); return PNOL_OK; }
+int pnol_memset(pnol_ctx *, void * p, int value, size_t bytes) { std::memset(p, value, bytes); return PNOL_OK; }
+
+int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * desc, pnol_functor ** out)
+{
+	if (!desc || desc->kind < 1 || desc->kind >= 100) return unavailable(ctx, "pnol_functor_create (residual models)");
+	*out = new pnol_functor{*desc};
+	return PNOL_OK;
+}
+void pnol_functor_destroy(pnol_functor * f) { delete f; }
+long long pnol_functor_rows(const pnol_functor * f) { return f->d.kind >= 100 ? f->d.m : 0; }
+
+int pnol_eval_batch(pnol_ctx *, const pnol_functor * f, const double * pts, long long B, int n, long long ld, const unsigned char * indicator,
+                    double * f_out)
+{
+	oracle_eval_batch(FARGS(f), pts, B, n, ld, indicator, f_out);
+	return PNOL_OK;
+}
+int pnol_fd_gradient(pnol_ctx *, const pnol_functor * f, const double * x, const double * dx, int n, double * g_out, double * f0_out)
+{
+	oracle_fd_gradient(FARGS(f), x, dx, n, g_out, f0_out);
+	return PNOL_OK;
+}
+int pnol_eval_recur(pnol_ctx *, const pnol_functor * f, const double * xr, int nr, const double * const_x, const unsigned char * const_ind,
+                    int nfull, double * f_out)
+{
+	*f_out = oracle_eval_recur(FARGS(f), xr, nr, const_x, const_ind, nfull);
+	return PNOL_OK;
+}
+int pnol_fd_gradient_recur(pnol_ctx *, const pnol_functor * f, const double * xr, const double * dxr, int nr, const double * const_x,
+                           const unsigned char * const_ind, int nfull, double * g_out, double * f0_out)
+{
+	oracle_fd_gradient_recur(FARGS(f), xr, dxr, nr, const_x, const_ind, nfull, g_out, f0_out);
+	return PNOL_OK;
+}
+int pnol_fd_hessian(pnol_ctx *, const pnol_functor * f, const double * x, const double * dx, int n, double * B_out)
+{
+	oracle_fd_hessian(FARGS(f), x, dx, n, B_out);
+	return PNOL_OK;
+}
+int pnol_alpha_pool(pnol_ctx *, const pnol_functor * f, const double * x, const double * p, int n, const double * alpha, int npool,
+                    double dalpha, const unsigned char * eval_ind, const double * const_x, const unsigned char * const_ind, int nfull,
+                    double * phi, double * dphi, int * bad_out)
+{
+	int bad = 0;
+	oracle_alpha_pool(FARGS(f), x, p, n, alpha, npool, dalpha, eval_ind, const_x, const_ind, const_ind ? nfull : n, phi, dphi, &bad);
+	if (bad_out) *bad_out = bad;
+	return PNOL_OK;
+}
+int pnol_matvec_neg(pnol_ctx *, const double * D, const double * g, int n, double * p) { oracle_matvec_neg(D, g, n, p); return PNOL_OK; }
+// both update modes map to the reference's literal two-product form: that is what the verbatim reference computes
+int pnol_bfgs_update_hinv(pnol_ctx *, double * D, const double * g, const double * s, int n, int) { oracle_update_hinv(D, g, s, n); return PNOL_OK; }
+// the reference inverts the FD Hessian with matrixInverse (LU, partial pivoting); column-wise LU solves give the same numbers
+int pnol_spd_solve(pnol_ctx *, const double * A, const double * rhs, int n, double * x, int * info)
+{
+	oracle_lu_solve(A, rhs, n, x);
+	if (info) *info = 0;
+	return PNOL_OK;
+}
+int pnol_check_box_bounds(double * x, const double * xlb, const double * xub, int n, int * n_replaced)
+{
+	int c = oracle_check_box_bounds(x, xlb, xub, n);
+	if (n_replaced) *n_replaced = c;
+	return PNOL_OK;
+}
+double pnol_compute_alpha_bnd(const double * x, const double * xlb, const double * xub, const double * p, int n)
+{
+	return oracle_compute_alpha_bnd(x, xlb, xub, p, n);
+}
+double pnol_stream_uniform(uint64_t seed, uint64_t k, double scale) { return oracle_stream_uniform(seed, k, scale); }
+
+// ---- not part of the host-logic tests (LM and GA loops are restated in the oracle itself) ----
+int pnol_residual_eval(pnol_ctx * ctx, const pnol_functor *, const double *, int, double *, double *) { return unavailable(ctx, "pnol_residual_eval"); }
+int pnol_fd_jacobian(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double *, double *, int) { return unavailable(ctx, "pnol_fd_jacobian"); }
+int pnol_lm_step(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double *, const double *, double *, double, int, int,
+                 double *, double *, double *, double *, int *) { return unavailable(ctx, "pnol_lm_step"); }
+int pnol_ga_create(pnol_ctx * ctx, const pnol_functor *, const pnol_ga_params *, int, const double *, const double *, const pnol_stream_desc *,
+                   pnol_ga **) { return unavailable(ctx, "pnol_ga_create"); }
+void pnol_ga_destroy(pnol_ga *) {}
+int pnol_ga_init(pnol_ga *, const double *, double *) { return PNOL_ERR_NO_FUNCTOR; }
+int pnol_ga_generation(pnol_ga *) { return PNOL_ERR_NO_FUNCTOR; }
+int pnol_ga_status_get(pnol_ga *, pnol_ga_status *) { return PNOL_ERR_NO_FUNCTOR; }
+int pnol_ga_get_population(pnol_ga *, double *, double *) { return PNOL_ERR_NO_FUNCTOR; }
+int pnol_ga_pop_sort(pnol_ctx * ctx, double *, double *, long long, int) { return unavailable(ctx, "pnol_ga_pop_sort"); }
+int pnol_ga_check_bounds(pnol_ctx * ctx, double *, long long, int, const double *, const double *, unsigned char *, const pnol_stream_desc *,
+                         uint64_t *) { return unavailable(ctx, "pnol_ga_check_bounds"); }
+int pnol_ga_check_identical(pnol_ctx * ctx, double *, long long, int, const double *, const double *, unsigned char *, const pnol_stream_desc *,
+                            uint64_t *) { return unavailable(ctx, "pnol_ga_check_identical"); }
+
+} // extern "C"

@@ -1,0 +1,141 @@
+"""CPU: the host controllers of the plugin API (parallelnonlinearoptimizationlibrary_b200/host/*.cpp: BFGS, BFGS_MPI, BFGS_Bnd,
+BFGS_Bnd_MPI_SW, BFGSBnd_MPI, SimplexSearch, the Objective stencil members, the box helpers) WITHOUT a GPU: the unmodified host sources
+are linked into a test-only library against oracle/host_logic_device.cpp, which answers the C-ABI calls of these paths with the CPU
+oracle instead of CUDA kernels (test infrastructure; the product libraries have no CPU path and this library is never shipped).
+
+With the oracle's arithmetic underneath -- the same sequential sums and literal two-product updateHessianInv the verbatim reference
+was compiled with -- every controller reproduces the committed outputs of the verbatim reference BIT FOR BIT: iterates, f0, fOpt,
+iteration counts, random draws. So the control flow (line searches, pools, active-set recursion, steepest-descent retries, Nelder-Mead
+steps) is the reference's, decision for decision, and what the GPU tests see beyond that (1e-9 ... 1e-5, tests/test_gpu_host_api.py)
+is the summation order of the device's dense algebra and nothing else."""
+import ctypes as C
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+G = np.load(os.path.join(HERE, "golden", "ref_golden.npz"))
+
+
+def g(case, name):
+    return G["%s/%s" % (case, name)]
+
+
+@pytest.fixture(scope="module")
+def hl(tmp_path_factory):
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++ on this box")
+    so = str(tmp_path_factory.mktemp("host_logic") / "libpnol_host_logic_test.so")
+    host = os.path.join(ROOT, "parallelnonlinearoptimizationlibrary_b200", "host")
+    # -Bsymbolic: the library's own pnol_* definitions win over a product library another test may have loaded RTLD_GLOBAL
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-w", "-shared", "-Wl,-Bsymbolic", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + host] + sorted(glob.glob(os.path.join(host, "*.cpp"))) +
+                          [os.path.join(ROOT, "oracle", "host_logic_device.cpp"), os.path.join(ROOT, "oracle", "pnol_oracle.cpp"), "-o", so])
+    lib = C.CDLL(so, mode=C.RTLD_LOCAL)
+    lib.pnolhost_last_error.restype = C.c_char_p
+    lib.pnolhost_set_hinv_mode(0)          # PNOL_HINV_LITERAL: the reference's two matrix products
+    return lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def bfgs(lib, variant, obj, x0, params, lb=None, ub=None, pool=0):
+    X = np.array(x0, dtype=np.float64).copy()
+    p = np.array(params, dtype=np.float64)
+    lb = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
+    ub = None if ub is None else np.ascontiguousarray(ub, dtype=np.float64)
+    f0, fo, it = C.c_double(), C.c_double(), C.c_int()
+    st = lib.pnolhost_bfgs(variant.encode(), obj.encode(), _p(X), X.size, _p(p), _p(lb), _p(ub), int(pool), 0, C.byref(f0), C.byref(fo), C.byref(it))
+    assert st == 0, (st, lib.pnolhost_last_error())
+    return dict(X=X, f0=f0.value, fOpt=fo.value, iterations=it.value)
+
+
+def same(r, case):
+    return np.array_equal(r["X"], g(case, "X")) and r["f0"] == g(case, "f0")[0] and r["fOpt"] == g(case, "fOpt")[0]
+
+
+BF = [1e-4, 0.9, 1e-6, 1.0, 1000, 1e-7, 1e-3, 0, 1e-5, 1e-5, 0]        # testBFGS params (Source/Examples.cpp:247); [7] = maxIter
+SW = [1e-4, 0.8, 1e-6, 1.0, 1e-10, 2.0, 50, 1e-5, 1e-6, 1e-3, 0, 1e-5, 1e-5, 0]     # testBFGSBndMPISW params (:37); [10] = maxIter
+
+
+@pytest.mark.parametrize("case,n,x0,iters", [("bfgs_cfg1_it5", 10, 3.0, 5), ("bfgs_cfg1_it100", 10, 3.0, 100), ("testBFGS", 5, 3.0, 100)])
+def test_bfgs_bit_for_bit(hl, case, n, x0, iters):
+    p = list(BF)
+    p[7] = iters
+    assert same(bfgs(hl, "bfgs", "rosenbrock", np.full(n, x0), p), case)
+
+
+@pytest.mark.parametrize("iters", [5, 60])
+def test_bfgs_mpi_pool_bit_for_bit(hl, iters):
+    p = [1e-4, 0.9, 4.0, 1.0, 50, 1e-7, 1e-3, iters, 1e-5, 1e-5, 0]
+    assert same(bfgs(hl, "bfgs_mpi", "rosenbrock", np.full(10, 10.0), p, pool=4), "bfgs_mpi_P4_it%d" % iters)
+
+
+@pytest.mark.parametrize("case,P,iters", [("testBFGSBndMPISW_P2", 2, 200), ("testBFGSBndMPISW_P8", 8, 200), ("bfgs_bnd_sw_n64_P8_it3", 8, 3),
+                                          ("bfgs_bnd_sw_n64_P8_it20", 8, 20)])
+def test_bfgs_bnd_mpi_sw_bit_for_bit(hl, case, P, iters):
+    p = list(SW)
+    p[10] = iters
+    x0 = g(case, "x0")
+    lb, ub = (g(case, "lb"), g(case, "ub")) if case.startswith("test") else (np.full(x0.size, -5.0), np.full(x0.size, 5.0))
+    assert same(bfgs(hl, "bfgs_bnd_sw", "rosenbrock", x0, p, lb, ub, pool=P), case)
+
+
+@pytest.mark.parametrize("case,n,iters", [("testBFGSBnd_it4", 5, 4), ("testBFGSBnd_it200", 5, 200), ("bfgs_bnd_n12_it6", 12, 6)])
+def test_bfgs_bnd_serial_bit_for_bit(hl, case, n, iters):
+    p = list(SW)
+    p[10] = iters
+    x0 = g(case, "x0") if case.startswith("bfgs_bnd") else np.full(n, 2.0)
+    assert same(bfgs(hl, "bfgs_bnd", "rosenbrock", x0, p, np.full(n, -5.0), np.full(n, 5.0)), case)
+
+
+def test_bfgsbnd_mpi_bit_for_bit(hl):
+    from make_bfgsbnd_mpi_golden import PARAMS, cases
+    G2 = np.load(os.path.join(HERE, "golden", "bfgsbnd_mpi_golden.npz"))
+    k = PARAMS
+    for name, (obj, x0, lb, ub, P, iters, extra, _) in cases().items():
+        p = [k["c1"], k["c2"], k["alphamin"], k["maxalphamult"], k["alphaguess"], k["maxiterls"], k["dxgrad"], k["dxhess"], iters, k["xmindiff"],
+             k["mingrad"], k["fsteptol"], extra.get("inithess", 0)]
+        r = bfgs(hl, "bfgsbnd_mpi", obj, x0, p, lb, ub, pool=P)
+        assert np.array_equal(r["X"], G2[name + "/X"]) and r["f0"] == G2[name + "/f0"][0] and r["fOpt"] == G2[name + "/fOpt"][0], name
+        assert r["iterations"] == int(G2[name + "/iterations_done"]), name       # outer + recursive iterations
+
+
+def test_simplex_search_bit_for_bit(hl):
+    from make_simplex_golden import CASES
+    S = np.load(os.path.join(HERE, "golden", "simplex_golden.npz"))
+    for name, (obj, x0, kw, stream) in CASES.items():
+        if stream[0] == "values":
+            vals = np.ascontiguousarray(stream[1], dtype=np.float64)
+            hl.pnolhost_set_stream(_p(vals), C.c_ulonglong(vals.size), C.c_ulonglong(0), C.c_double(1.0))
+        else:
+            hl.pnolhost_set_stream(C.c_void_p(0), C.c_ulonglong(0), C.c_ulonglong(stream[1]), C.c_double(stream[2]))
+        X = np.array(x0, dtype=np.float64).copy()
+        p = np.array([kw.get("alpha", 1.0), kw.get("gamma", 2.0), kw.get("rho", 0.5), kw.get("sigma", 0.5), kw.get("maxiter", 10000),
+                      kw.get("initrandmax", 1.0), kw.get("xmindiff", 1e-7)], dtype=np.float64)
+        f0, fo = C.c_double(), C.c_double()
+        rep = np.zeros(2)
+        st = hl.pnolhost_simplex(obj.encode(), _p(X), X.size, _p(p), 0, C.byref(f0), C.byref(fo), _p(rep))
+        assert st == 0, hl.pnolhost_last_error()
+        assert np.array_equal(X, S[name + "/X"]) and f0.value == S[name + "/f0"][0] and fo.value == S[name + "/fOpt"][0], name
+        assert int(rep[1]) == int(S[name + "/stream_pos"][0])
+
+
+def test_paths_outside_the_stand_in_fail_loudly(hl):
+    # LM / GA entry points are not answered by the stand-in: the host classes surface the status as an error, nothing is faked
+    X = np.array([9.0, 0.5, 0.3])
+    rep = np.zeros(6)
+    st = hl.pnolhost_lm_example(b"expcurve", _p(X), 3, C.c_double(0.001), C.c_double(10.0), C.c_double(1e-6), C.c_double(5.0), C.c_double(1e-6),
+                                None, None, _p(rep))
+    assert st != 0 and b"stand-in" in hl.pnolhost_last_error()
