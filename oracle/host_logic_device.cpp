@@ -1,18 +1,20 @@
 // host_logic_device.cpp -- TEST INFRASTRUCTURE, never shipped, never loaded by the product (the product's libraries are
 // lib/libpnol_b200.so + lib/libpnol_b200_host.so and have no CPU path).
 //
-// The part of the C-ABI (include/pnol_b200.h) that the BFGS family, SimplexSearch and the scalar-objective stencils of the host
+// The part of the C-ABI (include/pnol_b200.h) that the BFGS family, SimplexSearch, LevMarq[MPI] and the stencil members of the host
 // C++ mirror call, answered by the CPU oracle (pnol_oracle.cpp) instead of CUDA kernels. tests/test_host_logic_cpu.py links the
 // UNMODIFIED host sources (parallelnonlinearoptimizationlibrary_b200/host/*.cpp) against this file into a test-only library and runs
 // the reference's control flow on a box without a GPU: with the oracle's arithmetic (= the oracle shim's: sequential sums, the
 // literal two-product updateHessianInv) under them, the host controllers reproduce the verbatim reference's iterates BIT FOR BIT,
-// which isolates every difference seen on the GPU to the summation order of the device's dense algebra. Entry points of the LM /
-// GA paths are not provided here (they return an error): those loops are restated in the oracle itself.
+// which isolates every difference seen on the GPU to the summation order of the device's dense algebra. The Levenberg-Marquardt
+// entry points (residuals, FD Jacobian, one iteration's device work) are answered the same way; the GA entry points are not provided
+// (they return an error): that loop is restated in the oracle itself.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../include/pnol_b200.h"
 
@@ -34,6 +36,11 @@ void oracle_alpha_pool(int kind, const double * scalars, const long long * ints,
                        const double * X, const double * p, int n, const double * alpha, int npool, double dalpha,
                        const unsigned char * eval_ind, const double * constantX, const unsigned char * const_ind, int nfull,
                        double * phi, double * dphi, int * bad);
+void oracle_residual(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                     const double * X, int n, double * F);
+void oracle_fd_jacobian(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+                        const double * X, const double * dX, int N, double * J, double * Fout);
+void oracle_lm_normal_eq(const double * J, const double * F, long long m, int n, double lambda, double * JTJ, double * A, double * rhs);
 void oracle_update_hinv(double * D, const double * g, const double * s, int n);
 void oracle_matvec_neg(const double * D, const double * g, int n, double * p);
 void oracle_lu_solve(const double * A, const double * b, int n, double * x);
@@ -43,7 +50,10 @@ double oracle_stream_uniform(uint64_t seed, uint64_t k, double scale);
 }
 
 struct pnol_ctx { std::string err; };
-struct pnol_functor { pnol_functor_desc d; };
+struct pnol_functor {
+	pnol_functor_desc d;
+	std::vector<std::vector<double> > owned;      // residual models: the data columns are copied (as the product copies them to the device)
+};
 struct pnol_ga { int unused; };
 
 #define FARGS(f) (f)->d.kind, (f)->d.scalars, (f)->d.ints, (f)->d.columns, (f)->d.m
@@ -69,8 +79,14 @@ int pnol_memset(pnol_ctx *, void * p, int value, size_t bytes) { std::memset(p, 
 
 int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * desc, pnol_functor ** out)
 {
-	if (!desc || desc->kind < 1 || desc->kind >= 100) return unavailable(ctx, "pnol_functor_create (residual models)");
-	*out = new pnol_functor{*desc};
+	if (!desc || desc->kind < 1) return unavailable(ctx, "pnol_functor_create");
+	pnol_functor * f = new pnol_functor;
+	f->d = *desc;
+	for (int c = 0; c < desc->n_columns && c < PNOL_MAX_COLUMNS; c++) {
+		f->owned.emplace_back(desc->columns[c], desc->columns[c] + desc->m);
+	}
+	for (size_t c = 0; c < f->owned.size(); c++) f->d.columns[c] = f->owned[c].data();
+	*out = f;
 	return PNOL_OK;
 }
 void pnol_functor_destroy(pnol_functor * f) { delete f; }
@@ -135,11 +151,55 @@ double pnol_compute_alpha_bnd(const double * x, const double * xlb, const double
 }
 double pnol_stream_uniform(uint64_t seed, uint64_t k, double scale) { return oracle_stream_uniform(seed, k, scale); }
 
-// ---- not part of the host-logic tests (LM and GA loops are restated in the oracle itself) ----
-int pnol_residual_eval(pnol_ctx * ctx, const pnol_functor *, const double *, int, double *, double *) { return unavailable(ctx, "pnol_residual_eval"); }
-int pnol_fd_jacobian(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double *, double *, int) { return unavailable(ctx, "pnol_fd_jacobian"); }
-int pnol_lm_step(pnol_ctx * ctx, const pnol_functor *, const double *, const double *, int, double *, const double *, double *, double, int, int,
-                 double *, double *, double *, double *, int *) { return unavailable(ctx, "pnol_lm_step"); }
+// ---- Levenberg-Marquardt (Source/LevenbergMarquardtMPI.cpp:42-108): residuals, FD Jacobian, one iteration's device work ----
+static double sumsq_sequential(const double * F, long long m)          // vector2Norm(F)^2 before the sqrt: one running sum
+{
+	double s = 0;
+	for (long long k = 0; k < m; k++) s = s + F[k] * F[k];
+	return s;
+}
+int pnol_residual_eval(pnol_ctx * ctx, const pnol_functor * f, const double * x, int n, double * F, double * sumsq_out)
+{
+	if (f->d.kind < 100) return unavailable(ctx, "pnol_residual_eval on a scalar functor");
+	oracle_residual(FARGS(f), x, n, F);
+	if (sumsq_out) *sumsq_out = sumsq_sequential(F, f->d.m);
+	return PNOL_OK;
+}
+int pnol_fd_jacobian(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J, double * F, int)
+{
+	if (f->d.kind < 100) return unavailable(ctx, "pnol_fd_jacobian on a scalar functor");
+	oracle_fd_jacobian(FARGS(f), x, dx, n, J, F);
+	return PNOL_OK;
+}
+int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J, const double * F,
+                 double * Ftrial, double lambda, int, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
+                 double * sumsq_trial_out, int * spd_info_out)
+{
+	if (f->d.kind < 100) return unavailable(ctx, "pnol_lm_step on a scalar functor");
+	const long long m = f->d.m;
+	const size_t nn = (size_t) n * n;
+	std::vector<double> A(nn), rhs(n), sigma(n), xt(n), Jown;
+	if (!reuse_jtj) {
+		if (!J) { Jown.resize((size_t) m * n); J = Jown.data(); }       // the caller keeps no J
+		oracle_fd_jacobian(FARGS(f), x, dx, n, J, nullptr);
+		oracle_lm_normal_eq(J, F, m, n, lambda, JTJ, A.data(), rhs.data());
+		std::memcpy(JTJ + nn, rhs.data(), (size_t) n * sizeof(double));  // J^T J followed by -J^T F, as the product keeps them
+	} else {
+		for (int i = 0; i < n; i++)
+			for (int j = 0; j < n; j++) A[(size_t) i * n + j] = (i == j) ? (1 + lambda) * JTJ[(size_t) i * n + j] : JTJ[(size_t) i * n + j];
+		std::memcpy(rhs.data(), JTJ + nn, (size_t) n * sizeof(double));
+	}
+	oracle_lu_solve(A.data(), rhs.data(), n, sigma.data());              // luSolve (:88)
+	for (int i = 0; i < n; i++) xt[i] = x[i] + sigma[i];                 // (:97-100)
+	oracle_residual(FARGS(f), xt.data(), n, Ftrial);
+	if (sumsq_trial_out) *sumsq_trial_out = sumsq_sequential(Ftrial, m);
+	if (sigma_out) std::memcpy(sigma_out, sigma.data(), (size_t) n * sizeof(double));
+	if (x_trial_out) std::memcpy(x_trial_out, xt.data(), (size_t) n * sizeof(double));
+	if (spd_info_out) *spd_info_out = 0;
+	return PNOL_OK;
+}
+
+// ---- not part of the host-logic tests (the GA loop is restated in the oracle itself) ----
 int pnol_ga_create(pnol_ctx * ctx, const pnol_functor *, const pnol_ga_params *, int, const double *, const double *, const pnol_stream_desc *,
                    pnol_ga **) { return unavailable(ctx, "pnol_ga_create"); }
 void pnol_ga_destroy(pnol_ga *) {}

@@ -1,12 +1,13 @@
 """CPU: the host controllers of the plugin API (parallelnonlinearoptimizationlibrary_b200/host/*.cpp: BFGS, BFGS_MPI, BFGS_Bnd,
-BFGS_Bnd_MPI_SW, BFGSBnd_MPI, SimplexSearch, the Objective stencil members, the box helpers) WITHOUT a GPU: the unmodified host sources
+BFGS_Bnd_MPI_SW, BFGSBnd_MPI, SimplexSearch, LevMarq, LevMarqMPI, the Objective stencil members, the box helpers) WITHOUT a GPU: the unmodified host sources
 are linked into a test-only library against oracle/host_logic_device.cpp, which answers the C-ABI calls of these paths with the CPU
 oracle instead of CUDA kernels (test infrastructure; the product libraries have no CPU path and this library is never shipped).
 
 With the oracle's arithmetic underneath -- the same sequential sums and literal two-product updateHessianInv the verbatim reference
 was compiled with -- every controller reproduces the committed outputs of the verbatim reference BIT FOR BIT: iterates, f0, fOpt,
 iteration counts, random draws. So the control flow (line searches, pools, active-set recursion, steepest-descent retries, Nelder-Mead
-steps) is the reference's, decision for decision, and what the GPU tests see beyond that (1e-9 ... 1e-5, tests/test_gpu_host_api.py)
+steps, and the accept / reject / damping rule of Levenberg-Marquardt with and without a stored Jacobian) is the reference's, decision
+for decision, and what the GPU tests see beyond that (1e-9 ... 1e-5, tests/test_gpu_host_api.py)
 is the summation order of the device's dense algebra and nothing else."""
 import ctypes as C
 import glob
@@ -132,10 +133,50 @@ def test_simplex_search_bit_for_bit(hl):
         assert int(rep[1]) == int(S[name + "/stream_pos"][0])
 
 
+@pytest.mark.parametrize("case", ["lm_lorentz_K8", "lm_lorentz_K16"])
+@pytest.mark.parametrize("serial", [0, 1])
+@pytest.mark.parametrize("store_j", [1, 0])
+def test_levenberg_marquardt_bit_for_bit(hl, case, serial, store_j):
+    # LevMarqMPI / LevMarq::findMin (accept / reject, damping, stop rule on the host; residuals, FD Jacobian, normal equations and solve
+    # behind pnol_residual_eval / pnol_lm_step), with a J buffer and without one (Runtime::setStoreJacobian(false))
+    t, y, w, x0, iters = g(case, "t"), g(case, "y"), float(g(case, "w")), g(case, "x0"), int(g(case, "iters"))
+    hl.pnolhost_set_store_jacobian(store_j)
+    try:
+        X = x0.copy()
+        m = t.size
+        F0, F, rep = np.empty(m), np.empty(m), np.zeros(6)
+        st = hl.pnolhost_lm_lorentz(_p(t), _p(y), C.c_longlong(m), C.c_double(w), _p(X), X.size, C.c_double(0.001), C.c_double(10.0),
+                                    C.c_double(1e-7), C.c_double(iters), C.c_double(0.0), serial, _p(F0), _p(F), _p(rep))
+    finally:
+        hl.pnolhost_set_store_jacobian(1)
+    assert st == 0, hl.pnolhost_last_error()
+    assert np.array_equal(X, g(case, "X")) and np.array_equal(F0, g(case, "F0")) and np.array_equal(F, g(case, "F"))
+    assert int(rep[0]) == iters and int(rep[1]) + int(rep[2]) == iters          # iterations = accepted + rejected
+
+
+def test_levenberg_marquardt_reference_examples(hl):
+    # testLMCubicLinearCoef (Source/Examples.cpp:415-452): bit for bit. testLMExpMPI (:128-159): the product's ExpCurve model calls the
+    # shared host/device exp instead of libm's (include/pnol/ExampleObjectives.hpp), so the fit agrees to 1e-9, not to the bit
+    for name, key, x0, exact in (("cubic", "testLMCubicLinearCoef", np.full(4, 0.1), True), ("expcurve", "testLMExpMPI", np.array([9.0, 0.5, 0.3]), False)):
+        X = x0.copy()
+        rep = np.zeros(6)
+        st = hl.pnolhost_lm_example(name.encode(), _p(X), X.size, C.c_double(0.001), C.c_double(10.0), C.c_double(1e-6), C.c_double(100.0),
+                                    C.c_double(1e-6), None, None, _p(rep))
+        assert st == 0, hl.pnolhost_last_error()
+        if exact:
+            assert np.array_equal(X, g(key, "X"))
+        else:
+            assert np.linalg.norm(X - g(key, "X")) <= 1e-9 * np.linalg.norm(g(key, "X"))
+            assert np.allclose(X, [10.2, 0.4, 0.1], rtol=1e-8)              # the known answer (Source/ExampleObjectives.hpp:145)
+
+
 def test_paths_outside_the_stand_in_fail_loudly(hl):
-    # LM / GA entry points are not answered by the stand-in: the host classes surface the status as an error, nothing is faked
-    X = np.array([9.0, 0.5, 0.3])
-    rep = np.zeros(6)
-    st = hl.pnolhost_lm_example(b"expcurve", _p(X), 3, C.c_double(0.001), C.c_double(10.0), C.c_double(1e-6), C.c_double(5.0), C.c_double(1e-6),
-                                None, None, _p(rep))
+    # the GA entry points are not answered by the stand-in: the host class surfaces the status as an error, nothing is faked
+    X = np.full(4, 3.0)
+    lb, ub = np.full(4, -10.0), np.full(4, 10.0)
+    f0, fo = C.c_double(), C.c_double()
+    rep = np.zeros(7)
+    hl.pnolhost_set_stream(C.c_void_p(0), C.c_ulonglong(0), C.c_ulonglong(1), C.c_double(0.99))
+    st = hl.pnolhost_ga(b"rosenbrock", _p(X), 4, _p(lb), _p(ub), 50, 3, C.c_double(0.1), C.c_double(0.3), C.c_double(0.2), C.c_double(0.5),
+                        C.c_double(0.01), C.c_double(50.0), 0, C.byref(f0), C.byref(fo), _p(rep))
     assert st != 0 and b"stand-in" in hl.pnolhost_last_error()
