@@ -180,3 +180,46 @@ def test_paths_outside_the_stand_in_fail_loudly(hl):
     st = hl.pnolhost_ga(b"rosenbrock", _p(X), 4, _p(lb), _p(ub), 50, 3, C.c_double(0.1), C.c_double(0.3), C.c_double(0.2), C.c_double(0.5),
                         C.c_double(0.01), C.c_double(50.0), 0, C.byref(f0), C.byref(fo), _p(rep))
     assert st != 0 and b"stand-in" in hl.pnolhost_last_error()
+
+
+def test_reference_example_drivers_print_the_reference_numbers(tmp_path):
+    # The reference's OWN Source/Examples.cpp (unmodified, from where it lies; oracle/dropin_examples.cpp) compiled against include/pnol,
+    # the unmodified host sources and the oracle-backed stand-in: what its drivers print is what the verbatim reference prints
+    # (tests/golden/examples_ref.json) -- iterates digit for digit (17 significant digits) and, for the serial classes, the number of
+    # objective evaluations (getEvals(): host objEval calls + points evaluated behind the C-ABI). Needs /root/reference to build.
+    import json
+    from test_gpu_dropin_examples import scalar, vectors
+    cxx = shutil.which("g++")
+    if cxx is None or not os.path.isdir("/root/reference/Source"):
+        pytest.skip("needs g++ and /root/reference (the reference's Examples.cpp is compiled from where it lies)")
+    host = os.path.join(ROOT, "parallelnonlinearoptimizationlibrary_b200", "host")
+    exe = str(tmp_path / "examples_cpu")
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-I" + os.path.join(inc, "pnol", "nompi"), "-I" + os.path.join(inc, "pnol"),
+                           "-I" + inc, "-I" + host, "-I/root/reference/Source", os.path.join(ROOT, "oracle", "dropin_examples.cpp")] +
+                          sorted(glob.glob(os.path.join(host, "*.cpp"))) +
+                          [os.path.join(ROOT, "oracle", "host_logic_device.cpp"), os.path.join(ROOT, "oracle", "pnol_oracle.cpp"), "-o", exe])
+    ref = json.load(open(os.path.join(HERE, "golden", "examples_ref.json")))
+
+    def run(driver):
+        r = subprocess.run([exe, driver, str(ref["pool_width"]), str(ref["seed"])], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (driver, r.stderr[-500:])
+        return r.stdout, ref["tails"][driver]
+
+    for driver, key in (("testBFGS", "X = "), ("testBFGS_booth", "X = "), ("testBFGS_MPI", "X = "), ("testBFGSBnd", "Xopt = "),
+                        ("testBFGSBndMPISW", "Xopt = "), ("testBFGSBnd_MPI", "X = ")):
+        ours, want = run(driver)
+        assert np.array_equal(vectors(ours, key)[-1], vectors(want, key)[-1]), driver
+        assert scalar(ours, "f0 =") == scalar(want, "f0 =")
+    for driver in ("testBFGS", "testBFGS_booth", "testBFGSBnd"):                 # serial classes: same evaluation count
+        ours, want = run(driver)
+        assert scalar(ours, "Optimization used") == scalar(want, "Optimization used"), driver
+    ours, want = run("testSimplexSearch")
+    assert scalar(ours, "Optimization used") == scalar(want, "Optimization used") == 3884
+    assert np.allclose(vectors(ours, "X = ")[-1], vectors(want, "X = ")[-1], atol=2e-5)      # the reference prints 5 digits here
+    ours, want = run("testLMCubicLinearCoef")
+    assert np.array_equal(vectors(ours)[-1], vectors(want)[-1])
+    for driver in ("testGradientEvaluation", "testGradientApproxMultMPIRecur"):
+        ours, want = run(driver)
+        a, b = vectors(ours), vectors(want)
+        assert len(a) == len(b) and all(np.array_equal(u, v) for u, v in zip(a, b)), driver
