@@ -7,8 +7,8 @@
 // the reference's control flow on a box without a GPU: with the oracle's arithmetic (= the oracle shim's: sequential sums, the
 // literal two-product updateHessianInv) under them, the host controllers reproduce the verbatim reference's iterates BIT FOR BIT,
 // which isolates every difference seen on the GPU to the summation order of the device's dense algebra. The Levenberg-Marquardt
-// entry points (residuals, FD Jacobian, one iteration's device work) are answered the same way; the GA entry points are not provided
-// (they return an error): that loop is restated in the oracle itself.
+// entry points (residuals, FD Jacobian, one iteration's device work) are answered the same way, the GA state machine by replaying the
+// oracle's restatement of the whole loop up to the requested generation. The stand-alone GA stage entry points are not provided.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -47,6 +47,12 @@ void oracle_lu_solve(const double * A, const double * b, int n, double * x);
 int oracle_check_box_bounds(double * X, const double * Xlb, const double * Xub, int n);
 double oracle_compute_alpha_bnd(const double * X, const double * Xlb, const double * Xub, const double * p, int Nprm);
 double oracle_stream_uniform(uint64_t seed, uint64_t k, double scale);
+int oracle_ga(int kind, const double * scalars, const long long * ints, const double * const * cols, long long m,
+              double * X, const double * Xlb, const double * Xub, int Nparam, int Npop, int maxGenerations, double eliteFrac,
+              double crossFrac, double eliteMutationFrac, double mutationSize, double eliteMutationSize,
+              double NstaticGenerations, int stopAfter, const double * values, uint64_t n_values, uint64_t seed, double scale,
+              double * f0_out, double * fOpt_out, double * Xpop_out, double * F_out, int * cross_idx, int * mut_idx,
+              int * elite_idx, uint64_t * stream_pos_out);
 }
 
 struct pnol_ctx { std::string err; };
@@ -54,7 +60,11 @@ struct pnol_functor {
 	pnol_functor_desc d;
 	std::vector<std::vector<double> > owned;      // residual models: the data columns are copied (as the product copies them to the device)
 };
-struct pnol_ga { int unused; };
+struct pnol_ga {
+	pnol_ctx * ctx; const pnol_functor * f; pnol_ga_params prm; int n; pnol_stream_desc stream;
+	std::vector<double> lb, ub, values, x0, pop, F;
+	int generations; double f0; pnol_ga_status st;
+};
 
 #define FARGS(f) (f)->d.kind, (f)->d.scalars, (f)->d.ints, (f)->d.columns, (f)->d.m
 
@@ -199,14 +209,64 @@ int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const
 	return PNOL_OK;
 }
 
-// ---- not part of the host-logic tests (the GA loop is restated in the oracle itself) ----
-int pnol_ga_create(pnol_ctx * ctx, const pnol_functor *, const pnol_ga_params *, int, const double *, const double *, const pnol_stream_desc *,
-                   pnol_ga **) { return unavailable(ctx, "pnol_ga_create"); }
-void pnol_ga_destroy(pnol_ga *) {}
-int pnol_ga_init(pnol_ga *, const double *, double *) { return PNOL_ERR_NO_FUNCTOR; }
-int pnol_ga_generation(pnol_ga *) { return PNOL_ERR_NO_FUNCTOR; }
-int pnol_ga_status_get(pnol_ga *, pnol_ga_status *) { return PNOL_ERR_NO_FUNCTOR; }
-int pnol_ga_get_population(pnol_ga *, double *, double *) { return PNOL_ERR_NO_FUNCTOR; }
+// ---- genetic algorithm (Source/GeneticAlgorithmMPI.cpp:12-276): the oracle restates the whole loop (oracle_ga); the state machine
+// of the C-ABI is answered by replaying it up to the requested generation (deterministic: same stream, same start) ----
+int pnol_ga_create(pnol_ctx * ctx, const pnol_functor * f, const pnol_ga_params * params, int n, const double * xlb, const double * xub,
+                   const pnol_stream_desc * stream, pnol_ga ** out)
+{
+	if (!f || !params || !stream || f->d.kind >= 100 || params->npop < 2) return unavailable(ctx, "pnol_ga_create (bad arguments)");
+	pnol_ga * ga = new pnol_ga;
+	ga->ctx = ctx; ga->f = f; ga->prm = *params; ga->n = n; ga->stream = *stream;
+	ga->lb.assign(xlb, xlb + n); ga->ub.assign(xub, xub + n);
+	if (stream->values) { ga->values.assign(stream->values, stream->values + stream->n_values); }
+	ga->generations = 0;
+	std::memset(&ga->st, 0, sizeof ga->st);
+	*out = ga;
+	return PNOL_OK;
+}
+void pnol_ga_destroy(pnol_ga * ga) { delete ga; }
+static int ga_replay(pnol_ga * ga)
+{
+	const pnol_ga_params & p = ga->prm;
+	std::vector<double> X(ga->x0);
+	ga->pop.assign((size_t) p.npop * ga->n, 0.0);
+	ga->F.assign(p.npop, 0.0);
+	double f0 = 0, fOpt = 0;
+	uint64_t pos = 0;
+	int it = oracle_ga(FARGS(ga->f), X.data(), ga->lb.data(), ga->ub.data(), ga->n, p.npop, p.max_generations, p.elite_frac, p.cross_frac,
+	                   p.elite_mutation_frac, p.mutation_size, p.elite_mutation_size, p.n_static_generations, ga->generations,
+	                   ga->values.empty() ? nullptr : ga->values.data(), (uint64_t) ga->values.size(), ga->stream.seed, ga->stream.scale,
+	                   &f0, &fOpt, ga->pop.data(), ga->F.data(), nullptr, nullptr, nullptr, &pos);
+	if (it == -1) { ga->ctx->err = "GA fractions leave no room for random children"; return PNOL_ERR_INVALID; }
+	if (it == -2) { ga->ctx->err = "random stream exhausted"; return PNOL_ERR_STREAM; }
+	ga->f0 = f0;
+	ga->st.generation = it;
+	ga->st.stopped = it < ga->generations ? 1 : 0;        // the static-generation test ended the loop before the requested generation
+	ga->st.f_best = fOpt;
+	ga->st.stream_pos = pos;
+	ga->st.n_elite = (int) std::ceil(p.elite_frac * p.npop);
+	ga->st.n_elite_mut = (int) std::ceil(p.elite_mutation_frac * p.npop);
+	ga->st.n_cross = (int) std::ceil(p.cross_frac * p.npop);
+	ga->st.n_rand = p.npop - ga->st.n_elite - ga->st.n_elite_mut - ga->st.n_cross;
+	return PNOL_OK;
+}
+int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out)
+{
+	ga->x0.assign(x0, x0 + ga->n);
+	ga->generations = 0;
+	int st = ga_replay(ga);
+	if (st == PNOL_OK && f0_out) *f0_out = ga->f0;
+	return st;
+}
+int pnol_ga_generation(pnol_ga * ga) { ga->generations++; return ga_replay(ga); }
+int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * st) { *st = ga->st; return PNOL_OK; }
+int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F)
+{
+	if (xpop) std::memcpy(xpop, ga->pop.data(), ga->pop.size() * sizeof(double));
+	if (F) std::memcpy(F, ga->F.data(), ga->F.size() * sizeof(double));
+	return PNOL_OK;
+}
+// the stand-alone stage entry points are exercised against the oracle on the GPU (tests/test_gpu_ga.py); not answered here
 int pnol_ga_pop_sort(pnol_ctx * ctx, double *, double *, long long, int) { return unavailable(ctx, "pnol_ga_pop_sort"); }
 int pnol_ga_check_bounds(pnol_ctx * ctx, double *, long long, int, const double *, const double *, unsigned char *, const pnol_stream_desc *,
                          uint64_t *) { return unavailable(ctx, "pnol_ga_check_bounds"); }

@@ -1,5 +1,6 @@
 """CPU: the host controllers of the plugin API (parallelnonlinearoptimizationlibrary_b200/host/*.cpp: BFGS, BFGS_MPI, BFGS_Bnd,
-BFGS_Bnd_MPI_SW, BFGSBnd_MPI, SimplexSearch, LevMarq, LevMarqMPI, the Objective stencil members, the box helpers) WITHOUT a GPU: the unmodified host sources
+BFGS_Bnd_MPI_SW, BFGSBnd_MPI, SimplexSearch, LevMarq, LevMarqMPI, GeneticAlgorithm[MPI], the Objective stencil members, the box helpers)
+WITHOUT a GPU: the unmodified host sources
 are linked into a test-only library against oracle/host_logic_device.cpp, which answers the C-ABI calls of these paths with the CPU
 oracle instead of CUDA kernels (test infrastructure; the product libraries have no CPU path and this library is never shipped).
 
@@ -170,16 +171,37 @@ def test_levenberg_marquardt_reference_examples(hl):
             assert np.allclose(X, [10.2, 0.4, 0.1], rtol=1e-8)              # the known answer (Source/ExampleObjectives.hpp:145)
 
 
+@pytest.mark.parametrize("spec,obj", [("powerprod2", "power:2"), ("rastrigin", "rastrigin"), ("rosenbrock", "rosenbrock")])
+@pytest.mark.parametrize("serial", [0, 1])
+def test_genetic_algorithm_host_class_bit_for_bit(hl, spec, obj, serial):
+    # GeneticAlgorithmMPI / GeneticAlgorithm::findMinBnd over the GA state machine of the C-ABI (answered by replaying the oracle's
+    # restatement of the loop): result, f0, fOpt, generations and the number of random draws of the verbatim reference
+    c = "ga_%s" % spec
+    hl.pnolhost_set_stream(C.c_void_p(0), C.c_ulonglong(0), C.c_ulonglong(int(g(c, "seed"))), C.c_double(float(g(c, "scale"))))
+    X = g(c, "x0").copy()
+    lb, ub = g(c, "lb"), g(c, "ub")
+    f0, fo = C.c_double(), C.c_double()
+    rep = np.zeros(7)
+    st = hl.pnolhost_ga(obj.encode(), _p(X), X.size, _p(lb), _p(ub), int(g(c, "npop")), int(g(c, "gens")), C.c_double(0.1), C.c_double(0.3),
+                        C.c_double(0.2), C.c_double(0.5), C.c_double(0.01), C.c_double(50.0), serial, C.byref(f0), C.byref(fo), _p(rep))
+    assert st == 0, hl.pnolhost_last_error()
+    assert np.array_equal(X, g(c, "X")) and f0.value == g(c, "f0")[0] and fo.value == g(c, "fOpt")[0]
+    assert int(rep[0]) == int(g(c, "gens")) and int(rep[2]) == int(g(c, "stream_pos")[0])
+
+
 def test_paths_outside_the_stand_in_fail_loudly(hl):
-    # the GA entry points are not answered by the stand-in: the host class surfaces the status as an error, nothing is faked
+    # what the stand-in does not answer comes back as an error through the host classes, nothing is faked: invalid GA fractions, and a
+    # residual model handed to a scalar algorithm
     X = np.full(4, 3.0)
     lb, ub = np.full(4, -10.0), np.full(4, 10.0)
     f0, fo = C.c_double(), C.c_double()
     rep = np.zeros(7)
     hl.pnolhost_set_stream(C.c_void_p(0), C.c_ulonglong(0), C.c_ulonglong(1), C.c_double(0.99))
-    st = hl.pnolhost_ga(b"rosenbrock", _p(X), 4, _p(lb), _p(ub), 50, 3, C.c_double(0.1), C.c_double(0.3), C.c_double(0.2), C.c_double(0.5),
+    st = hl.pnolhost_ga(b"rosenbrock", _p(X), 4, _p(lb), _p(ub), 50, 3, C.c_double(0.6), C.c_double(0.6), C.c_double(0.2), C.c_double(0.5),
                         C.c_double(0.01), C.c_double(50.0), 0, C.byref(f0), C.byref(fo), _p(rep))
-    assert st != 0 and b"stand-in" in hl.pnolhost_last_error()
+    assert st != 0 and b"random children" in hl.pnolhost_last_error()
+    st = hl.pnolhost_bfgs(b"bfgs", b"no_such_objective", _p(X), 4, _p(np.zeros(11)), None, None, 0, 0, C.byref(f0), C.byref(fo), C.byref(C.c_int()))
+    assert st != 0
 
 
 def test_reference_example_drivers_print_the_reference_numbers(tmp_path):
@@ -219,6 +241,10 @@ def test_reference_example_drivers_print_the_reference_numbers(tmp_path):
     assert np.allclose(vectors(ours, "X = ")[-1], vectors(want, "X = ")[-1], atol=2e-5)      # the reference prints 5 digits here
     ours, want = run("testLMCubicLinearCoef")
     assert np.array_equal(vectors(ours)[-1], vectors(want)[-1])
+    for driver in ("testGA", "testGAParallel"):                                  # same stream, same draws: bit for bit
+        ours, want = run(driver)
+        assert np.array_equal(vectors(ours, "at params:")[-1], vectors(want, "at params:")[-1]), driver
+        assert scalar(ours, "At generation =") == scalar(want, "At generation =")
     for driver in ("testGradientEvaluation", "testGradientApproxMultMPIRecur"):
         ours, want = run(driver)
         a, b = vectors(ours), vectors(want)
