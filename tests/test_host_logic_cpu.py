@@ -189,6 +189,40 @@ def test_genetic_algorithm_host_class_bit_for_bit(hl, spec, obj, serial):
     assert int(rep[0]) == int(g(c, "gens")) and int(rep[2]) == int(g(c, "stream_pos")[0])
 
 
+@pytest.mark.parametrize("spec,obj,n", [("rosenbrock", "rosenbrock", 5), ("rosenbrock", "rosenbrock", 40), ("booth", "booth", 2),
+                                        ("goldstein", "goldstein", 2), ("powerprod3", "power:3", 5), ("rastrigin", "rastrigin", 12)])
+def test_objective_stencil_members_bit_for_bit(hl, spec, obj, n):
+    # Objective::gradientApproximation / gradientApproximationMPI / hessianApproximation as a user calls them, against the committed
+    # outputs of the reference's own members (Source/PNOL_Objective.cpp:12-34, 88-159, 38-85)
+    case = "fdgrad_%s_%d" % (spec, n)
+    x, dx = np.ascontiguousarray(g(case, "x")), np.ascontiguousarray(g(case, "dx"))
+    for which, key in ((0, "g"), (1, "g_mpi")):
+        out = np.empty(n)
+        assert hl.pnolhost_gradient(obj.encode(), _p(x), _p(dx), n, which, _p(out)) == 0, hl.pnolhost_last_error()
+        assert np.array_equal(out, g(case, key))
+    if n <= 12:
+        dxh = np.ascontiguousarray(g(case, "dxh"))
+        B = np.empty((n, n))
+        assert hl.pnolhost_hessian(obj.encode(), _p(x), _p(dxh), n, _p(B)) == 0, hl.pnolhost_last_error()
+        assert np.array_equal(B, g(case, "B"))
+
+
+def test_recur_gradient_and_box_helpers_bit_for_bit(hl):
+    c = "recur_rosenbrock_8"
+    xr, constx = np.ascontiguousarray(g(c, "xr")), np.ascontiguousarray(g(c, "constx"))
+    ind = np.ascontiguousarray(g(c, "ind"), dtype=np.uint8)
+    dxr = np.full(xr.size, 1e-6)
+    gr, f = np.empty(xr.size), C.c_double()
+    assert hl.pnolhost_gradient_recur(b"rosenbrock", _p(xr), _p(dxr), xr.size, _p(constx), _p(ind), constx.size, _p(gr), C.byref(f)) == 0
+    assert np.array_equal(gr, g(c, "g_mpi")) and f.value == g(c, "f")[0]
+    hl.pnolhost_compute_alpha_bnd.restype = C.c_double
+    x, lb, ub, p = (np.ascontiguousarray(g("box", k)) for k in ("xin", "lb", "ub", "p"))
+    assert hl.pnolhost_compute_alpha_bnd(_p(x), _p(lb), _p(ub), _p(p), x.size) == g("box", "alphabnd")[0]
+    xo = np.ascontiguousarray(g("box", "x")).copy()
+    assert hl.pnolhost_check_box_bounds(_p(xo), _p(lb), _p(ub), xo.size) == 0
+    assert np.array_equal(xo, g("box", "Xfixed"))
+
+
 def test_paths_outside_the_stand_in_fail_loudly(hl):
     # what the stand-in does not answer comes back as an error through the host classes, nothing is faked: invalid GA fractions, and a
     # residual model handed to a scalar algorithm
