@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * BFGS_bnd_linesearch.hpp -- BFGS_Bnd: the serial box-bounded BFGS of /root/reference/Source/BFGS_bnd_linesearch.hpp:30-146
  * (same setParams order, defaults :125-141, setGradVec / setinitialScalingVec).
@@ -19,6 +21,7 @@ class BFGS_Bnd : public AlgorithmBnd {
   public:
 	void findMinBnd( vector <double> & X, vector <double> & Xlb, vector <double> & Xub, double & f0, double & fOpt )
 	{
+		pnol::LocalScope serial;         // the serial class never touches the communicator (Source/BFGS_bnd_linesearch.cpp)
 		impl.setObjPtr( *objPtr );
 		impl.findMinBnd( X, Xlb, Xub, f0, fOpt );
 	}

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * BFGS_bnd_linesearch_MPI_SW.hpp -- BFGS_Bnd_MPI_SW: box-bounded BFGS with a pooled strong-Wolfe line search and
  * active-set recursion. Interface of /root/reference/Source/BFGS_bnd_linesearch_MPI_SW.hpp:29-164 (setParams order

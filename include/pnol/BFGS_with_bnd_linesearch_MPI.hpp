@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * BFGS_with_bnd_linesearch_MPI.hpp -- BFGSBnd_MPI: the older box-bounded BFGS with the pooled SECANT line search and the
  * one-level active-set recursion, interface of /root/reference/Source/BFGS_with_bnd_linesearch_MPI.hpp:35-122 (same

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * BFGS_with_linesearch.hpp -- BFGS (unbounded, cubic-interpolation strong-Wolfe line search), interface of
  * /root/reference/Source/BFGS_with_linesearch.hpp:25-105, and the two free functions every BFGS variant shares.

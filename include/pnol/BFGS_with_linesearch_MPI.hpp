@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * BFGS_with_linesearch_MPI.hpp -- BFGS_MPI (pooled secant line search), interface of
  * /root/reference/Source/BFGS_with_linesearch_MPI.hpp:32-103. The reference evaluates a pool of Nprocs step lengths,

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * Box_boundary_functions.hpp -- box-bound helpers, same names as
  * /root/reference/Source/Box_boundary_functions.hpp:28-32 plus computeAlphaBnd / checkAlphaPoolBnd which the

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * GeneticAlgorithm.hpp -- GeneticAlgorithm (the reference's serial class, /root/reference/Source/GeneticAlgorithm.hpp:37-87).
  * Same device path as GeneticAlgorithmMPI (the two reference classes produce identical populations for one stream);
@@ -23,6 +25,7 @@ class GeneticAlgorithm : public AlgorithmBnd {
   public:
 	void findMinBnd( std::vector <double> & X, std::vector <double> & Xlb, std::vector <double> & Xub, double & f0 , double & fOpt )
 	{
+		pnol::LocalScope serial;         // the serial class never touches the communicator (Source/GeneticAlgorithm.cpp)
 		pnol::gaFindMinBnd( objPtr, Npop, maxGenerations, eliteFrac, crossFrac, eliteMutationFrac, mutationSize, eliteMutationSize,
 				NstaticGenerations, verbose, X, Xlb, Xub, f0, fOpt, report );
 	}

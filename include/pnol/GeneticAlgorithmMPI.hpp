@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * GeneticAlgorithmMPI.hpp -- GeneticAlgorithmMPI, interface of /root/reference/Source/GeneticAlgorithmMPI.hpp:35-82.
  * The whole generation loop runs on the device (pnol_ga_*): population, fitness sweep, selection, crossover,

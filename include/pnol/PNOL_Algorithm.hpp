@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * PNOL_Algorithm.hpp -- algorithm base classes, identical in shape to the reference
  * (/root/reference/Source/PNOL_Algorithm.hpp:22-65): non-owning objective pointers set with setObjPtr(), pure

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * PNOL_Objective.hpp -- the objective plugin API, kept source compatible with the reference
  * (/root/reference/Source/PNOL_Objective.hpp:25-62): same class names, same pure virtual objEval signatures (non-const

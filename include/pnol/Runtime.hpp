@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * Runtime.hpp -- process-wide device runtime behind the PNOL plugin classes.
  *
@@ -40,8 +42,15 @@ class Runtime {
 	// random stream used by the genetic algorithms (replaces srand(time(0)) + timeRand(),
 	// Source/GeneticAlgorithmMPI.cpp:57,66)
 	void setRandomStream(const pnol_stream_desc & s) { stream_ = s; haveStream_ = true; }
+	void clearRandomStream() { haveStream_ = false; }   // back to the default (clock-seeded, rank-0-broadcast) stream
 	bool haveRandomStream() const { return haveStream_; }
 	const pnol_stream_desc & randomStream() const { return stream_; }
+	// The stream an algorithm uses when the caller set none: srand((unsigned) time(0)) of the reference
+	// (Source/GeneticAlgorithmMPI.cpp:57, Source/SimplexSearch.cpp:57) as a clock-seeded counter stream. The reference takes
+	// every random decision from ROOT (zero-and-Allreduce of the population, Source/GeneticAlgorithmMPI.cpp:300-330), so ranks
+	// seeded from their own clocks are harmless there; here every rank replays the same stream, so the seed is drawn on rank 0
+	// and broadcast over the context's communicator (a collective call: all ranks enter the algorithm together, as in the reference).
+	pnol_stream_desc defaultStream(double scale);
 	// BFGS inverse-Hessian update form (PNOL_HINV_RANK2 default, PNOL_HINV_LITERAL = the reference's two products)
 	int hessianUpdateMode() const { return hinvMode_; }
 	void setHessianUpdateMode(int m) { hinvMode_ = m; }
@@ -69,6 +78,20 @@ class Runtime {
 	int jacMode_;
 	bool jacCache_;
 	bool storeJ_ = true;
+};
+
+// RAII local (non-collective) mode for the serial classes: the reference's BFGS, BFGS_Bnd, LevMarq, GeneticAlgorithm and the
+// non-MPI stencil members never call MPI (a program may run them on one rank only), so nothing under this scope may issue a
+// collective even when the context carries a communicator (pnol_comm_set_local).
+class LocalScope {
+  public:
+	LocalScope() : ctx_(Runtime::instance().ctx()), prev_(pnol_comm_set_local(ctx_, 1)) {}
+	~LocalScope() { pnol_comm_set_local(ctx_, prev_); }
+	LocalScope(const LocalScope &) = delete;
+	LocalScope & operator=(const LocalScope &) = delete;
+  private:
+	pnol_ctx * ctx_;
+	int prev_;
 };
 
 // RAII device functor (the device twin an Objective / MultiObjective hands to the algorithms)

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * SimplexSearch.hpp -- SimplexSearch (the reference's Nelder-Mead class, /root/reference/Source/SimplexSearch.hpp:23-62) behind the
  * unchanged API: setObjPtr / setSimplexParams / findMin(X, f0, fOpt).

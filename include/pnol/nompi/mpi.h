@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 /*
  * mpi.h -- what is left of MPI for a user translation unit that is compiled against include/pnol instead of the reference's
  * Source/ (the reference's headers #include <mpi.h>, /root/reference/Source/PNOL_Objective.hpp:20, and its example drivers ask

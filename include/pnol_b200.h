@@ -16,6 +16,18 @@
  *   - one context drives one GPU; multi-GPU runs use one process (or thread) per GPU and a communicator
  *     attached with pnol_comm_init(). A context must not be used from two host threads at once.
  *   - reference citations are path:line under /root/reference/.
+ *
+ * Environment switches read by the library (tuning / A-B timing runs; the defaults are the product path). Read once per
+ * process unless stated:
+ *   PNOL_SYRK_NO_PAIR=1   J^T J with the stream-K TMA kernel instead of the CTA-pair kernel (n = 256, no F)
+ *   PNOL_SYRK_LEGACY=1    J^T J with the LDGSTS-ring kernel (one tile role per CTA)
+ *   PNOL_SYRK_WDIAG=w     cost of a diagonal tile's chunk in the stream-K work plan
+ *   PNOL_SYRK_NOF=1       J^T J without J^T F (timing only: results lack the right-hand side)
+ *   PNOL_SWEEP_DEEP=0     fitness sweep with one load ahead instead of four; PNOL_SWEEP_G / PNOL_SWEEP_WAVES: sweep tile shapes
+ *   PNOL_COPY_THREADS=k   host threads of the staged pageable <-> device copies (1..8, default 4)
+ *   PNOL_FUSED_MB=x       MB of J per row block of pnol_lm_normal_eq_fused / J == NULL steps (read per call, default 512)
+ *   PNOL_GA_LEGACY=1      genetic algorithm with the stage-by-stage generation of round 1 instead of the fused pipeline
+ * and by the host classes (include/pnol/Runtime.hpp): PNOL_DEVICE, PNOL_POOL_WIDTH, PNOL_LM_JACOBIAN_CACHE.
  */
 #ifndef PNOL_B200_H_
 #define PNOL_B200_H_
@@ -71,6 +83,10 @@ int pnol_comm_unique_id(char id[PNOL_COMM_ID_BYTES]);                 /* rank 0 
 int pnol_comm_init(pnol_ctx * ctx, const char id[PNOL_COMM_ID_BYTES], int nranks, int rank);
 int pnol_comm_rank(pnol_ctx * ctx);                                   /* 0 when no communicator */
 int pnol_comm_size(pnol_ctx * ctx);                                   /* 1 when no communicator */
+/* local (non-collective) mode: while on, the context behaves like a single-GPU context -- no entry point issues a collective and
+ * pnol_comm_rank / pnol_comm_size answer 0 / 1. The serial plugin classes (BFGS, BFGS_Bnd, LevMarq, GeneticAlgorithm, SimplexSearch,
+ * Objective::gradientApproximation) run under it, as the reference's serial classes never touch MPI. Returns the previous setting. */
+int pnol_comm_set_local(pnol_ctx * ctx, int on);
 int pnol_comm_allreduce_sum(pnol_ctx * ctx, double * buf, size_t count);   /* in place, host or device buf */
 int pnol_comm_allgather(pnol_ctx * ctx, const double * send, double * recv, size_t count_per_rank);
 int pnol_comm_broadcast(pnol_ctx * ctx, double * buf, size_t count, int root);
@@ -213,6 +229,13 @@ int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, const double
 /* a9: damped solve  A sigma = rhs  by Cholesky (A symmetric positive definite, only the lower triangle is
  * read). *info = 0 ok, k > 0: pivot k not positive. Replaces luSolve (Source/LevenbergMarquardtMPI.cpp:88). */
 int pnol_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info);
+
+/* General inverse Ainv = A^-1 by LU with partial pivoting (first largest |entry| on ties) and one pair of substitutions per unit
+ * vector: `matrixInverse` of the forward-difference Hessian when initHessFD is set (Source/BFGS_bnd_linesearch_MPI_SW.cpp:51-59,
+ * Source/BFGS_with_linesearch.cpp:35-41). An indefinite A is inverted like any other, as the reference does; *info = k + 1 when
+ * pivot k is exactly zero (the entries are then inf / NaN, as the reference's would be), else 0. Operation for operation the
+ * oracle/shim definition of matrixInverse (the reference takes it from an un-vendored library), so results agree bit for bit. */
+int pnol_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info);
 
 /* ---------------------------------------------------------------------------------------------------
  * a11 / a12: dense BFGS pieces

@@ -80,6 +80,11 @@ int pnol_ctx_create(pnol_ctx ** ctx, int) { *ctx = new pnol_ctx; return PNOL_OK;
 void pnol_ctx_destroy(pnol_ctx * ctx) { delete ctx; }
 const char * pnol_last_error(pnol_ctx * ctx) { return ctx ? ctx->err.c_str() : ""; }
 int pnol_comm_rank(pnol_ctx *) { return 0; }
+int pnol_comm_size(pnol_ctx *) { return 1; }
+int pnol_comm_set_local(pnol_ctx *, int) { return 0; }
+int pnol_comm_broadcast(pnol_ctx *, double *, size_t, int) { return PNOL_OK; }
+int pnol_comm_allreduce_sum(pnol_ctx *, double *, size_t) { return PNOL_OK; }
+int pnol_comm_allgather(pnol_ctx *, const double * send, double * recv, size_t n) { std::memmove(recv, send, n * sizeof(double)); return PNOL_OK; }
 
 // "device" memory is host memory here
 int pnol_malloc(pnol_ctx *, void ** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? PNOL_OK : PNOL_ERR_CUDA; }
@@ -146,6 +151,18 @@ int pnol_bfgs_update_hinv(pnol_ctx *, double * D, const double * g, const double
 int pnol_spd_solve(pnol_ctx *, const double * A, const double * rhs, int n, double * x, int * info)
 {
 	oracle_lu_solve(A, rhs, n, x);
+	if (info) *info = 0;
+	return PNOL_OK;
+}
+// matrixInverse of the FD Hessian: one LU solve per unit vector (the shim's definition)
+int pnol_lu_inverse(pnol_ctx *, const double * A, int n, double * Ainv, int * info)
+{
+	std::vector<double> e(n), col(n);
+	for (int j = 0; j < n; j++) {
+		for (int i = 0; i < n; i++) e[i] = (i == j) ? 1.0 : 0.0;
+		oracle_lu_solve(A, e.data(), n, col.data());
+		for (int i = 0; i < n; i++) Ainv[(size_t) i * n + j] = col[i];
+	}
 	if (info) *info = 0;
 	return PNOL_OK;
 }

@@ -81,10 +81,10 @@ EXPORTS = [
     "pnol_ctx_create", "pnol_ctx_destroy", "pnol_last_error", "pnol_ctx_device", "pnol_ctx_stream", "pnol_ctx_sync",
     "pnol_ctx_sm_count", "pnol_ctx_launches", "pnol_version", "pnol_malloc", "pnol_free", "pnol_memcpy", "pnol_memset",
     "pnol_host_alloc", "pnol_host_free", "pnol_comm_unique_id", "pnol_comm_init", "pnol_comm_rank", "pnol_comm_size",
-    "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
+    "pnol_comm_set_local", "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
     "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
     "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
-    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve",
+    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve", "pnol_lu_inverse",
     "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
@@ -292,6 +292,10 @@ class Context:
     def comm_rank(self):
         return self.lib.pnol_comm_rank(self.h)
 
+    def set_local(self, on):
+        """local (non-collective) mode on / off; returns the previous setting"""
+        return bool(self.lib.pnol_comm_set_local(self.h, int(bool(on))))
+
     def allreduce_sum(self, buf, count):
         self.check(self.lib.pnol_comm_allreduce_sum(self.h, _ptr(buf), C.c_size_t(count)))
 
@@ -439,6 +443,14 @@ class Context:
         info = C.c_int()
         self.check(self.lib.pnol_spd_solve(self.h, _ptr(A), _ptr(rhs), int(n), _ptr(x), C.byref(info)))
         return x
+
+    def lu_inverse(self, A, n):
+        """general inverse (LU, partial pivoting) -- matrixInverse of the FD Hessian; returns (Ainv, info)"""
+        A = _f64(A)
+        out = np.empty((n, n))
+        info = C.c_int()
+        self.check(self.lib.pnol_lu_inverse(self.h, _ptr(A), int(n), _ptr(out), C.byref(info)))
+        return out, info.value
 
     # ---- BFGS dense pieces ----
     def matvec_neg(self, D, g, n, p=None):

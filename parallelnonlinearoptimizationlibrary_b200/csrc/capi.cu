@@ -766,12 +766,13 @@ static int normal_eq_blocks(pnol_ctx * ctx, const pnol_functor * f, const double
 			if (st == PNOL_OK) st = launch_syrk(ctx, Jb, Fr, nr, n, part);
 		}
 		if (st == PNOL_OK) {
-			packed_accumulate_kernel<<<(unsigned) ((packed_count + 255) / 256), 256, 0, ctx->stream>>>(total, part, (long long) packed_count);
-			ctx->launches++;
-			if (cudaGetLastError() != cudaSuccess) st = PNOL_ERR_CUDA;
+			st = [&]() -> int {
+				PNOL_LAUNCH(ctx, packed_accumulate_kernel, (unsigned) ((packed_count + 255) / 256), 256, 0, total, part, (long long) packed_count);
+				return PNOL_OK;
+			}();
 		}
 	}
-	cudaFreeAsync(scratch, ctx->stream);
+	if (cudaFreeAsync(scratch, ctx->stream) != cudaSuccess && st == PNOL_OK) { PNOL_SET_ERR(ctx, "normal_eq_blocks: freeing the block scratch failed"); st = PNOL_ERR_CUDA; }
 	if (st == PNOL_ERR_CUDA && ctx->err.empty()) PNOL_SET_ERR(ctx, "normal_eq_blocks: CUDA error in the block loop");
 	return st;
 }
@@ -820,6 +821,25 @@ extern "C" int pnol_spd_solve(pnol_ctx * ctx, const double * A, const double * r
 	PNOL_CHECK(finish(ctx));
 	if (info) *info = inf;
 	if (inf != 0) { PNOL_SET_ERR(ctx, "spd_solve: pivot %d is not positive", inf); return PNOL_ERR_NOT_SPD; }
+	return PNOL_OK;
+}
+
+// general inverse (LU, partial pivoting): matrixInverse of the FD Hessian, Source/BFGS_bnd_linesearch_MPI_SW.cpp:51-59
+extern "C" int pnol_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info)
+{
+	if (!ctx) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, A && Ainv && n >= 1, "lu_inverse: bad arguments");
+	DevIn<double> dA; DevOut<double> dI;
+	PNOL_CHECK(dA.init(ctx, A, (size_t) n * n));
+	PNOL_CHECK(dI.init(ctx, Ainv, (size_t) n * n));
+	PNOL_CHECK(ws_reserve(ctx, 3, 64));
+	int * info_dev = (int *) ctx->ws[3];
+	PNOL_CHECK(launch_lu_inverse(ctx, dA.get(), n, dI.get(), info_dev));
+	PNOL_CHECK(dI.commit());
+	int inf = 0;
+	PNOL_CUDA(ctx, cudaMemcpyAsync(&inf, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	PNOL_CHECK(finish(ctx));
+	if (info) *info = inf;
 	return PNOL_OK;
 }
 

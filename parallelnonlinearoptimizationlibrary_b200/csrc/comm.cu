@@ -5,6 +5,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <mutex>
 
 namespace pnol {
 
@@ -21,21 +22,17 @@ struct NcclApi {
 	std::string why;
 };
 
-static NcclApi & nccl_api()
+static void nccl_api_load(NcclApi & api)
 {
-	static NcclApi api;
-	static bool tried = false;
-	if (tried) return api;
-	tried = true;
 	const char * names[] = {"libnccl.so.2", "libnccl.so"};
 	for (const char * nm : names) {
 		api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
 		if (api.handle) break;
 	}
-	if (!api.handle) { api.why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return api; }
+	if (!api.handle) { api.why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return; }
 #define PNOL_SYM(field, name)                                                        \
 	api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));      \
-	if (!api.field) { api.why = std::string("missing NCCL symbol ") + name; return api; }
+	if (!api.field) { api.why = std::string("missing NCCL symbol ") + name; return; }
 	PNOL_SYM(GetUniqueId, "ncclGetUniqueId");
 	PNOL_SYM(CommInitRank, "ncclCommInitRank");
 	PNOL_SYM(CommDestroy, "ncclCommDestroy");
@@ -45,6 +42,14 @@ static NcclApi & nccl_api()
 	PNOL_SYM(GetErrorString, "ncclGetErrorString");
 #undef PNOL_SYM
 	api.ok = true;
+}
+
+// loaded once per process, whichever thread / context asks first
+static NcclApi & nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] { nccl_api_load(api); });
 	return api;
 }
 
@@ -67,8 +72,9 @@ int comm_allreduce_dev(pnol_ctx * ctx, double * dev_buf, size_t count)
 
 int comm_allgather_dev(pnol_ctx * ctx, const double * send, double * recv, size_t count_per_rank)
 {
+	if (count_per_rank == 0) return PNOL_OK;
 	if (ctx->nranks <= 1) {
-		if (send != recv && count_per_rank)
+		if (send != recv)
 			PNOL_CUDA(ctx, cudaMemcpyAsync(recv, send, count_per_rank * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 		return PNOL_OK;
 	}
@@ -88,6 +94,7 @@ void comm_destroy(pnol_ctx * ctx)
 {
 	if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) ctx->comm);
 	ctx->comm = nullptr; ctx->nranks = 1; ctx->rank = 0;
+	ctx->local = false; ctx->comm_nranks = 1; ctx->comm_rank = 0;
 }
 
 } // namespace pnol
@@ -113,6 +120,10 @@ extern "C" int pnol_comm_init(pnol_ctx * ctx, const char id[PNOL_COMM_ID_BYTES],
 	NcclApi & api = nccl_api();
 	if (!api.ok) { PNOL_SET_ERR(ctx, "NCCL unavailable: %s", api.why.c_str()); return PNOL_ERR_COMM; }
 	PNOL_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (ctx->comm) {                                     // re-initialisation: the old communicator must not leak
+		PNOL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		comm_destroy(ctx);
+	}
 	ncclUniqueId uid;
 	memcpy(&uid, id, sizeof uid);
 	ncclComm_t comm;
@@ -120,7 +131,21 @@ extern "C" int pnol_comm_init(pnol_ctx * ctx, const char id[PNOL_COMM_ID_BYTES],
 	ctx->comm = (ncclComm *) comm;
 	ctx->nranks = nranks;
 	ctx->rank = rank;
+	ctx->local = false; ctx->comm_nranks = nranks; ctx->comm_rank = rank;
 	return PNOL_OK;
+}
+
+// Local (non-collective) mode. The reference's serial classes (BFGS, BFGS_Bnd, LevMarq, GeneticAlgorithm, SimplexSearch and the
+// non-MPI stencil members of Objective) never touch MPI, so a program may call them on one rank only. While local mode is on this
+// context behaves like a single-GPU context: no entry point issues a collective, a residual functor's rows are ALL the rows,
+// pnol_comm_rank / pnol_comm_size answer 0 / 1. Returns the previous setting (for nesting).
+extern "C" int pnol_comm_set_local(pnol_ctx * ctx, int on)
+{
+	if (!ctx) return 0;
+	const int prev = ctx->local ? 1 : 0;
+	if (on && !ctx->local) { ctx->local = true; ctx->nranks = 1; ctx->rank = 0; }
+	else if (!on && ctx->local) { ctx->local = false; ctx->nranks = ctx->comm_nranks; ctx->rank = ctx->comm_rank; }
+	return prev;
 }
 
 extern "C" int pnol_comm_rank(pnol_ctx * ctx) { return ctx ? ctx->rank : 0; }

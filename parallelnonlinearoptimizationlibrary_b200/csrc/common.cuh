@@ -50,6 +50,10 @@ struct pnol_ctx {
 	ncclComm * comm = nullptr;
 	int rank = 0;
 	int nranks = 1;
+	// local (non-collective) mode, pnol_comm_set_local: rank / nranks read 0 / 1 while it is on, the real values wait here
+	bool local = false;
+	int comm_rank = 0;
+	int comm_nranks = 1;
 
 	// timers
 	bool timers_on = false;
@@ -248,6 +252,7 @@ int syrk_plan_selftest(long long m, int n, int sm_count, int with_f);
 int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs);
 int launch_dgemm_nn(pnol_ctx * ctx, const double * A, const double * B, double * C, int M, int N, int K);
 int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev);
+int launch_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info_dev);
 int launch_matvec_neg(pnol_ctx * ctx, const double * D, const double * g, int n, double * p);
 int launch_hinv_rank2(pnol_ctx * ctx, double * D, const double * g, const double * s, int n);
 int launch_hinv_literal(pnol_ctx * ctx, double * D, const double * g, const double * s, int n);

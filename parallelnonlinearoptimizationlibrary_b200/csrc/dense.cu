@@ -270,6 +270,120 @@ int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n
 }
 
 // ---------------------------------------------------------------------------------------------------
+// General inverse by LU with partial pivoting: the reference inverts the forward-difference Hessian with `matrixInverse`
+// (Source/BFGS_bnd_linesearch_MPI_SW.cpp:51-59, BFGS_with_linesearch.cpp:35-41) and carries on with whatever comes back, also
+// when the Hessian is indefinite (away from a minimum that is the normal case). matrixInverse lives in the un-vendored utility
+// library; oracle/shim defines it as Doolittle LU with partial pivoting (first largest |entry| on ties) followed by one pair of
+// substitutions per unit vector. This kernel performs exactly those operations, each entry's updates in the same order
+// (k ascending, one rounding per multiply and per subtract, -fmad=false), so the result is the shim's bit for bit.
+// One CTA: n is small wherever an FD Hessian is affordable (3 n^2 / 2 objective evaluations).
+//   LU  (n x n, global, L2-resident) in/out: A on entry, the factors on exit;  piv (n ints);  Y (n x n scratch);  Ainv (n x n)
+//   info: 0, or k+1 when pivot k is exactly zero (the reference would divide by zero and go on with inf / NaN -- so do we)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kLuThreads = 1024;
+
+__global__ void __launch_bounds__(kLuThreads, 1)
+lu_inverse_kernel(double * __restrict__ LU, int n, int * __restrict__ piv, double * __restrict__ Y, double * __restrict__ Ainv,
+                  int * __restrict__ info)
+{
+	extern __shared__ double lu_sm[];
+	double * rowk = lu_sm;                                   // n: row k right of the diagonal
+	__shared__ double red_v[kLuThreads / 32];
+	__shared__ int red_i[kLuThreads / 32];
+	__shared__ int s_p;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	int first_zero = 0;
+	for (int i = tid; i < n; i += kLuThreads) piv[i] = i;
+	__syncthreads();
+	for (int k = 0; k < n; k++) {
+		// pivot: first row i >= k with the largest |LU[i][k]| (strict > in the reference's scan keeps the first)
+		double best = -1.0;
+		int bi = n;
+		for (int i = k + tid; i < n; i += kLuThreads) {
+			const double v = fabs(LU[(size_t) i * n + k]);
+			if (v > best) { best = v; bi = i; }              // i ascending per thread: the first of equal values is kept
+		}
+		// NaN entries never win a `>` comparison in the reference either (best starts at |LU[k][k]|; handled below)
+		for (int o = 16; o > 0; o >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+		}
+		if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+		__syncthreads();
+		if (warp == 0) {
+			best = lane < kLuThreads / 32 ? red_v[lane] : -1.0;
+			bi = lane < kLuThreads / 32 ? red_i[lane] : n;
+			for (int o = 16; o > 0; o >>= 1) {
+				const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+			}
+			if (lane == 0) {
+				// the reference starts from p = k, best = |LU[k][k]| and moves only on a strictly larger value: a NaN diagonal keeps p = k
+				const double dk = fabs(LU[(size_t) k * n + k]);
+				s_p = (dk != dk || bi >= n || !(best > dk)) ? k : bi;
+			}
+		}
+		__syncthreads();
+		const int p = s_p;
+		if (p != k) {
+			for (int j = tid; j < n; j += kLuThreads) {
+				const double a = LU[(size_t) p * n + j], b = LU[(size_t) k * n + j];
+				LU[(size_t) p * n + j] = b; LU[(size_t) k * n + j] = a;
+			}
+			if (tid == 0) { const int t = piv[p]; piv[p] = piv[k]; piv[k] = t; }
+		}
+		__syncthreads();
+		for (int j = k + tid; j < n; j += kLuThreads) rowk[j] = LU[(size_t) k * n + j];
+		__syncthreads();
+		const double d = rowk[k];
+		if (d == 0.0 && first_zero == 0) first_zero = k + 1;
+		// rows below: warp per row, lanes along the columns
+		for (int i = k + 1 + warp; i < n; i += kLuThreads / 32) {
+			double * r = LU + (size_t) i * n;
+			const double l = r[k] / d;
+			for (int j = k + 1 + lane; j < n; j += 32) r[j] = r[j] - l * rowk[j];
+			__syncwarp();
+			if (lane == 0) r[k] = l;
+		}
+		__syncthreads();
+	}
+	// columns of the inverse: thread c solves L y = P e_c, U x = y (sums in ascending k, as luBackSub)
+	for (int c = tid; c < n; c += kLuThreads) {
+		for (int i = 0; i < n; i++) {
+			double s = (piv[i] == c) ? 1.0 : 0.0;
+			const double * r = LU + (size_t) i * n;
+			for (int k = 0; k < i; k++) s = s - r[k] * Y[(size_t) k * n + c];
+			Y[(size_t) i * n + c] = s;
+		}
+		for (int i = n - 1; i >= 0; i--) {
+			double s = Y[(size_t) i * n + c];
+			const double * r = LU + (size_t) i * n;
+			for (int k = i + 1; k < n; k++) s = s - r[k] * Ainv[(size_t) k * n + c];
+			Ainv[(size_t) i * n + c] = s / r[i];
+		}
+	}
+	if (tid == 0) *info = first_zero;
+}
+
+int launch_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info_dev)
+{
+	PNOL_REQUIRE(ctx, n >= 1 && n <= 8192, "lu_inverse: n = %d outside [1, 8192]", n);
+	TimerScope ts(ctx, "lu_inverse");
+	const size_t nn = (size_t) n * n;
+	PNOL_CHECK(ws_reserve(ctx, 1, (2 * nn + (size_t) n + 8) * sizeof(double)));
+	double * LU = (double *) ctx->ws[1];
+	double * Y = LU + nn;
+	int * piv = (int *) (Y + nn);
+	PNOL_CUDA(ctx, cudaMemcpyAsync(LU, A, nn * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	const size_t smem = (size_t) n * sizeof(double);
+	PNOL_CUDA(ctx, cudaFuncSetAttribute(lu_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	PNOL_LAUNCH(ctx, lu_inverse_kernel, 1, kLuThreads, smem, LU, n, piv, Y, Ainv, info_dev);
+	return PNOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // a12: p = -D g    (Source/BFGS_bnd_linesearch_MPI_SW.cpp:143-144). One warp per row, coalesced row reads.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // BFGS_bnd_linesearch_MPI_SW.cpp -- BFGS_Bnd_MPI_SW: bounded BFGS, pooled strong-Wolfe line search, active-set
 // recursion. The host control flow follows Source/BFGS_bnd_linesearch_MPI_SW.cpp of the reference decision for
 // decision (iterates must match it); gradient stencils, p = -D g, the alpha pools and updateHessianInv are device work.

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // BFGS_with_bnd_linsearch_MPI.cpp -- BFGSBnd_MPI: box-bounded BFGS with the pooled secant line search and a one-level
 // active-set recursion. The host control flow follows Source/BFGS_with_bnd_linsearch_MPI.cpp of the
 // reference decision for decision (iterates must match it); the FD gradients, p = -D g, the alpha pools and

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // BFGS_with_linesearch.cpp -- BFGS::findMin, the strong-Wolfe cubic-interpolation line search, and the shared
 // inverse-Hessian machinery. Control flow follows Source/BFGS_with_linesearch.cpp of the reference; the gradient
 // stencil, p = -D g, every phi(alpha) evaluation and updateHessianInv run on the device through the C-ABI.
@@ -62,27 +64,22 @@ void InverseHessian::update( const vector<double> & g, const vector<double> & s 
 	rt.check( pnol_bfgs_update_hinv( rt.ctx(), D_.data(), g.data(), s.data(), n_, rt.hessianUpdateMode() ) );
 }
 
-// D = inverse of the forward-difference Hessian (Source/BFGS_with_linesearch.cpp:35-41). The inverse of the small
-// SPD-ish matrix is taken column by column with the device Cholesky solve; a non-SPD Hessian raises pnol::Error
-// (the reference's matrixInverse would return an indefinite D and the search direction would not be a descent one).
+// D = inverse of the forward-difference Hessian (Source/BFGS_with_linesearch.cpp:35-41, BFGS_bnd_linesearch_MPI_SW.cpp:51-59):
+// B from the FD stencil, then the reference's `matrixInverse` -- LU with partial pivoting, on the device (pnol_lu_inverse), ONE
+// factorisation and n pairs of substitutions. An indefinite Hessian (the normal case away from a minimum) is inverted like any
+// other and the run carries on with an indefinite D, exactly as the reference does.
 void InverseHessian::setFromInverseOfFDHessian( Objective * obj, vector<double> & X, double dXHess )
 {
 	Runtime & rt = Runtime::instance();
 	vector<double> dXH( n_, dXHess );
 	vector<vector<double> > B( n_, vector<double>( n_ ) );
 	obj->hessianApproximation( X, dXH, B );
-	vector<double> flat( (size_t) n_*n_ ), inv( (size_t) n_*n_ ), e( n_ ), col( n_ );
+	vector<double> flat( (size_t) n_*n_ );
 	for( int i = 0; i < n_; i++ ) for( int j = 0; j < n_; j++ ) flat[(size_t) i*n_ + j] = B[i][j];
 	DeviceArray Bd( flat.size() );
 	Bd.upload( flat.data(), flat.size() );
-	for( int j = 0; j < n_; j++ )
-	{
-		for( int i = 0; i < n_; i++ ) e[i] = (i == j) ? 1.0 : 0.0;
-		int info = 0;
-		rt.check( pnol_spd_solve( rt.ctx(), Bd.data(), e.data(), n_, col.data(), &info ) );
-		for( int i = 0; i < n_; i++ ) inv[(size_t) i*n_ + j] = col[i];
-	}
-	D_.upload( inv.data(), inv.size() );
+	int info = 0;
+	rt.check( pnol_lu_inverse( rt.ctx(), Bd.data(), n_, D_.data(), &info ) );
 }
 
 } // namespace pnol
@@ -153,6 +150,7 @@ double BFGS::lineSearchFDDerivative( double alpha, double phialpha, vector <doub
 // Source/BFGS_with_linesearch.cpp:12-139
 void BFGS::findMin( vector <double> & X, double & f0, double & fOpt )
 {
+	pnol::LocalScope serial;             // the serial class never touches the communicator (Source/BFGS_with_linesearch.cpp)
 	int Nparam = (int) X.size();
 	vector<double> Xprev( Nparam, 0 );
 	vector<double> dX( Nparam, dXGrad );

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // BFGS_with_linesearch_MPI.cpp -- BFGS_MPI: BFGS with the pooled secant line search of
 // Source/BFGS_with_linesearch_MPI.cpp. The pool of step lengths the reference spreads over MPI ranks
 // (evalAlphaPoolMPI, :163-223) is one batched kernel launch here.

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // Box_boundary_functions.cpp -- box-bound helpers (host arithmetic) behind the reference's names.
 #include "pnol/Box_boundary_functions.hpp"
 #include "pnol/Runtime.hpp"

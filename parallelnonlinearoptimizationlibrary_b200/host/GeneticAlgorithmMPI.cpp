@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // GeneticAlgorithmMPI.cpp -- host face of the device GA (Source/GeneticAlgorithmMPI.cpp, Source/GeneticAlgorithm.cpp).
 #include "pnol/GeneticAlgorithm.hpp"
 
@@ -9,15 +11,8 @@ namespace {
 
 pnol_stream_desc currentStream( int Npop )
 {
-	pnol::Runtime & rt = pnol::Runtime::instance();
-	if( rt.haveRandomStream() ) return rt.randomStream();
-	// srand((unsigned) time(0)) of the reference (Source/GeneticAlgorithmMPI.cpp:57): a clock-seeded counter stream.
 	// scale keeps round(u * Npop) < Npop, where the reference would index one past the end of its arrays (:138-140).
-	pnol_stream_desc s;
-	s.values = nullptr; s.n_values = 0;
-	s.seed = (uint64_t) std::chrono::system_clock::now().time_since_epoch().count();
-	s.scale = 1.0 - 1.0/(double) Npop;
-	return s;
+	return pnol::Runtime::instance().defaultStream( 1.0 - 1.0/(double) Npop );
 }
 
 void flatten( const vector<vector<double> > & A, vector<double> & flat )

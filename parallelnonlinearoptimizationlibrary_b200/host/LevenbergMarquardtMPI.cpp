@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // LevenbergMarquardtMPI.cpp -- LevMarqMPI::findMin / LevMarq::findMin: the control flow of
 // Source/LevenbergMarquardtMPI.cpp:12-173 (serial twin Source/LevenbergMarquardt.cpp:11-177) on the host, every
 // O(m) or O(n^2) statement as a kernel through the C-ABI. J, F and the trial F never leave the device.
@@ -114,6 +116,29 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 		print1DVector( X );
 		cout << "-----------------------------------------------------------------------------------" << endl << endl;
 	}
+}
+
+// The reference's findMin hands the FULL F0 / FOpt to every rank; under row sharding a rank only has its block (see the header).
+// This rebuilds the full vector: block lengths travel in one small all-reduce, the blocks in one all-gather of padded slots.
+void gatherResiduals( const vector <double> & local, vector <double> & full )
+{
+	Runtime & rt = Runtime::instance();
+	pnol_ctx * ctx = rt.ctx();
+	const int R = pnol_comm_size( ctx ), r = pnol_comm_rank( ctx );
+	if( R <= 1 ) { full = local; return; }
+	vector <double> lens( R, 0.0 );
+	lens[r] = (double) local.size();
+	rt.check( pnol_comm_allreduce_sum( ctx, lens.data(), (size_t) R ) );
+	size_t slot = 0, total = 0;
+	for( int k = 0; k < R; k++ ) { if( (size_t) lens[k] > slot ) slot = (size_t) lens[k]; total += (size_t) lens[k]; }
+	if( slot == 0 ) { full.clear(); return; }
+	vector <double> send( slot, 0.0 ), recv( slot*R, 0.0 );
+	for( size_t i = 0; i < local.size(); i++ ) send[i] = local[i];
+	rt.check( pnol_comm_allgather( ctx, send.data(), recv.data(), slot ) );
+	full.resize( total );
+	size_t at = 0;
+	for( int k = 0; k < R; k++ )
+		for( size_t i = 0; i < (size_t) lens[k]; i++ ) full[at++] = recv[(size_t) k*slot + i];
 }
 
 } // namespace pnol

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // PNOL_Objective.cpp -- the derivative stencils of the plugin API (Source/PNOL_Objective.cpp of the reference),
 // each a thin host call into the C-ABI: the N+1 (or n+1 residual-vector) evaluations run as CUDA kernels.
 #include "pnol/PNOL_Objective.hpp"
@@ -20,20 +22,22 @@ pnol_functor * MultiObjective::requireFunctor( const char * who )
 	return f;
 }
 
-// Source/PNOL_Objective.cpp:12-34
+// Source/PNOL_Objective.cpp:12-34. The serial stencil never touches MPI in the reference, so it runs in local mode here: no
+// collective, all coordinates on this GPU, whatever communicator the context carries.
 void Objective::gradientApproximation( vector <double> & X, vector <double> & dX, vector <double> & dFdX )
+{
+	pnol::LocalScope serial;
+	gradientApproximationMPI( X, dX, dFdX );
+}
+
+// Source/PNOL_Objective.cpp:88-159: the reference deals the N+1 evaluations out to MPI ranks and sums; the values are
+// the same as the serial stencil. With a communicator attached the C-ABI splits the coordinates across GPUs (collective call).
+void Objective::gradientApproximationMPI( vector <double> & X, vector <double> & dX, vector <double> & dFdX )
 {
 	pnol::Runtime & rt = pnol::Runtime::instance();
 	pnol_functor * f = requireFunctor( "Objective::gradientApproximation" );
 	rt.check( pnol_fd_gradient( rt.ctx(), f, X.data(), dX.data(), (int) X.size(), dFdX.data(), nullptr ) );
 	noteDeviceEvaluations( (long long) X.size() + 1 );                        // N + 1 points (:19-32)
-}
-
-// Source/PNOL_Objective.cpp:88-159: the reference deals the N+1 evaluations out to MPI ranks and sums; the values are
-// the same as the serial stencil. With a communicator attached the C-ABI splits the coordinates across GPUs.
-void Objective::gradientApproximationMPI( vector <double> & X, vector <double> & dX, vector <double> & dFdX )
-{
-	gradientApproximation( X, dX, dFdX );
 }
 
 // Source/PNOL_Objective.cpp:38-85
@@ -64,8 +68,16 @@ double Objective::objEvalRecur( vector <double> & Xrecur, vector <double> & cons
 	return objEval( X );
 }
 
-// Source/PNOL_Objective.cpp:337-360
+// Source/PNOL_Objective.cpp:337-360 (serial: local mode, see gradientApproximation)
 void Objective::gradientApproximationRecur( vector <double> & X, vector <double> & dX, vector <double> & dFdX,
+		vector <double> & constantX, vector<bool> & constantIndicator )
+{
+	pnol::LocalScope serial;
+	gradientApproximationMPIRecur( X, dX, dFdX, constantX, constantIndicator );
+}
+
+// Source/PNOL_Objective.cpp:366-459 (coordinates split across the communicator's GPUs: collective call)
+void Objective::gradientApproximationMPIRecur( vector <double> & X, vector <double> & dX, vector <double> & dFdX,
 		vector <double> & constantX, vector<bool> & constantIndicator )
 {
 	pnol::Runtime & rt = pnol::Runtime::instance();
@@ -75,13 +87,6 @@ void Objective::gradientApproximationRecur( vector <double> & X, vector <double>
 	rt.check( pnol_fd_gradient_recur( rt.ctx(), f, X.data(), dX.data(), (int) X.size(), constantX.data(), ind.data(),
 			(int) constantX.size(), dFdX.data(), nullptr ) );
 	noteDeviceEvaluations( (long long) X.size() + 1 );                        // (:345-358)
-}
-
-// Source/PNOL_Objective.cpp:366-459
-void Objective::gradientApproximationMPIRecur( vector <double> & X, vector <double> & dX, vector <double> & dFdX,
-		vector <double> & constantX, vector<bool> & constantIndicator )
-{
-	gradientApproximationRecur( X, dX, dFdX, constantX, constantIndicator );
 }
 
 // Source/PNOL_Objective.cpp:165-197. The drop-in signature returns J as Ndata host rows; the device produces it

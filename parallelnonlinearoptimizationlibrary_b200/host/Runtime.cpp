@@ -1,6 +1,9 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // Runtime.cpp -- pnol::Runtime, DeviceFunctor, DeviceArray (host C++ above the C-ABI).
 #include "pnol/Runtime.hpp"
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -53,6 +56,26 @@ void Runtime::reset()
 	if (ctx_ && owned_) pnol_ctx_destroy(ctx_);
 	ctx_ = nullptr;
 	owned_ = false;
+}
+
+pnol_stream_desc Runtime::defaultStream(double scale)
+{
+	if (haveStream_) return stream_;
+	// one clock seed per process, drawn at the first use (the reference re-seeds with srand(time(0)) in every findMin call)
+	static const uint64_t clockSeed = (uint64_t) std::chrono::system_clock::now().time_since_epoch().count();
+	uint64_t seed = clockSeed;
+	pnol_ctx * c = ctx();
+	if (pnol_comm_size(c) > 1) {
+		// rank 0's seed for everybody: two doubles carrying 32 bits each (exact), one broadcast
+		double halves[2] = {(double) (uint32_t) (seed >> 32), (double) (uint32_t) (seed & 0xFFFFFFFFu)};
+		check(pnol_comm_broadcast(c, halves, 2, 0));
+		seed = ((uint64_t) (uint32_t) halves[0] << 32) | (uint64_t) (uint32_t) halves[1];
+	}
+	pnol_stream_desc s;
+	s.values = nullptr; s.n_values = 0;
+	s.seed = seed;
+	s.scale = scale;
+	return s;
 }
 
 void Runtime::check(int status) const

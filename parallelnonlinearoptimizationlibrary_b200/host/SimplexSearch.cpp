@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // SimplexSearch.cpp -- the Nelder-Mead controller of Source/SimplexSearch.cpp:13-349 on the host; every objective evaluation is a
 // pnol_eval_batch on the objective's device twin (one point, or all n + 1 vertices in one launch).
 #include "pnol/SimplexSearch.hpp"
@@ -22,11 +24,9 @@ struct SimplexStore {
 	}
 };
 
-double nextUniform( pnol::Runtime & rt, unsigned long long & pos )
+// the k-th draw of the stream `s` (explicit array or counter stream)
+double nextUniform( const pnol_stream_desc & s, unsigned long long & pos )
 {
-	if( !rt.haveRandomStream() )
-		throw pnol::Error( PNOL_ERR_STREAM, "SimplexSearch::findMin: no random stream set (Runtime::setRandomStream); the start simplex needs n*n draws" );
-	const pnol_stream_desc & s = rt.randomStream();
 	double u;
 	if( s.values )
 	{
@@ -91,10 +91,12 @@ void SimplexSearch::findMin( vector <double> & X, double & f0, double & fOpt )
 
 	// first vertex = the start point, the others = start point + uniform noise (:47-65)
 	for( int j = 0; j < Ndim; j++ ) xvec[0][j] = X[j];
+	// without an explicit stream the reference seeds from the clock (srand((unsigned) time(0)), :57): so does the default stream
+	const pnol_stream_desc stream = rt.defaultStream( 1.0 );
 	unsigned long long pos = 0;
 	for( int i = 1; i < Nsimplex; i++ )
 		for( int j = 0; j < Ndim; j++ )
-			xvec[i][j] = xvec[0][j] + initRandMax * (nextUniform( rt, pos ) - 0.5) * 2.0;
+			xvec[i][j] = xvec[0][j] + initRandMax * (nextUniform( stream, pos ) - 0.5) * 2.0;
 	streamPos_ = pos;
 
 	// evaluate and sort the initial set (:67-73)

@@ -1,3 +1,5 @@
+/* This Source Code Form is subject to the terms of the Mozilla Public License, v. 2.0 (LICENSE at the repository root).
+ * It mirrors the interface / host control flow of briandaniel/ParallelNonlinearOptimizationLibrary (MPL-2.0); see NOTICE. */
 // host_capi.cpp -- C entry points that drive the host C++ plugin classes (include/pnol/*.hpp) so that Python tests and
 // bench.py can exercise exactly what a C++ user of the reference API would call (LevMarqMPI::findMin, BFGS*::findMin*,
 // GeneticAlgorithmMPI::findMinBnd, Objective::gradientApproximation ...). Not part of the drop-in C-ABI
@@ -69,6 +71,7 @@ int pnolhost_set_stream( const double * values, unsigned long long n_values, uns
 	pnol::Runtime::instance().setRandomStream( s );
 	return PNOL_OK;
 }
+int pnolhost_clear_stream() { pnol::Runtime::instance().clearRandomStream(); return PNOL_OK; }
 
 // LevMarqMPI::findMin (serial != 0: LevMarq) on the Lorentz-sum model with caller data. report[6] = iterations,
 // accepted, rejected, chiSq, lambda, xdiff2Norm

@@ -93,6 +93,13 @@ def set_stream(values=None, seed=0, scale=1.0):
         lib().pnolhost_set_stream(C.c_void_p(0), C.c_ulonglong(0), C.c_ulonglong(seed), C.c_double(scale))
 
 
+def clear_stream():
+    """forget the explicit stream: the algorithms fall back to the clock-seeded default stream (seed drawn on rank 0, broadcast)"""
+    global _stream_keep
+    _stream_keep = None
+    lib().pnolhost_clear_stream()
+
+
 def lm_lorentz(t, y, w, x0, lambda0=0.001, factor=10.0, dxgrad=1e-7, maxiter=10, xmindiff=0.0, serial=False, X=None, F0=None,
                F=None):
     """LevMarqMPI::findMin (LevMarq when serial) on LorentzSumObjective(t, y, w). t/y/F0/F may be numpy arrays or raw host

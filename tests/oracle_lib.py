@@ -148,6 +148,19 @@ def lm(f, x0, lambda0=0.001, factor=10.0, dxgrad=1e-6, maxiter=100, xmindiff=1e-
     return dict(X=X, F0=F0, F=F, iters=it, chisq=chisq.value, lam=lam.value, trace=trace)
 
 
+def lm_mt(f, x0, lambda0=0.001, factor=10.0, dxgrad=1e-6, maxiter=100, xmindiff=1e-6, want_trace=False, threads=None):
+    """oracle_lm with the loops re-nested and dealt to host threads (oracle/pnol_oracle_mt.cpp): the same bits, at full BASELINE sizes"""
+    X = f64(x0).copy()
+    n = X.size
+    F0, F = np.empty(f.m), np.empty(f.m)
+    chisq, lam = C.c_double(), C.c_double()
+    trace = np.full((maxiter + 1, n + 2), np.nan) if want_trace else None
+    threads = threads or os.cpu_count() or 1
+    it = lib().oracle_lm_mt(*f.args(), _p(X), C.c_int(n), C.c_double(lambda0), C.c_double(factor), C.c_double(dxgrad),
+                            C.c_int(maxiter), C.c_double(xmindiff), _p(F0), _p(F), C.byref(chisq), C.byref(lam), _p(trace), C.c_int(threads))
+    return dict(X=X, F0=F0, F=F, iters=it, chisq=chisq.value, lam=lam.value, trace=trace)
+
+
 def update_hinv(D, g, s):
     D = f64(D).copy()
     g, s = f64(g), f64(s)

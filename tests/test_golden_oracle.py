@@ -158,3 +158,36 @@ def test_alpha_pool_oracle_against_the_committed_reference_outputs():
             r = M.run_reference(c, nprocs=2)
             assert np.array_equal(r["phi"], G2[name + "/phi"]) and np.array_equal(r["dphi"], G2[name + "/dphi"], equal_nan=True)
     assert np.all(G2["rosenbrock6_overflow/phi"] == 1e10)
+
+
+# ---- BASELINE.json shapes (tests/golden/baseline_lm_golden.npz, made by tests/golden/make_baseline_lm_golden.py) ----
+GB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "baseline_lm_golden.npz"))
+
+
+@pytest.mark.parametrize("K,m,iters", [(8, 3000, 8), (32, 1500, 5), (128, 300, 3)])
+def test_threaded_lm_restatement_equals_the_sequential_one(K, m, iters):
+    # oracle_lm_mt (loops re-nested, rows / bands of J^T J dealt to threads) must give oracle_lm's bits at any thread count
+    from parallelnonlinearoptimizationlibrary_b200 import problems
+    pr = problems.lorentz_problem(m, K)
+    f = O.OFunctor(103, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    a = O.lm(f, pr["x0"], 0.001, 10.0, 1e-7, iters, 0.0, want_trace=True)
+    for threads in (1, 3, 8):
+        b = O.lm_mt(f, pr["x0"], 0.001, 10.0, 1e-7, iters, 0.0, want_trace=True, threads=threads)
+        assert a["iters"] == b["iters"] and a["chisq"] == b["chisq"] and a["lam"] == b["lam"]
+        assert np.array_equal(a["X"], b["X"]) and np.array_equal(a["F"], b["F"]) and np.array_equal(a["F0"], b["F0"])
+        assert np.array_equal(a["trace"], b["trace"], equal_nan=True)
+
+
+@pytest.mark.parametrize("case", ["cfg2_it6", "cfg2_to_stop", "lm_K128"])
+def test_baseline_shape_lm_golden_is_what_the_oracle_produces(case):
+    # cfg2 at FULL size (m = 100k, n = 16) and n = 256 (K = 128): the committed outputs of the verbatim reference, bit for bit
+    from parallelnonlinearoptimizationlibrary_b200 import problems
+    q = lambda k: GB["%s/%s" % (case, k)]      # noqa: E731
+    pr = problems.lorentz_problem(int(q("m")), int(q("K")))
+    f = O.OFunctor(103, (pr["w"],), (), (pr["t"], pr["y"]), pr["m"])
+    w = O.lm_mt(f, pr["x0"], float(q("lambda0")), float(q("factor")), float(q("dxgrad")), int(q("maxiter")), float(q("xmindiff")))
+    assert w["iters"] == int(q("iters")) and np.array_equal(w["X"], q("X")) and w["chisq"] == float(q("chisq"))
+    if case == "lm_K128":
+        assert np.array_equal(w["F"], q("F")) and np.array_equal(w["F0"], q("F0"))
+    else:
+        assert np.array_equal(w["F"][::100], q("F_every100")) and np.array_equal(w["F0"][::100], q("F0_every100"))

@@ -45,3 +45,10 @@ def test_simplex_search_needs_a_stream_and_a_device_twin(host):
     host.set_stream(values=np.full(3, 0.5))
     with pytest.raises(Exception):
         host.simplex("rosenbrock", np.full(4, 1.0), maxiter=5)
+
+
+def test_simplex_search_self_seeds_like_the_reference(host):
+    # no stream given: the reference seeds from the clock (Source/SimplexSearch.cpp:57); unmodified driver code must run
+    host.clear_stream()
+    r = host.simplex("booth", np.array([0.0, 0.0]), maxiter=4000, xmindiff=1e-10)
+    assert np.allclose(r["X"], [1.0, 3.0], atol=1e-4) and r["stream_pos"] == 4
