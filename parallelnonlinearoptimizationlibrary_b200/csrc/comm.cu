@@ -83,6 +83,18 @@ int comm_allgather_dev(pnol_ctx * ctx, const double * send, double * recv, size_
 	return PNOL_OK;
 }
 
+int comm_allgather_bytes_dev(pnol_ctx * ctx, const void * send, void * recv, size_t bytes_per_rank)
+{
+	if (bytes_per_rank == 0) return PNOL_OK;
+	if (ctx->nranks <= 1) {
+		if (send != recv) PNOL_CUDA(ctx, cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+		return PNOL_OK;
+	}
+	TimerScope ts(ctx, "allgather");
+	PNOL_NCCL(ctx, nccl_api().AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t) ctx->comm, ctx->stream));
+	return PNOL_OK;
+}
+
 int comm_broadcast_dev(pnol_ctx * ctx, double * buf, size_t count, int root)
 {
 	if (ctx->nranks <= 1 || count == 0) return PNOL_OK;

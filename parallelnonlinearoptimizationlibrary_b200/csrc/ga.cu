@@ -16,36 +16,13 @@
 //   * bounds     : out-of-box genes take one draw each in row-major order (prefix sum over per-row counts);
 //   * popSort    : stable LSD radix sort of the objective values (== repeated first-minimum extraction).
 // Integer / index work is bit-exact against the oracle by construction; see tests/test_gpu_ga.py.
-#include "common.cuh"
+#include "ga_common.cuh"
 
 #include <math.h>
 #include <algorithm>
 #include <utility>
 
 namespace pnol {
-
-// ---------------------------------------------------------------------------------------------------
-// random stream on the device
-// ---------------------------------------------------------------------------------------------------
-struct StreamDev {
-	const double * values;      // explicit stream (device copy) or nullptr
-	unsigned long long n_values;
-	unsigned long long seed;
-	double scale;
-	int * exhausted;            // set to 1 when an explicit stream is read past its end
-	__device__ __forceinline__ double u(unsigned long long k) const
-	{
-		if (values) {
-			if (k >= n_values) { *exhausted = 1; return 0.0; }
-			return values[k];
-		}
-		unsigned long long z = seed + (k + 1ULL) * 0x9E3779B97F4A7C15ULL;
-		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-		z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-		z = z ^ (z >> 31);
-		return ((double) (z >> 11) * (1.0 / 9007199254740992.0)) * scale;
-	}
-};
 
 // one selection trial at stream position q: index = round(u(q) * Npop), accepted iff index != 0 (the reference's
 // while(index == 0) loop never keeps 0), index < Npop (the reference reads out of bounds there) and
@@ -62,7 +39,6 @@ __device__ __forceinline__ int trial_index(const StreamDev & st, unsigned long l
 // ---------------------------------------------------------------------------------------------------
 // exclusive prefix sum of unsigned ints (three kernels, deterministic)
 // ---------------------------------------------------------------------------------------------------
-constexpr int kScanTile = 2048;      // elements per block (256 threads x 8)
 
 __global__ void __launch_bounds__(256)
 scan_reduce_kernel(const unsigned * __restrict__ in, long long n, unsigned long long * __restrict__ block_sums)
@@ -151,14 +127,6 @@ static int exclusive_scan_u32(pnol_ctx * ctx, const unsigned * in, long long n, 
 // ---------------------------------------------------------------------------------------------------
 // stable LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits; passes whose digit is constant are skipped
 // ---------------------------------------------------------------------------------------------------
-constexpr int kSortTile = 2048;      // keys per block: 8 warps x 8 rounds x 32 lanes
-constexpr int kSortWarps = 8;
-
-__device__ __forceinline__ unsigned long long double_to_key(double d)
-{
-	unsigned long long b = (unsigned long long) __double_as_longlong(d);
-	return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
-}
 
 // counts[pass][digit][block] for every pass in ONE read of the keys
 __global__ void __launch_bounds__(256)
@@ -250,41 +218,6 @@ sort_scatter_kernel(const unsigned long long * __restrict__ keys_in, const unsig
 		}
 	}
 }
-
-struct SortScratch {
-	unsigned long long * keys_alt;
-	unsigned * vals_alt;
-	unsigned * counts;              // [8][256][nblocks]
-	unsigned long long * offsets;   // [256][nblocks]
-	unsigned long long * scan_tmp;
-	int * skip;                     // [8]
-	static size_t bytes(long long n)
-	{
-		long long nb = (n + kSortTile - 1) / kSortTile;
-		if (nb < 1) nb = 1;
-		size_t s = 0;
-		s += (size_t) n * 8 + 256;                 // keys_alt
-		s += (size_t) n * 4 + 256;                 // vals_alt
-		s += (size_t) 8 * 256 * nb * 4 + 256;      // counts
-		s += (size_t) 256 * nb * 8 + 256;          // offsets
-		s += (size_t) ((256 * nb + kScanTile - 1) / kScanTile + 1) * 8 + 256;
-		s += 256;
-		return s;
-	}
-	void carve(void * base, long long n)
-	{
-		long long nb = (n + kSortTile - 1) / kSortTile;
-		if (nb < 1) nb = 1;
-		unsigned char * p = (unsigned char *) base;
-		auto take = [&](size_t b) { void * r = p; p += (b + 255) & ~(size_t) 255; return r; };
-		keys_alt = (unsigned long long *) take((size_t) n * 8);
-		vals_alt = (unsigned *) take((size_t) n * 4);
-		counts = (unsigned *) take((size_t) 8 * 256 * nb * 4);
-		offsets = (unsigned long long *) take((size_t) 256 * nb * 8);
-		scan_tmp = (unsigned long long *) take((size_t) ((256 * nb + kScanTile - 1) / kScanTile + 1) * 8);
-		skip = (int *) take(64);
-	}
-};
 
 // sorts (keys, vals) in place (result ends in the given arrays); stable
 static int radix_sort_pairs(pnol_ctx * ctx, unsigned long long * keys, unsigned * vals, long long n, SortScratch & sc)
@@ -673,36 +606,6 @@ using namespace pnol;
 // ---------------------------------------------------------------------------------------------------
 // state object
 // ---------------------------------------------------------------------------------------------------
-struct pnol_ga {
-	pnol_ctx * ctx;
-	const pnol_functor * f;
-	pnol_ga_params prm;
-	int n;
-	int nelite, nelmut, ncross, nrand;
-	// device state
-	double * Xpop, * Xnew, * F, * Fnew, * fitness, * lb, * ub, * x0;
-	unsigned char * indicator;
-	int * cross_idx, * mut_idx, * elite_idx;
-	long long * mut_pos;
-	double * stream_values;
-	int * exhausted;
-	// scratch
-	void * sort_mem; SortScratch sort;
-	unsigned long long * keys; unsigned * perm;
-	unsigned * u32a; unsigned long long * u64a; unsigned long long * scan_tmp; unsigned long long * total_dev;
-	long long * ll_dev;
-	// mutation tables (grown on demand)
-	void * mut_mem; size_t mut_bytes;
-	double * gather = nullptr;           // all-gather buffer of the sharded fitness sweep (multi-GPU)
-	// host state
-	pnol_stream_desc stream;
-	uint64_t pos;
-	int generation, n_static, stopped;
-	double f_best_prev, f_best;
-	double accept_rate;
-	std::vector<void *> owned;
-};
-
 static StreamDev ga_stream_dev(pnol_ga * ga)
 {
 	StreamDev st;
@@ -753,6 +656,7 @@ extern "C" void pnol_ga_destroy(pnol_ga * ga)
 {
 	if (!ga) return;
 	cudaStreamSynchronize(ga->ctx->stream);
+	ga_pipe_destroy(ga);
 	for (void * p : ga->owned) cudaFree(p);
 	if (ga->mut_mem) cudaFree(ga->mut_mem);
 	delete ga;
@@ -821,6 +725,11 @@ extern "C" int pnol_ga_create(pnol_ctx * ctx, const pnol_functor * f, const pnol
 	cudaMemcpyAsync(ga->ub, xub, n * sizeof(double), cudaMemcpyDefault, ctx->stream);
 	cudaMemsetAsync(ga->exhausted, 0, 16, ctx->stream);
 	GA_TRY(finish(ctx));
+	// the fused generation pipeline (ga_pipeline.cu) unless PNOL_GA_LEGACY=1 asks for the stage-by-stage generation (A/B runs)
+	{
+		const char * e = getenv("PNOL_GA_LEGACY");
+		if (!(e && atoi(e) != 0)) GA_TRY(ga_pipe_create(ga));
+	}
 #undef GA_TRY
 	*out = ga;
 	return PNOL_OK;
@@ -928,6 +837,7 @@ extern "C" int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out)
 	PNOL_CHECK(ga_check_stream(ga));
 	ga->f_best_prev = fb; ga->f_best = fb;
 	if (f0_out) *f0_out = f0;
+	if (ga->pipe) PNOL_CHECK(ga_pipe_reset(ga));
 	return PNOL_OK;
 }
 
@@ -946,6 +856,7 @@ extern "C" int pnol_ga_generation(pnol_ga * ga)
 	if (!ga) return PNOL_ERR_INVALID;
 	pnol_ctx * ctx = ga->ctx;
 	if (ga->stopped || ga->generation >= ga->prm.max_generations) return PNOL_OK;
+	if (ga->pipe) return ga_pipe_generation(ga);
 	const int Npop = ga->prm.npop, n = ga->n;
 	const int Nelite = ga->nelite, Ncross = ga->ncross, Nrand = ga->nrand, NeliteMut = ga->nelmut;
 	StreamDev st = ga_stream_dev(ga);
@@ -1099,6 +1010,7 @@ extern "C" int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * s)
 extern "C" int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F)
 {
 	if (!ga) return PNOL_ERR_INVALID;
+	if (ga->pipe) return ga_pipe_get_population(ga, xpop, F);
 	pnol_ctx * ctx = ga->ctx;
 	if (xpop) PNOL_CUDA(ctx, cudaMemcpyAsync(xpop, ga->Xpop, (size_t) ga->prm.npop * ga->n * sizeof(double), cudaMemcpyDefault, ctx->stream));
 	if (F) PNOL_CUDA(ctx, cudaMemcpyAsync(F, ga->F, (size_t) ga->prm.npop * sizeof(double), cudaMemcpyDefault, ctx->stream));
@@ -1108,6 +1020,7 @@ extern "C" int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F)
 extern "C" int pnol_ga_get_indices(pnol_ga * ga, int * cross_idx, int * mut_idx, int * elite_idx)
 {
 	if (!ga) return PNOL_ERR_INVALID;
+	if (ga->pipe) return ga_pipe_get_indices(ga, cross_idx, mut_idx, elite_idx);
 	pnol_ctx * ctx = ga->ctx;
 	if (cross_idx) PNOL_CUDA(ctx, cudaMemcpyAsync(cross_idx, ga->cross_idx, (size_t) ga->ncross * ga->n * sizeof(int), cudaMemcpyDefault, ctx->stream));
 	if (mut_idx) PNOL_CUDA(ctx, cudaMemcpyAsync(mut_idx, ga->mut_idx, (size_t) ga->nrand * sizeof(int), cudaMemcpyDefault, ctx->stream));

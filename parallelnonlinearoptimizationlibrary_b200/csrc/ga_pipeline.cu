@@ -1,0 +1,1267 @@
+// ga_pipeline.cu -- one generation of GeneticAlgorithmMPI::findMinBnd (Source/GeneticAlgorithmMPI.cpp:87-249) as a fused,
+// sync-free kernel pipeline: every stage reads the stream position it starts from out of a status block in device memory, so the
+// host enqueues the whole generation and synchronises ONCE at its end to read that block (stream position, best objective, error
+// bits). Bit-exact with the stage-by-stage generation of ga.cu and with the oracle (tests/test_gpu_ga.py).
+//
+// What changed against the stage-by-stage generation (2.25 ms at 1M x 32, ~105 launches, 8 host round trips):
+//   * the population is never physically sorted. Rows stay where the generation that made them wrote them ("child order");
+//     `perm` maps sorted position -> row. Parents are fetched through perm (they are random accesses anyway), so popSort's
+//     gather of 256 MB in and 256 MB out per generation is gone; only pnol_ga_get_population materialises the sorted rows;
+//   * crossover (:128-153): ONE kernel. Trials are evaluated once, accepted trials are ranked by a chained ("decoupled
+//     look-back") prefix sum over ticketed tiles, and the tile that knows its ranks gathers the parent genes and writes the
+//     children (three kernels + a host-driven batch loop before);
+//   * mutation (:159-190): the sequential parser state at a block boundary is the offset of the next trial start; every CTA
+//     tabulates offset -> (exit offset, children) for its sub-blocks, one small kernel composes the CTA tables, a third emits the
+//     children of every sub-block. The window is sized from the measured acceptance rate; a window that turns out short sets an
+//     error bit and the generation is redone with a longer one (the old population is untouched until the generation commits);
+//   * child writers compute the row hash and the out-of-box gene count of the duplicate / bounds checks while they hold the row;
+//   * duplicates (GeneticAlgorithm.cpp:313-344): "row i equals a LATER row" through an open-addressing table keyed by the row hash
+//     that keeps the largest row index per hash; candidates are compared exactly, a hash collision without equality goes to an
+//     exhaustive scan (never seen, but exact);
+//   * bounds repair (:347-365) and duplicate replacement take their draws at positions from ONE packed prefix sum;
+//   * popSort (:370-412): stable LSD radix sort of (key(F), row) in ONE cooperative kernel (grid-wide barriers between the
+//     histogram and scatter phases of the passes, constant digits skipped on the device);
+//   * several GPUs: rank r creates, repairs and evaluates child rows [r per, (r+1) per) only; parents are read from the owner's
+//     memory over NVLink (CUDA IPC mappings), or from a local replica refreshed by an all-gather when peer mappings are
+//     unavailable. Row hashes / box counts and objective values are all-gathered (two small collectives per generation).
+#include "ga_common.cuh"
+
+#include <cooperative_groups.h>
+#include <math.h>
+#include <algorithm>
+
+namespace cg = cooperative_groups;
+
+namespace pnol {
+
+// error bits of GaDevStatus::error
+enum { kGaErrDegenerate = 1, kGaErrCrossWindow = 2, kGaErrMutWindow = 4, kGaErrStream = 8 };
+
+// device-resident bookkeeping of one generation
+struct GaDevStatus {
+	unsigned long long pos0;            // stream position at the start of the generation
+	long long cross_last_trial;         // trial whose acceptance completed the crossover children (-1: no crossover)
+	long long mut_last_q;               // stream offset (from the start of the mutation stage) of the last child's accepted trial
+	long long mut_children;             // children the mutation window reaches
+	unsigned long long pos_elite;       // start of the elite-mutation stage (set by the mutation emit kernel)
+	unsigned long long ndup;            // duplicate rows replaced
+	unsigned long long noob;            // out-of-box genes repaired
+	unsigned long long pos_end;         // stream position after the generation
+	double fbest;
+	double max_fitness;
+	int error;
+	unsigned int cross_ticket;          // tiles handed out by the crossover kernel
+	int cross_done;
+	unsigned int nsuspect;              // rows whose hash matched a later row that is NOT equal (exhaustive check)
+	int sort_result_in_alt;             // which buffer the radix sort ended in
+	int pad;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long * p)
+{
+	return *((const volatile unsigned long long *) p);
+}
+
+// index of the selection trial at stream position q (Source/GeneticAlgorithmMPI.cpp:134-144): round(u(q) Npop); 0 = rejected.
+// ratio[k] = fitness[k] / maxFitness is tabulated once per generation (the same IEEE division, 1M instead of ~40M times)
+__device__ __forceinline__ int pipe_trial(const StreamDev & st, unsigned long long q, const double * __restrict__ ratio, int Npop)
+{
+	const int randomIndex = (int) round(st.u(q) * Npop);
+	const double selectValue = st.u(q + 1);
+	if (randomIndex <= 0 || randomIndex >= Npop) return 0;
+	return (selectValue <= ratio[randomIndex]) ? randomIndex : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 0. fitness, acceptance ratios, elite objective values, status reset   (:101-124)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ga_prep_kernel(const double * __restrict__ Fs, int Npop, int Nelite, double * __restrict__ fitness, double * __restrict__ ratio,
+               double * __restrict__ Fchild, GaDevStatus * __restrict__ S, unsigned long long pos0)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const double fw = Fs[Npop - 1];
+	const double d0 = fw - Fs[0];
+	const double maxFitness = d0 * d0;                                     // fitness[0]
+	if (k < Npop) {
+		const double d = fw - Fs[k];
+		const double fit = d * d;                                          // pow(F[Npop-1] - F[k], 2)
+		fitness[k] = fit;
+		ratio[k] = fit / maxFitness;
+		if (k < Nelite) Fchild[k] = Fs[k];
+	}
+	if (k == 0) {
+		S->pos0 = pos0; S->cross_last_trial = -1; S->mut_last_q = -1; S->mut_children = 0; S->pos_elite = 0;
+		S->ndup = 0; S->noob = 0; S->pos_end = 0; S->fbest = 0; S->max_fitness = maxFitness;
+		// every trial would compare against NaN / inf: the reference spins forever in its while loops
+		S->error = (!(maxFitness > 0) || isinf(maxFitness)) ? kGaErrDegenerate : 0;
+		S->cross_ticket = 0; S->cross_done = 0; S->nsuspect = 0; S->sort_result_in_alt = 0;
+	}
+}
+
+// elite rows (:108-118): child row k = sorted row k, for the rows this rank owns; the row hash travels with the row
+__global__ void __launch_bounds__(256)
+ga_elite_copy_kernel(RowTable cur, const unsigned * __restrict__ perm, const unsigned long long * __restrict__ hash_cur, long long lo,
+                     long long hi, int n, double * __restrict__ Xloc, unsigned long long * __restrict__ hash_new,
+                     unsigned * __restrict__ bcount)
+{
+	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (row >= hi) return;
+	const unsigned from = perm[row];
+	const double * s = cur.row(from);
+	double * d = Xloc + (row - lo) * n;
+	for (int j = lane; j < n; j += 32) d[j] = __ldcg(s + j);
+	if (lane == 0) { hash_new[row] = hash_cur[from]; bcount[row] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 1. crossover (:128-153) in one kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int kCrossThreads = 256;
+constexpr int kCrossPer = 16;
+constexpr int kCrossTile = kCrossThreads * kCrossPer;          // trials per tile
+constexpr unsigned long long kDescAgg = 1ULL << 62, kDescPre = 2ULL << 62, kDescMask = (1ULL << 62) - 1;
+
+__global__ void __launch_bounds__(kCrossThreads)
+ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __restrict__ ratio, int Npop, long long need,
+                unsigned max_tiles, unsigned long long * __restrict__ desc, int * __restrict__ sel, RowTable cur,
+                const unsigned * __restrict__ perm, int n, double * __restrict__ Xloc, long long own_lo, long long own_hi,
+                long long row0)
+{
+	// own_lo / own_hi: child rows of the whole new population this rank owns; crossover child c is row row0 + c
+	__shared__ int s_idx[kCrossTile];
+	__shared__ unsigned s_warp[kCrossThreads / 32];
+	__shared__ unsigned s_tile;
+	__shared__ int s_done;
+	__shared__ unsigned long long s_prefix;
+	__shared__ unsigned s_agg;
+	if (S->error) return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned long long pos = S->pos0;
+	for (;;) {
+		__syncthreads();                                   // s_idx / s_tile of the previous tile are no longer read
+		if (tid == 0) { s_tile = atomicAdd(&S->cross_ticket, 1u); s_done = *((volatile int *) &S->cross_done); }
+		__syncthreads();
+		const unsigned tile = s_tile;
+		const int done = s_done;                           // one reading for the whole block: the exits below must be uniform
+		if (tile >= max_tiles) {
+			if (tid == 0 && !done) atomicOr(&S->error, kGaErrCrossWindow);
+			return;
+		}
+		if (done) {
+			// every rank this tile could hold lies past the last child: tell whoever looks back and leave
+			if (tid == 0) { __threadfence(); atomicExch(&desc[tile], kDescPre | (unsigned long long) need); }
+			return;
+		}
+		// ---- evaluate the tile's trials: thread t owns trials [t 16, t 16 + 16) of the tile, so thread order is trial order ----
+		const long long t0 = (long long) tile * kCrossTile + (long long) tid * kCrossPer;
+		int idx[kCrossPer];
+		unsigned c = 0;
+#pragma unroll
+		for (int e = 0; e < kCrossPer; e++) {
+			idx[e] = pipe_trial(st, pos + 2ULL * (unsigned long long) (t0 + e), ratio, Npop);
+			c += idx[e] != 0;
+		}
+		// ---- block-wide exclusive scan of the counts ----
+		unsigned incl = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned w = lane < kCrossThreads / 32 ? s_warp[lane] : 0;
+			unsigned wi = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+			if (lane < kCrossThreads / 32) s_warp[lane] = wi - w;          // exclusive warp offsets
+			const unsigned agg = __shfl_sync(0xffffffffu, wi, kCrossThreads / 32 - 1);
+			// ---- chained prefix over the tiles (tickets are handed out in tile order: every earlier tile is running or done) ----
+			unsigned long long prefix = 0;
+			if (tile > 0) {
+				if (lane == 0) { __threadfence(); atomicExch(&desc[tile], kDescAgg | (unsigned long long) agg); }
+				long long look = (long long) tile - 1;
+				for (;;) {
+					const long long j = look - lane;
+					unsigned long long d = kDescPre;                       // before tile 0: prefix 0
+					if (j >= 0) { do { d = ld_volatile_u64(&desc[j]); } while ((d >> 62) == 0); }
+					const unsigned has_pre = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+					const int first = has_pre ? __ffs(has_pre) - 1 : 32;   // nearest predecessor that knows its prefix
+					unsigned long long v = (lane <= first) ? (d & kDescMask) : 0;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+					prefix += v;
+					if (has_pre) break;
+					look -= 32;
+				}
+			}
+			if (prefix > (unsigned long long) need) prefix = (unsigned long long) need;
+			unsigned long long inclusive = prefix + agg;
+			if (inclusive > (unsigned long long) need) inclusive = (unsigned long long) need;    // saturate: ranks past `need` are never used
+			if (lane == 0) {
+				__threadfence();
+				atomicExch(&desc[tile], kDescPre | inclusive);
+				if (inclusive >= (unsigned long long) need) *((volatile int *) &S->cross_done) = 1;
+				s_prefix = prefix; s_agg = agg;
+			}
+		}
+		__syncthreads();
+		const unsigned long long prefix = s_prefix;
+		if (prefix >= (unsigned long long) need) return;           // nothing of this tile is used, nor of any later one
+		// ---- accepted trials in rank order -> shared memory ----
+		unsigned l = s_warp[warp] + incl - c;
+#pragma unroll
+		for (int e = 0; e < kCrossPer; e++) {
+			if (idx[e]) {
+				s_idx[l] = idx[e];
+				if (prefix + l == (unsigned long long) need - 1) S->cross_last_trial = t0 + e;
+				l++;
+			}
+		}
+		__syncthreads();
+		// ---- XpopNew[popIdx][i] = Xpop[indices[i]][i]  (:147-150): rank r is gene r % n of child r / n ----
+		const unsigned long long left = (unsigned long long) need - prefix;
+		const unsigned used = (unsigned long long) s_agg < left ? s_agg : (unsigned) left;
+		for (unsigned e = tid; e < used; e += kCrossThreads) {
+			const long long r = (long long) prefix + e;
+			const int parent = s_idx[e];
+			sel[r] = parent;
+			const long long child = r / n;
+			const int gene = (int) (r - child * n);
+			const long long row = row0 + child;
+			if (row >= own_lo && row < own_hi) Xloc[(row - own_lo) * n + gene] = __ldcg(cur.row(perm[parent]) + gene);
+		}
+	}
+}
+
+// row hash (and a zero box count: every gene of a crossover child is a parent's gene, which is inside the box) of rows [lo, hi)
+__global__ void __launch_bounds__(256)
+ga_rows_hash_kernel(const double * __restrict__ Xloc, long long own_lo, long long lo, long long hi, int n,
+                    unsigned long long * __restrict__ hash_new, unsigned * __restrict__ bcount)
+{
+	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (row >= hi) return;
+	const double * x = Xloc + (row - own_lo) * n;
+	unsigned long long h = 0;
+	for (int j = lane; j < n; j += 32) h += gene_hash(x[j], j);
+	for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+	if (lane == 0) { hash_new[row] = h; if (bcount) bcount[row] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2. mutation (:159-190). Stream layout from the stage start P1: [rejected trial (2 draws)]* [accepted trial (2)] [n mutation
+// draws] per child. Trial starts are multiples of g = gcd(2, n + 2); "candidate" j is stream offset g j. A trial at candidate j
+// moves the parser to j + stepA when accepted (stepA = (n + 2) / g) and to j + stepR otherwise (stepR = 2 / g).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMutSub = 1024;            // candidates per sub-block
+constexpr int kMutThreads = 256;
+
+struct MutGeom {
+	int g, stepA, stepR, SD;             // SD = stepA: entry offsets 0 .. stepA-1 (in candidates) a block can be entered at
+	int nsub;                            // sub-blocks per CTA
+	int nctas;
+};
+
+__device__ __forceinline__ unsigned long long mut_stage_pos(const GaDevStatus * S)
+{
+	return S->pos0 + 2ULL * (unsigned long long) (S->cross_last_trial + 1);
+}
+
+// acceptance bits of the CTA's candidates, sub-block tables entry offset -> (exit offset, children), CTA table
+__global__ void __launch_bounds__(kMutThreads)
+ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const double * __restrict__ ratio, int Npop, MutGeom G,
+                     unsigned * __restrict__ accbits, int * __restrict__ sub_exit, int * __restrict__ sub_cnt,
+                     int * __restrict__ cta_exit, long long * __restrict__ cta_cnt)
+{
+	extern __shared__ unsigned mut_sm[];
+	if (S->error) return;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int words = G.nsub * (kMutSub / 32);
+	unsigned * bits = mut_sm;                                        // words
+	int * t_exit = (int *) (bits + words);                           // nsub x SD
+	int * t_cnt = t_exit + G.nsub * G.SD;                            // nsub x SD
+	const unsigned long long P1 = mut_stage_pos(S);
+	const long long cand0 = (long long) blockIdx.x * G.nsub * kMutSub;
+	for (int w = tid >> 5; w < words; w += kMutThreads / 32) {
+		const long long j = cand0 + (long long) w * 32 + lane;
+		const bool acc = pipe_trial(st, P1 + (unsigned long long) G.g * (unsigned long long) j, ratio, Npop) != 0;
+		const unsigned m = __ballot_sync(0xffffffffu, acc);
+		if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
+	}
+	__syncthreads();
+	for (int e = tid; e < G.nsub * G.SD; e += kMutThreads) {
+		const int sub = e / G.SD, d = e - sub * G.SD;
+		const unsigned * b = bits + sub * (kMutSub / 32);
+		int j = d, cnt = 0;
+		while (j < kMutSub) {
+			if ((b[j >> 5] >> (j & 31)) & 1u) { cnt++; j += G.stepA; } else j += G.stepR;
+		}
+		t_exit[e] = j - kMutSub; t_cnt[e] = cnt;
+		sub_exit[(size_t) blockIdx.x * G.nsub * G.SD + e] = j - kMutSub;
+		sub_cnt[(size_t) blockIdx.x * G.nsub * G.SD + e] = cnt;
+	}
+	__syncthreads();
+	for (int d0 = tid; d0 < G.SD; d0 += kMutThreads) {
+		int d = d0;
+		long long cnt = 0;
+		for (int sub = 0; sub < G.nsub; sub++) {
+			if (d >= kMutSub) { d -= kMutSub; continue; }            // a jump longer than a sub-block (n + 2 > 1024 g)
+			cnt += t_cnt[sub * G.SD + d];
+			d = t_exit[sub * G.SD + d];
+		}
+		cta_exit[(size_t) blockIdx.x * G.SD + d0] = d;
+		cta_cnt[(size_t) blockIdx.x * G.SD + d0] = cnt;
+	}
+}
+
+// one thread: entry offset and first child of every CTA; children the window reaches
+__global__ void ga_mut_compose_kernel(GaDevStatus * __restrict__ S, MutGeom G, const int * __restrict__ cta_exit,
+                                      const long long * __restrict__ cta_cnt, int * __restrict__ cta_entry,
+                                      long long * __restrict__ cta_base, long long Nrand)
+{
+	if (S->error) return;
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	int d = 0;
+	long long cnt = 0;
+	const long long span = (long long) G.nsub * kMutSub;
+	for (int c = 0; c < G.nctas; c++) {
+		cta_entry[c] = d; cta_base[c] = cnt;
+		if (d >= span || d >= G.SD) { d -= (int) span; if (d < 0) d = 0; continue; }     // unreachable: SD <= span by construction
+		cnt += cta_cnt[(size_t) c * G.SD + d];
+		d = cta_exit[(size_t) c * G.SD + d];
+	}
+	S->mut_children = cnt;
+	if (cnt < Nrand) atomicOr(&S->error, kGaErrMutWindow);
+}
+
+// every sub-block walks from its entry offset and records (stream offset of the accepted trial, parent index) of its children
+__global__ void __launch_bounds__(kMutThreads)
+ga_mut_emit_kernel(StreamDev st, GaDevStatus * __restrict__ S, int Npop, int n, MutGeom G, const unsigned * __restrict__ accbits,
+                   const int * __restrict__ sub_exit, const int * __restrict__ sub_cnt, const int * __restrict__ cta_entry,
+                   const long long * __restrict__ cta_base, long long Nrand, long long NeliteMutGenes,
+                   long long * __restrict__ child_q, int * __restrict__ child_idx)
+{
+	extern __shared__ int emit_sm[];
+	if (S->error) return;
+	int * s_entry = emit_sm;                                         // nsub
+	long long * s_base = (long long *) (emit_sm + ((G.nsub + 1) & ~1));
+	const long long base0 = cta_base[blockIdx.x];
+	if (base0 >= Nrand) return;
+	if (threadIdx.x == 0) {
+		int d = cta_entry[blockIdx.x];
+		long long cnt = base0;
+		for (int sub = 0; sub < G.nsub; sub++) {
+			s_entry[sub] = d; s_base[sub] = cnt;
+			if (d >= kMutSub) { d -= kMutSub; continue; }
+			const size_t e = ((size_t) blockIdx.x * G.nsub + sub) * G.SD + d;
+			cnt += sub_cnt[e];
+			d = sub_exit[e];
+		}
+	}
+	__syncthreads();
+	const unsigned long long P1 = mut_stage_pos(S);
+	const int words = G.nsub * (kMutSub / 32);
+	for (int sub = threadIdx.x; sub < G.nsub; sub += kMutThreads) {
+		long long k = s_base[sub];
+		if (k >= Nrand) continue;
+		const unsigned * b = accbits + (size_t) blockIdx.x * words + sub * (kMutSub / 32);
+		const long long cand0 = ((long long) blockIdx.x * G.nsub + sub) * kMutSub;
+		int j = s_entry[sub];
+		while (j < kMutSub && k < Nrand) {
+			if ((b[j >> 5] >> (j & 31)) & 1u) {
+				const long long q = (long long) G.g * (cand0 + j);
+				child_q[k] = q;
+				child_idx[k] = (int) round(st.u(P1 + (unsigned long long) q) * Npop);
+				if (k == Nrand - 1) {
+					S->mut_last_q = q;
+					S->pos_elite = P1 + (unsigned long long) q + 2ULL + (unsigned long long) n;
+				}
+				k++;
+				j += G.stepA;
+			} else j += G.stepR;
+		}
+	}
+}
+
+// XpopNew[popIdx][j] = Xpop[index][j] + spreadRatio (Xub[j] - Xlb[j]) timeRand()   (:182-186), one warp per child of this rank;
+// row hash and out-of-box gene count on the way
+__global__ void __launch_bounds__(256)
+ga_mut_apply_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable cur, const unsigned * __restrict__ perm,
+                    const long long * __restrict__ child_q, const int * __restrict__ child_idx, long long k_lo, long long k_hi,
+                    long long row0, long long own_lo, int n, const double * __restrict__ lb, const double * __restrict__ ub,
+                    double spreadRatio, double * __restrict__ Xloc, unsigned long long * __restrict__ hash_new,
+                    unsigned * __restrict__ bcount)
+{
+	if (S->error) return;
+	const long long k = k_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (k >= k_hi) return;
+	const unsigned long long P1 = mut_stage_pos(S);
+	const unsigned long long q = P1 + (unsigned long long) child_q[k] + 2ULL;
+	const double * src = cur.row(perm[child_idx[k]]);
+	const long long row = row0 + k;
+	double * dst = Xloc + (row - own_lo) * n;
+	unsigned long long h = 0;
+	unsigned oob = 0;
+	for (int j = lane; j < n; j += 32) {
+		const double mutation = spreadRatio * (ub[j] - lb[j]) * st.u(q + (unsigned long long) j);
+		const double v = __ldcg(src + j) + mutation;
+		dst[j] = v;
+		h += gene_hash(v, j);
+		oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+	}
+	for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); oob += __shfl_xor_sync(0xffffffffu, oob, o); }
+	if (lane == 0) { hash_new[row] = h; bcount[row] = oob; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. mutations of the elite children (:195-207): two draws per gene at fixed positions
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ga_elite_mut_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable cur, const unsigned * __restrict__ perm,
+                    long long c_lo, long long c_hi, long long row0, long long own_lo, int n, int Nelite,
+                    const double * __restrict__ lb, const double * __restrict__ ub, double eliteMutationSize,
+                    double * __restrict__ Xloc, unsigned long long * __restrict__ hash_new, unsigned * __restrict__ bcount,
+                    int * __restrict__ elite_idx)
+{
+	if (S->error) return;
+	const long long c = c_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (c >= c_hi) return;
+	const unsigned long long P2 = S->pos_elite;
+	const long long row = row0 + c;
+	double * dst = Xloc + (row - own_lo) * n;
+	unsigned long long h = 0;
+	unsigned oob = 0;
+	for (int j = lane; j < n; j += 32) {
+		const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
+		const int randomEliteIdx = (int) round(st.u(P2 + 2ULL * e) * Nelite);
+		const double mutation = eliteMutationSize * (ub[j] - lb[j]) * st.u(P2 + 2ULL * e + 1ULL);
+		const double v = __ldcg(cur.row(perm[randomEliteIdx]) + j) + mutation;
+		dst[j] = v;
+		elite_idx[e] = randomEliteIdx;
+		h += gene_hash(v, j);
+		oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+	}
+	for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); oob += __shfl_xor_sync(0xffffffffu, oob, o); }
+	if (lane == 0) { hash_new[row] = h; bcount[row] = oob; }
+}
+
+// parent indices of ALL elite-mutation genes (pnol_ga_get_indices on a rank that only made its own children)
+__global__ void ga_elite_idx_kernel(StreamDev st, unsigned long long P2, long long count, int Nelite, int * __restrict__ elite_idx)
+{
+	const long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < count) elite_idx[e] = (int) round(st.u(P2 + 2ULL * (unsigned long long) e) * Nelite);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4. identical children (GeneticAlgorithm.cpp:313-344): row i is replaced iff a LATER row equals it
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ga_dup_insert_kernel(const unsigned long long * __restrict__ hash, long long Npop, unsigned long long * __restrict__ tkeys,
+                     unsigned * __restrict__ tmax, unsigned mask)
+{
+	const long long row = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= Npop) return;
+	unsigned long long h = hash[row];
+	if (h == 0) h = 1;                                               // 0 marks an empty slot
+	unsigned slot = (unsigned) (h >> 17) & mask;
+	for (;;) {
+		const unsigned long long prev = atomicCAS(&tkeys[slot], 0ULL, h);
+		if (prev == 0ULL || prev == h) { atomicMax(&tmax[slot], (unsigned) row); return; }
+		slot = (slot + 1) & mask;
+	}
+}
+
+__device__ __forceinline__ bool rows_equal(const double * a, const double * b, int n)
+{
+	int same = 0;
+	for (int j = 0; j < n; j++) same += (__ldcg(a + j) == __ldcg(b + j)) ? 1 : 0;      // the reference counts Nsame, NaN != NaN
+	return same == n;
+}
+
+__global__ void __launch_bounds__(256)
+ga_dup_query_kernel(const unsigned long long * __restrict__ hash, long long Npop, const unsigned long long * __restrict__ tkeys,
+                    const unsigned * __restrict__ tmax, unsigned mask, RowTable xnew, int n, unsigned char * __restrict__ dupflag,
+                    GaDevStatus * __restrict__ S, unsigned * __restrict__ suspects)
+{
+	const long long row = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= Npop) return;
+	unsigned long long h = hash[row];
+	if (h == 0) h = 1;
+	unsigned slot = (unsigned) (h >> 17) & mask;
+	while (tkeys[slot] != h) slot = (slot + 1) & mask;
+	const unsigned last = tmax[slot];                                // largest row with this hash
+	unsigned char flag = 0;
+	if (last > (unsigned) row) {
+		if (rows_equal(xnew.row(row), xnew.row(last), n)) flag = 1;
+		else suspects[atomicAdd(&S->nsuspect, 1u)] = (unsigned) row;   // a later row shares the hash but differs: look at all of them
+	}
+	dupflag[row] = flag;
+}
+
+// exhaustive check for the suspects (hash collisions, rows holding NaN): any later row with the same hash and equal genes?
+__global__ void __launch_bounds__(256)
+ga_dup_resolve_kernel(const unsigned long long * __restrict__ hash, long long Npop, RowTable xnew, int n,
+                      unsigned char * __restrict__ dupflag, const GaDevStatus * __restrict__ S, const unsigned * __restrict__ suspects)
+{
+	__shared__ int found;
+	const unsigned ns = S->nsuspect;
+	for (unsigned s = blockIdx.x; s < ns; s += gridDim.x) {
+		const unsigned row = suspects[s];
+		const unsigned long long h = hash[row];
+		if (threadIdx.x == 0) found = 0;
+		__syncthreads();
+		for (long long k = (long long) row + 1 + threadIdx.x; k < Npop; k += blockDim.x)
+			if (hash[k] == h && rows_equal(xnew.row(row), xnew.row(k), n)) found = 1;
+		__syncthreads();
+		if (threadIdx.x == 0 && found) dupflag[row] = 1;
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5. stream offsets of the replaced rows and of the repaired genes: exclusive prefix sum of the packed value
+//    (duplicate ? 1 : 0) << 40 | (duplicate ? 0 : out-of-box genes)     -- a replaced row is inside the box afterwards
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPackTile = 2048;
+__device__ __forceinline__ unsigned long long pack_row(const unsigned char * dupflag, const unsigned * bcount, long long row)
+{
+	return dupflag[row] ? (1ULL << 40) : (unsigned long long) bcount[row];
+}
+
+__global__ void __launch_bounds__(256)
+ga_pack_sums_kernel(const unsigned char * __restrict__ dupflag, const unsigned * __restrict__ bcount, long long Npop,
+                    unsigned long long * __restrict__ block_sums)
+{
+	__shared__ unsigned long long red[256];
+	const long long base = (long long) blockIdx.x * kPackTile;
+	unsigned long long s = 0;
+	for (int e = 0; e < 8; e++) {
+		const long long i = base + threadIdx.x * 8 + e;
+		if (i < Npop) s += pack_row(dupflag, bcount, i);
+	}
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = red[0];
+}
+
+// every block adds up the sums of the blocks before it (a few hundred values), then scans its own tile
+__global__ void __launch_bounds__(256)
+ga_pack_scan_kernel(const unsigned char * __restrict__ dupflag, const unsigned * __restrict__ bcount, long long Npop,
+                    const unsigned long long * __restrict__ block_sums, int nblocks, unsigned long long * __restrict__ offs,
+                    GaDevStatus * __restrict__ S, long long NeliteMutGenes, int n)
+{
+	__shared__ unsigned long long red[256];
+	unsigned long long before = 0;
+	for (int b = threadIdx.x; b < (int) blockIdx.x; b += 256) before += block_sums[b];
+	red[threadIdx.x] = before;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	before = red[0];
+	__syncthreads();
+	const long long base = (long long) blockIdx.x * kPackTile;
+	unsigned long long v[8], s = 0;
+	for (int e = 0; e < 8; e++) {
+		const long long i = base + threadIdx.x * 8 + e;
+		v[e] = i < Npop ? pack_row(dupflag, bcount, i) : 0;
+		s += v[e];
+	}
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 1; o < 256; o <<= 1) {
+		const unsigned long long t = threadIdx.x >= o ? red[threadIdx.x - o] : 0;
+		__syncthreads();
+		red[threadIdx.x] += t;
+		__syncthreads();
+	}
+	unsigned long long run = before + (threadIdx.x ? red[threadIdx.x - 1] : 0);
+	for (int e = 0; e < 8; e++) {
+		const long long i = base + threadIdx.x * 8 + e;
+		if (i < Npop) offs[i] = run;
+		run += v[e];
+	}
+	if ((int) blockIdx.x == nblocks - 1 && threadIdx.x == 255) {
+		S->ndup = run >> 40;
+		S->noob = run & ((1ULL << 40) - 1);
+	}
+}
+
+// replacement of duplicate rows and repair of out-of-box genes for the rows of this rank, one warp per row; evaluation flags
+__global__ void __launch_bounds__(256)
+ga_fix_kernel(StreamDev st, const GaDevStatus * __restrict__ S, long long own_lo, long long own_hi, int n, int Nelite,
+              long long NeliteMutGenes, const double * __restrict__ lb, const double * __restrict__ ub,
+              const unsigned char * __restrict__ dupflag, const unsigned * __restrict__ bcount,
+              const unsigned long long * __restrict__ offs, double * __restrict__ Xloc, unsigned char * __restrict__ indicator)
+{
+	if (S->error) return;
+	const long long row = own_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (row >= own_hi) return;
+	const bool dup = dupflag[row] != 0;
+	const unsigned cnt = bcount[row];
+	if (lane == 0) indicator[row - own_lo] = (row >= Nelite || dup) ? 1 : 0;       // elites keep their value unless replaced (:116, :220)
+	if (!dup && cnt == 0) return;
+	const unsigned long long P3 = S->pos_elite + 2ULL * (unsigned long long) NeliteMutGenes;      // after the elite mutations
+	const unsigned long long o = offs[row];
+	double * x = Xloc + (row - own_lo) * n;
+	if (dup) {
+		// Xpop[i][j] = Xlb[j] + (Xub[j] - Xlb[j]) timeRand(), n draws per replaced row in row order (GeneticAlgorithm.cpp:335-338)
+		const unsigned long long k = P3 + (o >> 40) * (unsigned long long) n;
+		for (int j = lane; j < n; j += 32) x[j] = lb[j] + (ub[j] - lb[j]) * st.u(k + (unsigned long long) j);
+		return;
+	}
+	// one draw per out-of-box gene in row-major order (GeneticAlgorithm.cpp:352-361), after all the replacement draws
+	unsigned long long k = P3 + S->ndup * (unsigned long long) n + (o & ((1ULL << 40) - 1));
+	for (int j0 = 0; j0 < n; j0 += 32) {
+		const int j = j0 + lane;
+		const double v = j < n ? x[j] : 0.0;
+		const bool out = j < n && (v > ub[j] || v < lb[j]);
+		const unsigned m = __ballot_sync(0xffffffffu, out);
+		if (out) x[j] = lb[j] + (ub[j] - lb[j]) * st.u(k + (unsigned long long) __popc(m & ((1u << lane) - 1)));
+		k += (unsigned long long) __popc(m);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 6. popSort (GeneticAlgorithm.cpp:370-412) == stable sort by objective value: LSD radix sort of (key(F), row), 8-bit digits,
+// in ONE cooperative kernel. Each CTA owns a contiguous range of the array; per pass: digit counts of the range -> grid barrier
+// -> every CTA derives its scatter offsets from all counts (and finds out whether one digit holds every key: pass skipped by all)
+// -> stable ranking inside the range and scatter -> grid barrier.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 1024;
+constexpr int kSortPerThread = 8;
+constexpr int kSortChunk = kSortThreads * kSortPerThread;          // keys ranked at a time
+
+__global__ void __launch_bounds__(kSortThreads, 1)
+ga_sort_kernel(const double * __restrict__ F, long long N, long long range, unsigned long long * __restrict__ keys0,
+               unsigned * __restrict__ vals0, unsigned long long * __restrict__ keys1, unsigned * __restrict__ vals1,
+               unsigned * __restrict__ counts /* [256][gridDim] */, GaDevStatus * __restrict__ S, double * __restrict__ Fsorted,
+               unsigned * __restrict__ perm_out)
+{
+	cg::grid_group grid = cg::this_grid();
+	__shared__ unsigned wcount[kSortThreads / 32][256];              // 32 KB
+	__shared__ unsigned long long dbase[256];
+	__shared__ unsigned long long dtot[256];
+	__shared__ int s_skip;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int G = gridDim.x, cta = blockIdx.x;
+	const long long lo = (long long) cta * range < N ? (long long) cta * range : N, hi = lo + range < N ? lo + range : N;
+	// keys from the objective values, values = row numbers
+	for (long long i = lo + tid; i < hi; i += kSortThreads) { keys0[i] = double_to_key(F[i]); vals0[i] = (unsigned) i; }
+	unsigned long long * kin = keys0, * kout = keys1;
+	unsigned * vin = vals0, * vout = vals1;
+	for (int pass = 0; pass < 8; pass++) {
+		const int shift = 8 * pass;
+		// ---- digit counts of this CTA's range ----
+		for (int e = tid; e < (kSortThreads / 32) * 256; e += kSortThreads) (&wcount[0][0])[e] = 0;
+		__syncthreads();
+		for (long long i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&wcount[warp & 7][(kin[i] >> shift) & 255], 1u);
+		__syncthreads();
+		if (tid < 256) {
+			unsigned c = 0;
+			for (int w = 0; w < 8; w++) c += wcount[w][tid];
+			counts[(size_t) tid * G + cta] = c;
+		}
+		grid.sync();
+		// ---- offsets of this range: total of the smaller digits + the same digit in the ranges before ----
+		if (tid < 256) {
+			unsigned long long tot = 0, before = 0;
+			const unsigned * c = counts + (size_t) tid * G;
+			for (int b = 0; b < G; b++) { const unsigned v = c[b]; tot += v; if (b < cta) before += v; }
+			dtot[tid] = tot;
+			dbase[tid] = before;
+		}
+		if (tid == 0) s_skip = 0;
+		__syncthreads();
+		if (tid < 256 && dtot[tid] == (unsigned long long) N) s_skip = 1;      // one digit value holds every key: nothing moves
+		__syncthreads();
+		if (s_skip) { grid.sync(); continue; }                                 // uniform over the grid: all CTAs see the same totals
+		if (tid == 0) {
+			unsigned long long run = 0;
+			for (int d = 0; d < 256; d++) { const unsigned long long t = dtot[d]; dbase[d] += run; run += t; }
+		}
+		__syncthreads();
+		// ---- stable ranking and scatter, kSortChunk keys at a time ----
+		for (long long c0 = lo; c0 < hi; c0 += kSortChunk) {
+			for (int e = tid; e < (kSortThreads / 32) * 256; e += kSortThreads) (&wcount[0][0])[e] = 0;
+			__syncthreads();
+			// warp w owns 256 consecutive keys of the chunk; round r covers keys base + 32 r + lane: (warp, round, lane) is key order
+			const long long base = c0 + (long long) warp * (32 * kSortPerThread);
+			unsigned long long k[kSortPerThread];
+			unsigned v[kSortPerThread];
+			unsigned short rank[kSortPerThread];
+#pragma unroll
+			for (int r = 0; r < kSortPerThread; r++) {
+				const long long i = base + r * 32 + lane;
+				const bool valid = i < hi;
+				k[r] = valid ? kin[i] : 0xFFFFFFFFFFFFFFFFULL;
+				v[r] = valid ? vin[i] : 0;
+				const unsigned d = valid ? (unsigned) ((k[r] >> shift) & 255) : 256u;
+				const unsigned m = __match_any_sync(0xffffffffu, d);
+				const unsigned ahead = __popc(m & ((1u << lane) - 1));
+				unsigned prev = 0;
+				if (valid) prev = wcount[warp][d];
+				__syncwarp();
+				if (valid && ahead == 0) wcount[warp][d] = prev + __popc(m);
+				__syncwarp();
+				rank[r] = (unsigned short) (prev + ahead);
+			}
+			__syncthreads();
+			if (tid < 256) {                                        // exclusive scan over the warps, per digit
+				unsigned run = 0;
+				for (int w = 0; w < kSortThreads / 32; w++) { const unsigned c = wcount[w][tid]; wcount[w][tid] = run; run += c; }
+				dtot[tid] = run;                                    // keys of this digit in the chunk
+			}
+			__syncthreads();
+#pragma unroll
+			for (int r = 0; r < kSortPerThread; r++) {
+				const long long i = base + r * 32 + lane;
+				if (i < hi) {
+					const unsigned d = (unsigned) ((k[r] >> shift) & 255);
+					const unsigned long long p = dbase[d] + wcount[warp][d] + rank[r];
+					kout[p] = k[r];
+					vout[p] = v[r];
+				}
+			}
+			__syncthreads();
+			if (tid < 256) dbase[tid] += dtot[tid];
+			__syncthreads();
+		}
+		{ unsigned long long * t = kin; kin = kout; kout = t; unsigned * u = vin; vin = vout; vout = u; }
+		grid.sync();
+	}
+	// sorted objective values and the permutation sorted position -> row
+	for (long long i = lo + tid; i < hi; i += kSortThreads) { Fsorted[i] = key_to_double(kin[i]); perm_out[i] = vin[i]; }
+	if (cta == 0 && tid == 0) S->sort_result_in_alt = (kin != keys0);
+}
+
+// end of the generation: stream position, best objective. The kernels above read the stream speculatively (trial windows), so
+// exhaustion of an explicit stream is decided here: the sequential algorithm consumed exactly the draws [0, pos_end)
+__global__ void ga_finish_kernel(GaDevStatus * __restrict__ S, const double * __restrict__ Fsorted, long long NeliteMutGenes, int n,
+                                 unsigned long long n_values)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (S->error) return;
+	S->pos_end = S->pos_elite + 2ULL * (unsigned long long) NeliteMutGenes + S->ndup * (unsigned long long) n + S->noob;
+	S->fbest = Fsorted[0];
+	if (S->pos_end > n_values) S->error |= kGaErrStream;
+}
+
+// dst[k] = src row perm[k] (materialising the sorted population for pnol_ga_get_population)
+__global__ void __launch_bounds__(256)
+ga_gather_sorted_kernel(RowTable cur, const unsigned * __restrict__ perm, long long k0, long long k1, int n, double * __restrict__ dst)
+{
+	const long long k = k0 + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (k >= k1) return;
+	const double * s = cur.row(perm[k]);
+	double * d = dst + (k - k0) * n;
+	for (int j = lane; j < n; j += 32) d[j] = __ldcg(s + j);
+}
+
+__global__ void ga_iota_kernel(unsigned * __restrict__ perm, long long n)
+{
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) perm[i] = (unsigned) i;
+}
+
+} // namespace pnol
+
+using namespace pnol;
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct GaPipe {
+	// population rows of THIS rank, double-buffered: XL[cur] holds rows [lo, hi) of the current population in child order
+	double * XL[2] = {nullptr, nullptr};
+	int cur = 0;
+	long long per = 0, lo = 0, hi = 0;               // rows per rank, own range
+	RowTable table[2];                               // where all ranks' rows of XL[0] / XL[1] are, as seen from this GPU
+	void * peer_maps[2][kGaMaxRanks] = {};           // IPC mappings to close
+	double * replica[2] = {nullptr, nullptr};        // fallback without peer mappings: full copies refreshed by all-gather
+	bool use_ipc = false;
+	// replicated per-row arrays (sorted order: Fs, ratio, perm; child order: hash, bcount, dupflag, Fchild, offs)
+	unsigned * perm[2] = {nullptr, nullptr};
+	double * Fs[2] = {nullptr, nullptr};
+	unsigned long long * hash[2] = {nullptr, nullptr};
+	double * ratio = nullptr, * Fchild = nullptr;
+	unsigned * bcount = nullptr;
+	unsigned char * dupflag = nullptr, * indicator = nullptr;
+	unsigned long long * offs = nullptr, * block_sums = nullptr;
+	unsigned * suspects = nullptr;
+	// gather staging (several ranks): [hash (8) | bcount (4)] per row, per rank slots
+	unsigned char * hb_send = nullptr, * hb_recv = nullptr;
+	double * f_recv = nullptr;
+	// crossover
+	unsigned long long * desc = nullptr; unsigned max_tiles = 0; unsigned tiles_dirty = 0;
+	// mutation
+	void * mut_mem = nullptr; size_t mut_bytes = 0;
+	// duplicate table
+	unsigned long long * tkeys = nullptr; unsigned * tmax = nullptr; unsigned tmask = 0;
+	// sort
+	unsigned long long * skeys[2] = {nullptr, nullptr}; unsigned * svals[2] = {nullptr, nullptr}; unsigned * scounts = nullptr;
+	int sort_grid = 0; long long sort_range = 0;
+	// status
+	GaDevStatus * status = nullptr; GaDevStatus * status_host = nullptr;
+	unsigned long long pos_elite_last = 0;           // start of the last generation's elite-mutation stage (for get_indices)
+	bool elite_idx_complete = true;
+	double accept_rate = 0.25;
+	std::vector<void *> owned;
+};
+
+namespace {
+
+template <class T> int pipe_alloc(pnol_ga * ga, T ** p, size_t count)
+{
+	void * d = nullptr;
+	PNOL_CUDA(ga->ctx, cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
+	ga->pipe->owned.push_back(d);
+	*p = (T *) d;
+	return PNOL_OK;
+}
+
+StreamDev pipe_stream(pnol_ga * ga)
+{
+	StreamDev st;
+	st.values = ga->stream_values; st.n_values = ga->stream.n_values; st.seed = ga->stream.seed; st.scale = ga->stream.scale;
+	st.exhausted = nullptr;            // speculative reads past the end are fine; ga_finish_kernel decides exhaustion
+	return st;
+}
+
+unsigned blocks_for(long long threads, int per_block) { return (unsigned) std::max<long long>(1, (threads + per_block - 1) / per_block); }
+
+// peer mappings of the ranks' row blocks (CUDA IPC over NVLink); false when any step fails (the caller falls back to replicas)
+bool pipe_open_peers(pnol_ga * ga)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	const int R = ctx->nranks;
+	static const bool disabled = [] { const char * e = getenv("PNOL_GA_NO_IPC"); return e && atoi(e) != 0; }();
+	int ok = disabled ? 0 : 1;
+	cudaIpcMemHandle_t mine[2];
+	for (int b = 0; b < 2 && ok; b++) if (cudaIpcGetMemHandle(&mine[b], P->XL[b]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+	// everybody must take the same path: exchange [ok | handles] through the communicator
+	const size_t slot = 8 + 2 * sizeof(cudaIpcMemHandle_t);
+	std::vector<unsigned char> send(slot, 0), recv(slot * R, 0);
+	send[0] = (unsigned char) ok;
+	memcpy(send.data() + 8, mine, sizeof mine);
+	unsigned char * dsend = nullptr, * drecv = nullptr;
+	if (cudaMalloc((void **) &dsend, slot) != cudaSuccess || cudaMalloc((void **) &drecv, slot * R) != cudaSuccess) return false;
+	cudaMemcpyAsync(dsend, send.data(), slot, cudaMemcpyHostToDevice, ctx->stream);
+	bool good = comm_allgather_bytes_dev(ctx, dsend, drecv, slot) == PNOL_OK;
+	cudaMemcpyAsync(recv.data(), drecv, slot * R, cudaMemcpyDeviceToHost, ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(dsend); cudaFree(drecv);
+	if (!good) return false;
+	for (int r = 0; r < R; r++) if (!recv[(size_t) r * slot]) return false;
+	bool opened = true;
+	for (int b = 0; b < 2; b++)
+		for (int r = 0; r < R; r++) {
+			if (r == ctx->rank) { P->table[b].base[r] = P->XL[b]; continue; }
+			cudaIpcMemHandle_t h;
+			memcpy(&h, recv.data() + (size_t) r * slot + 8 + b * sizeof h, sizeof h);
+			void * p = nullptr;
+			if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = false; p = nullptr; }
+			P->peer_maps[b][r] = p;
+			P->table[b].base[r] = (const double *) p;
+		}
+	// again a common decision: one failed mapping anywhere sends every rank to the replica path
+	double flag = opened ? 0.0 : 1.0;
+	double * dflag = nullptr;
+	if (cudaMalloc((void **) &dflag, sizeof(double)) != cudaSuccess) return false;
+	cudaMemcpyAsync(dflag, &flag, sizeof flag, cudaMemcpyHostToDevice, ctx->stream);
+	comm_allreduce_dev(ctx, dflag, 1);
+	cudaMemcpyAsync(&flag, dflag, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(dflag);
+	if (flag != 0.0) {
+		for (int b = 0; b < 2; b++)
+			for (int r = 0; r < R; r++) if (P->peer_maps[b][r]) { cudaIpcCloseMemHandle(P->peer_maps[b][r]); P->peer_maps[b][r] = nullptr; }
+		return false;
+	}
+	return true;
+}
+
+} // namespace
+
+namespace pnol {
+
+int ga_pipe_create(pnol_ga * ga)
+{
+	pnol_ctx * ctx = ga->ctx;
+	const long long Npop = ga->prm.npop;
+	const int n = ga->n, R = ctx->nranks;
+	PNOL_REQUIRE(ctx, R <= kGaMaxRanks, "ga: at most %d ranks", kGaMaxRanks);
+	GaPipe * P = new GaPipe();
+	ga->pipe = P;
+	P->per = (Npop + R - 1) / R;
+	P->lo = std::min<long long>(P->per * ctx->rank, Npop);
+	P->hi = std::min<long long>(P->lo + P->per, Npop);
+	for (int b = 0; b < 2; b++) {
+		PNOL_CHECK(pipe_alloc(ga, &P->XL[b], (size_t) P->per * n));
+		PNOL_CHECK(pipe_alloc(ga, &P->perm[b], (size_t) Npop));
+		PNOL_CHECK(pipe_alloc(ga, &P->Fs[b], (size_t) Npop));
+		PNOL_CHECK(pipe_alloc(ga, &P->hash[b], (size_t) P->per * R));
+		PNOL_CHECK(pipe_alloc(ga, &P->skeys[b], (size_t) Npop));
+		PNOL_CHECK(pipe_alloc(ga, &P->svals[b], (size_t) Npop));
+		P->table[b].per = P->per; P->table[b].n = n;
+		for (int r = 0; r < kGaMaxRanks; r++) P->table[b].base[r] = nullptr;
+		P->table[b].base[0] = P->XL[b];
+	}
+	PNOL_CHECK(pipe_alloc(ga, &P->ratio, (size_t) Npop));
+	PNOL_CHECK(pipe_alloc(ga, &P->Fchild, (size_t) P->per * R));
+	PNOL_CHECK(pipe_alloc(ga, &P->bcount, (size_t) P->per * R));
+	PNOL_CHECK(pipe_alloc(ga, &P->dupflag, (size_t) Npop));
+	PNOL_CHECK(pipe_alloc(ga, &P->indicator, (size_t) P->per));
+	PNOL_CHECK(pipe_alloc(ga, &P->offs, (size_t) Npop));
+	PNOL_CHECK(pipe_alloc(ga, &P->block_sums, (size_t) (Npop + kPackTile - 1) / kPackTile + 1));
+	PNOL_CHECK(pipe_alloc(ga, &P->suspects, (size_t) Npop));
+	PNOL_CHECK(pipe_alloc(ga, &P->status, 1));
+	PNOL_CUDA(ctx, cudaMallocHost((void **) &P->status_host, sizeof(GaDevStatus)));
+	// crossover tiles: room for an acceptance rate down to 1/256 (a lower one ends in kGaErrCrossWindow)
+	{
+		const long long need = (long long) ga->ncross * n;
+		long long tiles = need / kCrossTile * 256 + 1024;
+		if (tiles > (1LL << 24)) tiles = 1LL << 24;
+		P->max_tiles = (unsigned) tiles;
+		PNOL_CHECK(pipe_alloc(ga, &P->desc, (size_t) P->max_tiles));
+		PNOL_CUDA(ctx, cudaMemsetAsync(P->desc, 0, (size_t) P->max_tiles * 8, ctx->stream));
+	}
+	// duplicate table: at least 2 slots per row, power of two
+	{
+		unsigned slots = 1024;
+		while ((long long) slots < 2 * Npop) slots <<= 1;
+		P->tmask = slots - 1;
+		PNOL_CHECK(pipe_alloc(ga, &P->tkeys, (size_t) slots));
+		PNOL_CHECK(pipe_alloc(ga, &P->tmax, (size_t) slots));
+	}
+	// sort: one CTA per SM at most (cooperative launch), contiguous ranges that are multiples of the ranking chunk
+	{
+		int per_sm = 0;
+		PNOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ga_sort_kernel, kSortThreads, 0));
+		PNOL_REQUIRE(ctx, per_sm >= 1, "ga: the sort kernel does not fit an SM");
+		const int maxg = ctx->sm_count * per_sm;
+		long long range = (Npop + maxg - 1) / maxg;
+		range = (range + kSortChunk - 1) / kSortChunk * kSortChunk;
+		P->sort_range = range;
+		P->sort_grid = (int) ((Npop + range - 1) / range);
+		PNOL_CHECK(pipe_alloc(ga, &P->scounts, (size_t) 256 * P->sort_grid));
+	}
+	if (R > 1) {
+		PNOL_CHECK(pipe_alloc(ga, &P->hb_send, (size_t) P->per * 12));
+		PNOL_CHECK(pipe_alloc(ga, &P->hb_recv, (size_t) P->per * 12 * R));
+		PNOL_CHECK(pipe_alloc(ga, &P->f_recv, (size_t) P->per * R));
+		P->use_ipc = pipe_open_peers(ga);
+		if (!P->use_ipc) {
+			for (int b = 0; b < 2; b++) {
+				PNOL_CHECK(pipe_alloc(ga, &P->replica[b], (size_t) P->per * R * n));
+				for (int r = 0; r < R; r++) P->table[b].base[r] = P->replica[b] + (size_t) r * P->per * n;
+			}
+		}
+	}
+	return PNOL_OK;
+}
+
+void ga_pipe_destroy(pnol_ga * ga)
+{
+	GaPipe * P = ga->pipe;
+	if (!P) return;
+	cudaStreamSynchronize(ga->ctx->stream);
+	for (int b = 0; b < 2; b++)
+		for (int r = 0; r < kGaMaxRanks; r++) if (P->peer_maps[b][r]) cudaIpcCloseMemHandle(P->peer_maps[b][r]);
+	for (void * p : P->owned) cudaFree(p);
+	if (P->mut_mem) cudaFree(P->mut_mem);
+	if (P->status_host) cudaFreeHost(P->status_host);
+	delete P;
+	ga->pipe = nullptr;
+}
+
+// refresh the local replica of buffer b from every rank's block (path without peer mappings)
+static int pipe_refresh_replica(pnol_ga * ga, int b)
+{
+	GaPipe * P = ga->pipe;
+	if (ga->ctx->nranks <= 1 || P->use_ipc) return PNOL_OK;
+	return comm_allgather_dev(ga->ctx, P->XL[b], P->replica[b], (size_t) P->per * ga->n);
+}
+
+// after pnol_ga_init: ga->Xpop / ga->F hold the sorted start population (replicated). Rows -> this rank's block, perm = identity.
+int ga_pipe_reset(pnol_ga * ga)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	const long long Npop = ga->prm.npop;
+	const int n = ga->n;
+	P->cur = 0;
+	if (P->hi > P->lo)
+		PNOL_CUDA(ctx, cudaMemcpyAsync(P->XL[0], ga->Xpop + P->lo * n, (size_t) (P->hi - P->lo) * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	PNOL_CUDA(ctx, cudaMemcpyAsync(P->Fs[0], ga->F, (size_t) Npop * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	PNOL_LAUNCH(ctx, ga_iota_kernel, blocks_for(Npop, 256), 256, 0, P->perm[0], Npop);
+	// hashes of all rows (the full sorted population is at hand on every rank right now)
+	PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for(Npop * 32, 256), 256, 0, ga->Xpop, 0LL, 0LL, Npop, n, P->hash[0], (unsigned *) nullptr);
+	PNOL_CHECK(pipe_refresh_replica(ga, 0));
+	P->elite_idx_complete = true;
+	return PNOL_OK;
+}
+
+static int pipe_mut_reserve(pnol_ga * ga, size_t bytes)
+{
+	GaPipe * P = ga->pipe;
+	if (bytes <= P->mut_bytes) return PNOL_OK;
+	if (P->mut_mem) { PNOL_CUDA(ga->ctx, cudaStreamSynchronize(ga->ctx->stream)); cudaFree(P->mut_mem); P->mut_mem = nullptr; P->mut_bytes = 0; }
+	PNOL_CUDA(ga->ctx, cudaMalloc(&P->mut_mem, bytes + bytes / 4));
+	P->mut_bytes = bytes + bytes / 4;
+	return PNOL_OK;
+}
+
+// enqueue one generation; window_scale > 1 after a short mutation window
+static int pipe_enqueue(pnol_ga * ga, double window_scale)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	const int Npop = ga->prm.npop, n = ga->n, R = ctx->nranks;
+	const long long Nelite = ga->nelite, Ncross = ga->ncross, Nrand = ga->nrand, NeliteMut = ga->nelmut;
+	const int cur = P->cur, nxt = cur ^ 1;
+	const RowTable & T = P->table[cur];
+	const RowTable & Tn = P->table[nxt];
+	StreamDev st = pipe_stream(ga);
+	GaDevStatus * S = P->status;
+	double * Xloc = P->XL[nxt];
+	const long long lo = P->lo, hi = P->hi;
+	auto clampr = [&](long long a, long long b, long long & x0, long long & x1) {   // [a, b) cut to the own rows
+		x0 = std::max(a, lo); x1 = std::min(b, hi); if (x1 < x0) x1 = x0;
+	};
+
+	// 0. fitness / ratios / status
+	if (P->tiles_dirty) PNOL_CUDA(ctx, cudaMemsetAsync(P->desc, 0, (size_t) std::min(P->tiles_dirty, P->max_tiles) * 8, ctx->stream));
+	{
+		TimerScope ts(ctx, "ga_prep");
+		PNOL_LAUNCH(ctx, ga_prep_kernel, blocks_for(Npop, 256), 256, 0, P->Fs[cur], Npop, (int) Nelite, ga->fitness, P->ratio, P->Fchild, S,
+		            (unsigned long long) ga->pos);
+		long long a, b;
+		clampr(0, Nelite, a, b);
+		if (b > a) PNOL_LAUNCH(ctx, ga_elite_copy_kernel, blocks_for((b - a) * 32, 256), 256, 0, T, P->perm[cur], P->hash[cur], a, b, n,
+		                       Xloc + (a - lo) * n, P->hash[nxt], P->bcount);
+	}
+	// 1. crossover
+	if (Ncross > 0) {
+		TimerScope ts(ctx, "ga_crossover");
+		const long long need = Ncross * n;
+		PNOL_LAUNCH(ctx, ga_cross_kernel, ctx->sm_count * 6, kCrossThreads, 0, st, S, P->ratio, Npop, need, P->max_tiles, P->desc, ga->cross_idx,
+		            T, P->perm[cur], n, Xloc, lo, hi, Nelite);
+		long long a, b;
+		clampr(Nelite, Nelite + Ncross, a, b);
+		if (b > a) PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for((b - a) * 32, 256), 256, 0, Xloc, lo, a, b, n, P->hash[nxt], P->bcount);
+	}
+	// 2. mutation
+	{
+		TimerScope ts(ctx, "ga_mutation");
+		const double spreadRatio = ga->prm.mutation_size * (ga->prm.max_generations - ga->generation) / ga->prm.max_generations;   // (:159)
+		MutGeom G;
+		G.g = (n % 2 == 0) ? 2 : 1;
+		G.stepA = (n + 2) / G.g; G.stepR = 2 / G.g; G.SD = G.stepA;
+		const double rate = std::max(P->accept_rate, 1e-3);
+		// candidates per child: one accepted trial (stepA) and 1/rate - 1 rejected ones (stepR each)
+		double cand = (double) Nrand * (G.stepA + G.stepR * (1.0 / rate - 1.0)) * 1.12 * window_scale + 8.0 * kMutSub;
+		const size_t smem_cap = 96 * 1024;
+		int nsub_max = (int) (smem_cap / ((size_t) (kMutSub / 32) * 4 + (size_t) G.SD * 8));
+		PNOL_REQUIRE(ctx, nsub_max >= 1, "ga: n = %d is too large for the mutation tables", n);
+		long long subs = (long long) (cand / kMutSub) + 1;
+		const long long min_subs = ((long long) G.SD + kMutSub - 1) / kMutSub;            // a CTA spans at least the longest jump
+		int nsub = (int) std::max<long long>(min_subs, std::min<long long>(nsub_max, (subs + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count)));
+		PNOL_REQUIRE(ctx, nsub <= nsub_max, "ga: n = %d is too large for the mutation tables", n);
+		G.nsub = nsub;
+		G.nctas = (int) ((subs + nsub - 1) / nsub);
+		const size_t words = (size_t) G.nctas * nsub * (kMutSub / 32);
+		const size_t tabs = (size_t) G.nctas * nsub * G.SD;
+		const size_t ctab = (size_t) G.nctas * G.SD;
+		size_t bytes = words * 4 + tabs * 8 + ctab * 12 + (size_t) G.nctas * 12 + 4096;
+		PNOL_CHECK(pipe_mut_reserve(ga, bytes));
+		unsigned char * p = (unsigned char *) P->mut_mem;
+		auto take = [&](size_t b) { void * r = p; p += (b + 255) & ~(size_t) 255; return r; };
+		long long * cta_cnt = (long long *) take(ctab * 8);
+		long long * cta_base = (long long *) take((size_t) G.nctas * 8);
+		unsigned * accbits = (unsigned *) take(words * 4);
+		int * sub_exit = (int *) take(tabs * 4);
+		int * sub_cnt = (int *) take(tabs * 4);
+		int * cta_exit = (int *) take(ctab * 4);
+		int * cta_entry = (int *) take((size_t) G.nctas * 4);
+		const size_t smem1 = (size_t) nsub * (kMutSub / 32) * 4 + (size_t) nsub * G.SD * 8;
+		PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_mut_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1));
+		PNOL_LAUNCH(ctx, ga_mut_tables_kernel, G.nctas, kMutThreads, smem1, st, S, P->ratio, Npop, G, accbits, sub_exit, sub_cnt, cta_exit, cta_cnt);
+		PNOL_LAUNCH(ctx, ga_mut_compose_kernel, 1, 32, 0, S, G, cta_exit, cta_cnt, cta_entry, cta_base, Nrand);
+		const size_t smem3 = (size_t) ((nsub + 1) & ~1) * 4 + (size_t) nsub * 8;
+		PNOL_LAUNCH(ctx, ga_mut_emit_kernel, G.nctas, kMutThreads, smem3, st, S, Npop, n, G, accbits, sub_exit, sub_cnt, cta_entry, cta_base, Nrand,
+		            NeliteMut * n, ga->mut_pos, ga->mut_idx);
+		long long a, b;
+		clampr(Nelite + Ncross, Nelite + Ncross + Nrand, a, b);
+		if (b > a)
+			PNOL_LAUNCH(ctx, ga_mut_apply_kernel, blocks_for((b - a) * 32, 256), 256, 0, st, S, T, P->perm[cur], ga->mut_pos, ga->mut_idx,
+			            a - (Nelite + Ncross), b - (Nelite + Ncross), Nelite + Ncross, lo, n, ga->lb, ga->ub, spreadRatio, Xloc, P->hash[nxt], P->bcount);
+	}
+	// 3. elite mutations
+	if (NeliteMut > 0) {
+		TimerScope ts(ctx, "ga_elite_mutation");
+		const long long row0 = Nelite + Ncross + Nrand;
+		long long a, b;
+		clampr(row0, row0 + NeliteMut, a, b);
+		if (b > a)
+			PNOL_LAUNCH(ctx, ga_elite_mut_kernel, blocks_for((b - a) * 32, 256), 256, 0, st, S, T, P->perm[cur], a - row0, b - row0, row0, lo, n,
+			            (int) Nelite, ga->lb, ga->ub, ga->prm.elite_mutation_size, Xloc, P->hash[nxt], P->bcount, ga->elite_idx);
+	}
+	// hashes and box counts of all rows on every rank; the new rows where the duplicate check of another rank may look at them
+	if (R > 1) {
+		TimerScope ts(ctx, "ga_gather_hash");
+		const size_t own = (size_t) (hi - lo);
+		PNOL_CUDA(ctx, cudaMemsetAsync(P->hb_send, 0, (size_t) P->per * 12, ctx->stream));
+		if (own) {
+			PNOL_CUDA(ctx, cudaMemcpyAsync(P->hb_send, P->hash[nxt] + lo, own * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+			PNOL_CUDA(ctx, cudaMemcpyAsync(P->hb_send + (size_t) P->per * 8, P->bcount + lo, own * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+		PNOL_CHECK(comm_allgather_bytes_dev(ctx, P->hb_send, P->hb_recv, (size_t) P->per * 12));
+		for (int r = 0; r < R; r++) {
+			const unsigned char * slot = P->hb_recv + (size_t) r * P->per * 12;
+			PNOL_CUDA(ctx, cudaMemcpyAsync(P->hash[nxt] + (size_t) r * P->per, slot, (size_t) P->per * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+			PNOL_CUDA(ctx, cudaMemcpyAsync(P->bcount + (size_t) r * P->per, slot + (size_t) P->per * 8, (size_t) P->per * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+		PNOL_CHECK(pipe_refresh_replica(ga, nxt));
+	}
+	// 4. identical children
+	{
+		TimerScope ts(ctx, "ga_check_identical");
+		PNOL_CUDA(ctx, cudaMemsetAsync(P->tkeys, 0, ((size_t) P->tmask + 1) * 8, ctx->stream));
+		PNOL_CUDA(ctx, cudaMemsetAsync(P->tmax, 0, ((size_t) P->tmask + 1) * 4, ctx->stream));
+		PNOL_LAUNCH(ctx, ga_dup_insert_kernel, blocks_for(Npop, 256), 256, 0, P->hash[nxt], (long long) Npop, P->tkeys, P->tmax, P->tmask);
+		PNOL_LAUNCH(ctx, ga_dup_query_kernel, blocks_for(Npop, 256), 256, 0, P->hash[nxt], (long long) Npop, P->tkeys, P->tmax, P->tmask, Tn, n,
+		            P->dupflag, S, P->suspects);
+		PNOL_LAUNCH(ctx, ga_dup_resolve_kernel, 64, 256, 0, P->hash[nxt], (long long) Npop, Tn, n, P->dupflag, S, P->suspects);
+	}
+	// 5. stream offsets, replacement and repair, evaluation flags
+	{
+		TimerScope ts(ctx, "ga_check_bounds");
+		const int nb = (int) blocks_for(Npop, kPackTile);
+		PNOL_LAUNCH(ctx, ga_pack_sums_kernel, nb, 256, 0, P->dupflag, P->bcount, (long long) Npop, P->block_sums);
+		PNOL_LAUNCH(ctx, ga_pack_scan_kernel, nb, 256, 0, P->dupflag, P->bcount, (long long) Npop, P->block_sums, nb, P->offs, S, NeliteMut * n, n);
+		if (hi > lo)
+			PNOL_LAUNCH(ctx, ga_fix_kernel, blocks_for((hi - lo) * 32, 256), 256, 0, st, S, lo, hi, n, (int) Nelite, NeliteMut * n, ga->lb, ga->ub,
+			            P->dupflag, P->bcount, P->offs, Xloc, P->indicator);
+	}
+	// 6. the fitness sweep over this rank's rows (:217)
+	if (hi > lo) PNOL_CHECK(launch_eval_batch(ctx, ga->f, Xloc, hi - lo, n, n, P->indicator, P->Fchild + lo));
+	if (R > 1) {
+		TimerScope ts(ctx, "ga_gather_f");
+		// rows that were not evaluated (elites) already hold the same value on every rank, so gathering whole blocks is exact
+		PNOL_CHECK(comm_allgather_dev(ctx, P->Fchild + lo, P->f_recv, (size_t) P->per));
+		PNOL_CUDA(ctx, cudaMemcpyAsync(P->Fchild, P->f_recv, (size_t) P->per * R * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		PNOL_CHECK(pipe_refresh_replica(ga, nxt));      // repaired / replaced genes
+	}
+	// 7. popSort (:220): sorted objective values and the permutation, rows stay where they are
+	{
+		TimerScope ts(ctx, "ga_pop_sort");
+		const double * Fc = P->Fchild;
+		long long N = Npop, range = P->sort_range;
+		unsigned long long * k0 = P->skeys[0], * k1 = P->skeys[1];
+		unsigned * v0 = P->svals[0], * v1 = P->svals[1], * sc = P->scounts, * po = P->perm[nxt];
+		double * Fo = P->Fs[nxt];
+		void * args[] = {(void *) &Fc, (void *) &N, (void *) &range, (void *) &k0, (void *) &v0, (void *) &k1, (void *) &v1, (void *) &sc, (void *) &S,
+		                 (void *) &Fo, (void *) &po};
+		PNOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *) ga_sort_kernel, dim3(P->sort_grid), dim3(kSortThreads), args, 0, ctx->stream));
+		ctx->launches++;
+	}
+	PNOL_LAUNCH(ctx, ga_finish_kernel, 1, 32, 0, S, P->Fs[nxt], NeliteMut * n, n,
+	            ga->stream_values ? (unsigned long long) ga->stream.n_values : ~0ULL);
+	PNOL_CUDA(ctx, cudaMemcpyAsync(P->status_host, S, sizeof(GaDevStatus), cudaMemcpyDeviceToHost, ctx->stream));
+	return PNOL_OK;
+}
+
+// Source/GeneticAlgorithmMPI.cpp:87-249 (one pass of the while loop)
+int ga_pipe_generation(pnol_ga * ga)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	const int n = ga->n;
+	double scale = 1.0;
+	for (int attempt = 0;; attempt++) {
+		PNOL_CHECK(pipe_enqueue(ga, scale));
+		PNOL_CHECK(finish(ctx));
+		const GaDevStatus & H = *P->status_host;
+		P->tiles_dirty = H.cross_ticket;
+		if (H.error & kGaErrStream) {
+			PNOL_SET_ERR(ctx, "ga: the explicit random stream (%llu values) is exhausted", (unsigned long long) ga->stream.n_values);
+			return PNOL_ERR_STREAM;
+		}
+		if (H.error & kGaErrDegenerate) {
+			PNOL_SET_ERR(ctx, "ga: degenerate population (best and worst objective coincide or are not finite): selection cannot proceed");
+			return PNOL_ERR_NONFINITE;
+		}
+		if (H.error & kGaErrCrossWindow) { PNOL_SET_ERR(ctx, "ga: selection accepts (almost) no trial"); return PNOL_ERR_NONFINITE; }
+		if (H.error & kGaErrMutWindow) {
+			// the mutation window was too short for Nrand children: nothing has been committed, redo the generation with a longer one
+			if (attempt >= 6) { PNOL_SET_ERR(ctx, "ga: mutation selection accepts (almost) no trial"); return PNOL_ERR_NONFINITE; }
+			const double got = (double) std::max<long long>(H.mut_children, 1);
+			scale *= std::max(2.0, 1.3 * (double) ga->nrand / got);
+			continue;
+		}
+		// commit
+		if (ga->ncross > 0) P->accept_rate = (double) ga->ncross * n / (double) (H.cross_last_trial + 1);
+		else if (H.mut_last_q >= 0) {
+			const double g = (n % 2 == 0) ? 2.0 : 1.0;
+			const double per_child = (double) (H.mut_last_q + 2 + n) / (double) ga->nrand;       // n + 2 / rate
+			P->accept_rate = std::min(1.0, std::max(1e-3, 2.0 / std::max(per_child - n, 2.0)));
+			(void) g;
+		}
+		P->pos_elite_last = H.pos_elite;
+		P->elite_idx_complete = ctx->nranks <= 1;
+		P->cur ^= 1;
+		ga->pos = H.pos_end;
+		const double Fbest = H.fbest;
+		ga->f_best = Fbest;
+		if (Fbest == ga->f_best_prev) ga->n_static++; else ga->n_static = 0;                    // (:234-249)
+		if (ga->n_static > ga->prm.n_static_generations) { ga->stopped = 1; return PNOL_OK; }
+		ga->f_best_prev = Fbest;
+		ga->generation++;
+		return PNOL_OK;
+	}
+}
+
+int ga_pipe_get_population(pnol_ga * ga, double * xpop, double * F)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	const long long Npop = ga->prm.npop;
+	const int n = ga->n;
+	if (xpop) {
+		// sorted rows into the (otherwise idle) full-size buffer of the stage-by-stage path
+		PNOL_LAUNCH(ctx, ga_gather_sorted_kernel, blocks_for(Npop * 32, 256), 256, 0, P->table[P->cur], P->perm[P->cur], 0LL, Npop, n, ga->Xnew);
+		PNOL_CUDA(ctx, cudaMemcpyAsync(xpop, ga->Xnew, (size_t) Npop * n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+	}
+	if (F) PNOL_CUDA(ctx, cudaMemcpyAsync(F, P->Fs[P->cur], (size_t) Npop * sizeof(double), cudaMemcpyDefault, ctx->stream));
+	PNOL_CHECK(finish(ctx));
+	return PNOL_OK;
+}
+
+int ga_pipe_get_indices(pnol_ga * ga, int * cross_idx, int * mut_idx, int * elite_idx)
+{
+	pnol_ctx * ctx = ga->ctx;
+	GaPipe * P = ga->pipe;
+	if (elite_idx && !P->elite_idx_complete && ga->nelmut > 0) {
+		const long long count = (long long) ga->nelmut * ga->n;
+		PNOL_LAUNCH(ctx, ga_elite_idx_kernel, blocks_for(count, 256), 256, 0, pipe_stream(ga), P->pos_elite_last, count, ga->nelite, ga->elite_idx);
+		P->elite_idx_complete = true;
+	}
+	if (cross_idx) PNOL_CUDA(ctx, cudaMemcpyAsync(cross_idx, ga->cross_idx, (size_t) ga->ncross * ga->n * sizeof(int), cudaMemcpyDefault, ctx->stream));
+	if (mut_idx) PNOL_CUDA(ctx, cudaMemcpyAsync(mut_idx, ga->mut_idx, (size_t) ga->nrand * sizeof(int), cudaMemcpyDefault, ctx->stream));
+	if (elite_idx) PNOL_CUDA(ctx, cudaMemcpyAsync(elite_idx, ga->elite_idx, (size_t) ga->nelmut * ga->n * sizeof(int), cudaMemcpyDefault, ctx->stream));
+	return finish(ctx);
+}
+
+} // namespace pnol

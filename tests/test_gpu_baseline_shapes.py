@@ -26,6 +26,10 @@ def rel(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
 
 
+def chisq_bar(chisq, chisq0):
+    return TOL * chisq + 2.0 * np.sqrt(chisq) * TOL * np.sqrt(chisq0) + TOL * TOL * chisq0
+
+
 def q(case, k):
     return G["%s/%s" % (case, k)]
 
@@ -75,9 +79,11 @@ def test_lm_iterates_on_device_state_match_the_reference(ctx, case, stride):
     for k in range(iters):
         assert rel(rows[k, :n], want[k, :n]) <= TOL, "iterate %d" % k
     assert rel(X, q(case, "X")) <= TOL
-    # chi^2 falls by 15 or more decades on the zero-noise fit: compare each pass relative to chi^2 of the start point
+    # chi^2 = ||F||^2 falls by 20 decades on this zero-noise fit, so "relative to itself" stops meaning anything once F is the
+    # difference of nearly equal numbers. The bar that follows from residuals within TOL of the start residuals' norm:
+    # |d chi^2| <= 2 ||F|| ||dF|| + ||dF||^2 with ||dF|| <= TOL ||F0||  (plus TOL chi^2 itself)
     chi0 = float(np.dot(F0, F0))
-    assert np.all(np.abs(rows[:, n] - want[:, n]) <= TOL * np.maximum(want[:, n], 1e-16 * chi0))
+    assert np.all(np.abs(rows[:, n] - want[:, n]) <= chisq_bar(want[:, n], chi0))
     key0, key1 = ("F0", "F") if stride == 1 else ("F0_every%d" % stride, "F_every%d" % stride)
     assert np.array_equal(F0[::stride], q(case, key0)), "residuals at the start point are bit-exact"
     scale = np.linalg.norm(q(case, key0))
@@ -98,5 +104,5 @@ def test_levmarq_mpi_find_min_matches_the_reference(host, case, stride):
     scale = np.linalg.norm(q(case, key0))
     assert np.linalg.norm(np.array(r["F"][::stride]) - q(case, key1)) <= TOL * scale
     chi0 = float(np.dot(r["F0"], r["F0"]))
-    assert abs(r["chiSq"] - float(q(case, "chisq"))) <= TOL * max(float(q(case, "chisq")), 1e-16 * chi0)
+    assert abs(r["chiSq"] - float(q(case, "chisq"))) <= chisq_bar(float(q(case, "chisq")), chi0)
     prob.close()

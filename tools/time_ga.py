@@ -33,7 +33,7 @@ t1 = time.perf_counter()
 st = ga.status()
 print("npop=%d n=%d: %.3f ms/generation wall, f_best %.6f, stream_pos %d, sizes %d/%d/%d/%d" % (
     npop, n, (t1 - t0) * 1e3 / gens, st.f_best, st.stream_pos, st.n_elite, st.n_elite_mut, st.n_cross, st.n_rand))
-for name in ("ga_fitness", "ga_crossover", "ga_mutation", "ga_elite_mutation", "ga_check_identical", "ga_check_bounds", "ga_pop_sort", "eval_batch"):
+for name in ("ga_prep", "ga_fitness", "ga_crossover", "ga_mutation", "ga_elite_mutation", "ga_check_identical", "ga_check_bounds", "ga_pop_sort", "eval_batch"):
     ms, cnt = ctx.timer_get(name)
     if cnt:
         print("  %-20s %8.3f ms avg (%d)" % (name, ms / cnt, cnt))
