@@ -21,7 +21,14 @@ struct StreamDev {
 			if (k >= n_values) { if (exhausted) *exhausted = 1; return 0.0; }    // exhausted == nullptr: speculative reads (ga_pipeline.cu)
 			return values[k];
 		}
-		unsigned long long z = seed + (k + 1ULL) * 0x9E3779B97F4A7C15ULL;
+		return from_state(state(k));
+	}
+	// counter mode in two steps, for loops over equally spaced positions: state(k + d) = state(k) + d * kGamma saves the 64-bit
+	// multiply of the first step (a quarter of the generator's integer work, which is what the selection kernels are bound by)
+	static constexpr unsigned long long kGamma = 0x9E3779B97F4A7C15ULL;
+	__device__ __forceinline__ unsigned long long state(unsigned long long k) const { return seed + (k + 1ULL) * kGamma; }
+	__device__ __forceinline__ double from_state(unsigned long long z) const
+	{
 		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
 		z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
 		z = z ^ (z >> 31);
@@ -64,10 +71,13 @@ struct RowTable {
 	const double * base[kGaMaxRanks];
 	long long per;
 	int n;
-	__device__ __forceinline__ const double * row(long long r) const
+	int nranks;
+	// (row numbers fit 32 bits: a 64-bit division here cost more than the gene fetch it addresses)
+	__device__ __forceinline__ const double * row(unsigned r) const
 	{
-		const long long o = r / per;
-		return base[o] + (r - o * per) * n;
+		if (nranks <= 1) return base[0] + (size_t) r * n;
+		const unsigned o = r / (unsigned) per;
+		return base[o] + (size_t) (r - o * (unsigned) per) * n;
 	}
 };
 

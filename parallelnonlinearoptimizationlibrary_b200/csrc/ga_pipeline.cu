@@ -50,17 +50,12 @@ struct GaDevStatus {
 	double fbest;
 	double max_fitness;
 	int error;
-	unsigned int cross_ticket;          // tiles handed out by the crossover kernel
-	int cross_done;
+	unsigned int pad0;
+	int pad1;
 	unsigned int nsuspect;              // rows whose hash matched a later row that is NOT equal (exhaustive check)
 	int sort_result_in_alt;             // which buffer the radix sort ended in
 	int pad;
 };
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long * p)
-{
-	return *((const volatile unsigned long long *) p);
-}
 
 // index of the selection trial at stream position q (Source/GeneticAlgorithmMPI.cpp:134-144): round(u(q) Npop); 0 = rejected.
 // ratio[k] = fitness[k] / maxFitness is tabulated once per generation (the same IEEE division, 1M instead of ~40M times)
@@ -68,6 +63,15 @@ __device__ __forceinline__ int pipe_trial(const StreamDev & st, unsigned long lo
 {
 	const int randomIndex = (int) round(st.u(q) * Npop);
 	const double selectValue = st.u(q + 1);
+	if (randomIndex <= 0 || randomIndex >= Npop) return 0;
+	return (selectValue <= ratio[randomIndex]) ? randomIndex : 0;
+}
+
+// the same for a counter stream whose state at position q is at hand (the second draw's state is one increment on)
+__device__ __forceinline__ int pipe_trial_state(const StreamDev & st, unsigned long long z, const double * __restrict__ ratio, int Npop)
+{
+	const int randomIndex = (int) round(st.from_state(z) * Npop);
+	const double selectValue = st.from_state(z + StreamDev::kGamma);
 	if (randomIndex <= 0 || randomIndex >= Npop) return 0;
 	return (selectValue <= ratio[randomIndex]) ? randomIndex : 0;
 }
@@ -95,8 +99,24 @@ ga_prep_kernel(const double * __restrict__ Fs, int Npop, int Nelite, double * __
 		S->ndup = 0; S->noob = 0; S->pos_end = 0; S->fbest = 0; S->max_fitness = maxFitness;
 		// every trial would compare against NaN / inf: the reference spins forever in its while loops
 		S->error = (!(maxFitness > 0) || isinf(maxFitness)) ? kGaErrDegenerate : 0;
-		S->cross_ticket = 0; S->cross_done = 0; S->nsuspect = 0; S->sort_result_in_alt = 0;
+		S->nsuspect = 0; S->sort_result_in_alt = 0;
 	}
+}
+
+// Row kernels: a warp holds FOUR rows, eight lanes each (lane g of a group takes genes g, g + 8, ...). With one row per warp a
+// warp had a single 256-byte request in flight behind three dependent look-ups (child -> parent index -> perm -> row): these
+// kernels ran at the latency of that chain, 0.07-0.2 ms each at 1M x 32. Four independent chains per warp instead.
+constexpr int kRowLanes = 8;
+constexpr int kRowsPerBlock = 256 / kRowLanes;
+__device__ __forceinline__ unsigned long long group_sum(unsigned long long v)
+{
+	v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+	return v;
+}
+__device__ __forceinline__ unsigned group_sum(unsigned v)
+{
+	v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+	return v;
 }
 
 // elite rows (:108-118): child row k = sorted row k, for the rows this rank owns; the row hash travels with the row
@@ -105,133 +125,177 @@ ga_elite_copy_kernel(RowTable cur, const unsigned * __restrict__ perm, const uns
                      long long hi, int n, double * __restrict__ Xloc, unsigned long long * __restrict__ hash_new,
                      unsigned * __restrict__ bcount)
 {
-	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
+	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int g = threadIdx.x % kRowLanes;
 	if (row >= hi) return;
 	const unsigned from = perm[row];
 	const double * s = cur.row(from);
 	double * d = Xloc + (row - lo) * n;
-	for (int j = lane; j < n; j += 32) d[j] = __ldcg(s + j);
-	if (lane == 0) { hash_new[row] = hash_cur[from]; bcount[row] = 0; }
+	for (int j = g; j < n; j += kRowLanes) d[j] = __ldcg(s + j);
+	if (g == 0) { hash_new[row] = hash_cur[from]; bcount[row] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 1. crossover (:128-153) in one kernel
+// 1. crossover (:128-153) in one cooperative kernel. Trial t uses the draws (pos + 2t, pos + 2t + 1) whatever its outcome, and the
+// g-th gene (child g / n, gene g % n) takes the g-th ACCEPTED trial. Per round every CTA owns a contiguous range of trials:
+//   phase 1  evaluate the range, keep the acceptance bits in shared memory, publish the range's count;
+//   -------  grid barrier: every CTA adds up the counts of the ranges before it (a few hundred values) = its first rank;
+//   phase 2  walk the bits in chunks: accepted trials are compacted in rank order into shared memory, then all threads fetch the
+//            parent genes (random reads) and write children and indices with consecutive threads on consecutive ranks.
+// Rounds repeat until `need` genes are filled (the range length comes from the measured acceptance rate, so normally once).
+// A first version ranked tiles with a chained look-back prefix instead: with ~900 tiles in flight every tile summed up to 28
+// batches of predecessors before it could write, 0.41 ms; the barrier costs 3 us.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kCrossThreads = 256;
-constexpr int kCrossPer = 16;
-constexpr int kCrossTile = kCrossThreads * kCrossPer;          // trials per tile
-constexpr unsigned long long kDescAgg = 1ULL << 62, kDescPre = 2ULL << 62, kDescMask = (1ULL << 62) - 1;
+constexpr int kCrossThreads = 512;
+constexpr int kCrossChunkWords = 256;                          // words (32 trials each) compacted at a time
+constexpr int kCrossMaxWords = 6144;                           // per CTA and round (dynamic shared memory: 8 bytes per word)
 
 __global__ void __launch_bounds__(kCrossThreads)
-ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __restrict__ ratio, int Npop, long long need,
-                unsigned max_tiles, unsigned long long * __restrict__ desc, int * __restrict__ sel, RowTable cur,
+ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __restrict__ ratio, int Npop, long long need, int W,
+                int max_rounds, unsigned long long * __restrict__ cta_counts, int * __restrict__ sel, RowTable cur,
                 const unsigned * __restrict__ perm, int n, double * __restrict__ Xloc, long long own_lo, long long own_hi,
                 long long row0)
 {
 	// own_lo / own_hi: child rows of the whole new population this rank owns; crossover child c is row row0 + c
-	__shared__ int s_idx[kCrossTile];
-	__shared__ unsigned s_warp[kCrossThreads / 32];
-	__shared__ unsigned s_tile;
-	__shared__ int s_done;
-	__shared__ unsigned long long s_prefix;
-	__shared__ unsigned s_agg;
-	if (S->error) return;
+	cg::grid_group grid = cg::this_grid();
+	extern __shared__ unsigned cross_sm[];
+	unsigned * s_bits = cross_sm;                                // W acceptance words
+	unsigned * s_woff = cross_sm + W;                            // W: exclusive prefix of the words' popcounts inside the CTA
+	unsigned short * s_list = (unsigned short *) (cross_sm + 2 * W);   // accepted trials of a chunk (offset inside the chunk), rank order
+	__shared__ unsigned long long s_red[kCrossThreads / 32];
+	__shared__ unsigned long long s_before, s_total;
+	if (S->error) return;                                        // set before the launch: uniform over the grid
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int G = gridDim.x, cta = blockIdx.x;
 	const unsigned long long pos = S->pos0;
-	for (;;) {
-		__syncthreads();                                   // s_idx / s_tile of the previous tile are no longer read
-		if (tid == 0) { s_tile = atomicAdd(&S->cross_ticket, 1u); s_done = *((volatile int *) &S->cross_done); }
+	unsigned long long done = 0;                                 // ranks filled by earlier rounds
+	for (int pass = 0; pass < max_rounds; pass++) {
+		const long long tb = ((long long) pass * G + cta) * (long long) W * 32;      // first trial of this CTA's range
+		// ---- phase 1: acceptance bits and count of the range ----
+		unsigned cnt = 0;
+		if (st.values == nullptr) {
+			// counter stream: the generator state of the lane's trial advances by a constant from word to word
+			unsigned long long z = st.state(pos + 2ULL * (unsigned long long) (tb + (long long) warp * 32 + lane));
+			const unsigned long long dz = (unsigned long long) (2 * 32 * (kCrossThreads / 32)) * StreamDev::kGamma;
+			int w = warp;
+			for (; w + kCrossThreads / 32 < W; w += 2 * (kCrossThreads / 32), z += 2 * dz) {
+				// two independent trials per lane in flight: the ratio look-up of one hides behind the arithmetic of the other
+				const bool acc0 = pipe_trial_state(st, z, ratio, Npop) != 0;
+				const bool acc1 = pipe_trial_state(st, z + dz, ratio, Npop) != 0;
+				const unsigned m0 = __ballot_sync(0xffffffffu, acc0), m1 = __ballot_sync(0xffffffffu, acc1);
+				if (lane == 0) { s_bits[w] = m0; s_bits[w + kCrossThreads / 32] = m1; }
+				cnt += __popc(m0) + __popc(m1);                  // the same in every lane
+			}
+			for (; w < W; w += kCrossThreads / 32, z += dz) {
+				const bool acc = pipe_trial_state(st, z, ratio, Npop) != 0;
+				const unsigned m = __ballot_sync(0xffffffffu, acc);
+				if (lane == 0) s_bits[w] = m;
+				cnt += __popc(m);
+			}
+		} else {
+			for (int w = warp; w < W; w += kCrossThreads / 32) {
+				const long long t = tb + (long long) w * 32 + lane;
+				const bool acc = pipe_trial(st, pos + 2ULL * (unsigned long long) t, ratio, Npop) != 0;
+				const unsigned m = __ballot_sync(0xffffffffu, acc);
+				if (lane == 0) s_bits[w] = m;
+				cnt += __popc(m);
+			}
+		}
+		if (lane == 0) s_red[warp] = cnt;
 		__syncthreads();
-		const unsigned tile = s_tile;
-		const int done = s_done;                           // one reading for the whole block: the exits below must be uniform
-		if (tile >= max_tiles) {
-			if (tid == 0 && !done) atomicOr(&S->error, kGaErrCrossWindow);
-			return;
+		if (tid == 0) {
+			unsigned long long c = 0;
+			for (int w = 0; w < kCrossThreads / 32; w++) c += s_red[w];
+			cta_counts[cta] = c;
 		}
-		if (done) {
-			// every rank this tile could hold lies past the last child: tell whoever looks back and leave
-			if (tid == 0) { __threadfence(); atomicExch(&desc[tile], kDescPre | (unsigned long long) need); }
-			return;
+		grid.sync();
+		// ---- first rank of this range = ranks of earlier rounds + counts of the ranges before it ----
+		{
+			unsigned long long before = 0, total = 0;
+			for (int c = tid; c < G; c += kCrossThreads) { const unsigned long long v = cta_counts[c]; total += v; if (c < cta) before += v; }
+			for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+			__syncthreads();                                     // s_red of phase 1 has been read
+			if (lane == 0) { s_red[warp] = before; }
+			__syncthreads();
+			if (tid == 0) { unsigned long long b = 0; for (int w = 0; w < kCrossThreads / 32; w++) b += s_red[w]; s_before = b; }
+			__syncthreads();
+			if (lane == 0) { s_red[warp] = total; }
+			__syncthreads();
+			if (tid == 0) { unsigned long long b = 0; for (int w = 0; w < kCrossThreads / 32; w++) b += s_red[w]; s_total = b; }
+			__syncthreads();
 		}
-		// ---- evaluate the tile's trials: thread t owns trials [t 16, t 16 + 16) of the tile, so thread order is trial order ----
-		const long long t0 = (long long) tile * kCrossTile + (long long) tid * kCrossPer;
-		int idx[kCrossPer];
-		unsigned c = 0;
+		const unsigned long long first = done + s_before;
+		const unsigned long long total = s_total;
+		if (first < (unsigned long long) need) {
+			// ---- exclusive prefix of the word popcounts (thread t owns words [t per, t per + per)) ----
+			const int per = (W + kCrossThreads - 1) / kCrossThreads;
+			unsigned loc = 0;
+			for (int e = 0; e < per; e++) { const int w = tid * per + e; if (w < W) loc += __popc(s_bits[w]); }
+			unsigned incl = loc;
 #pragma unroll
-		for (int e = 0; e < kCrossPer; e++) {
-			idx[e] = pipe_trial(st, pos + 2ULL * (unsigned long long) (t0 + e), ratio, Npop);
-			c += idx[e] != 0;
-		}
-		// ---- block-wide exclusive scan of the counts ----
-		unsigned incl = c;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-		if (lane == 31) s_warp[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			unsigned w = lane < kCrossThreads / 32 ? s_warp[lane] : 0;
-			unsigned wi = w;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-			if (lane < kCrossThreads / 32) s_warp[lane] = wi - w;          // exclusive warp offsets
-			const unsigned agg = __shfl_sync(0xffffffffu, wi, kCrossThreads / 32 - 1);
-			// ---- chained prefix over the tiles (tickets are handed out in tile order: every earlier tile is running or done) ----
-			unsigned long long prefix = 0;
-			if (tile > 0) {
-				if (lane == 0) { __threadfence(); atomicExch(&desc[tile], kDescAgg | (unsigned long long) agg); }
-				long long look = (long long) tile - 1;
-				for (;;) {
-					const long long j = look - lane;
-					unsigned long long d = kDescPre;                       // before tile 0: prefix 0
-					if (j >= 0) { do { d = ld_volatile_u64(&desc[j]); } while ((d >> 62) == 0); }
-					const unsigned has_pre = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-					const int first = has_pre ? __ffs(has_pre) - 1 : 32;   // nearest predecessor that knows its prefix
-					unsigned long long v = (lane <= first) ? (d & kDescMask) : 0;
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-					prefix += v;
-					if (has_pre) break;
-					look -= 32;
+			for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+			__syncthreads();
+			if (lane == 31) s_red[warp] = incl;
+			__syncthreads();
+			if (tid == 0) { unsigned long long run = 0; for (int w = 0; w < kCrossThreads / 32; w++) { const unsigned long long v = s_red[w]; s_red[w] = run; run += v; } }
+			__syncthreads();
+			unsigned run = (unsigned) s_red[warp] + incl - loc;
+			for (int e = 0; e < per; e++) { const int w = tid * per + e; if (w < W) { s_woff[w] = run; run += __popc(s_bits[w]); } }
+			__syncthreads();
+			// ---- phase 2: chunks of 256 words ----
+			for (int c0 = 0; c0 < W; c0 += kCrossChunkWords) {
+				const int c1 = c0 + kCrossChunkWords < W ? c0 + kCrossChunkWords : W;
+				const unsigned coff = s_woff[c0];
+				if (first + coff >= (unsigned long long) need) break;                        // uniform
+				const unsigned cend = c1 < W ? s_woff[c1] : s_woff[W - 1] + __popc(s_bits[W - 1]);
+				for (int w = c0 + warp; w < c1; w += kCrossThreads / 32) {
+					const unsigned m = s_bits[w];
+					if ((m >> lane) & 1u) s_list[s_woff[w] - coff + __popc(m & ((1u << lane) - 1))] = (unsigned short) ((w - c0) * 32 + lane);
 				}
-			}
-			if (prefix > (unsigned long long) need) prefix = (unsigned long long) need;
-			unsigned long long inclusive = prefix + agg;
-			if (inclusive > (unsigned long long) need) inclusive = (unsigned long long) need;    // saturate: ranks past `need` are never used
-			if (lane == 0) {
-				__threadfence();
-				atomicExch(&desc[tile], kDescPre | inclusive);
-				if (inclusive >= (unsigned long long) need) *((volatile int *) &S->cross_done) = 1;
-				s_prefix = prefix; s_agg = agg;
-			}
-		}
-		__syncthreads();
-		const unsigned long long prefix = s_prefix;
-		if (prefix >= (unsigned long long) need) return;           // nothing of this tile is used, nor of any later one
-		// ---- accepted trials in rank order -> shared memory ----
-		unsigned l = s_warp[warp] + incl - c;
+				__syncthreads();
+				const unsigned long long left = (unsigned long long) need - (first + coff);
+				const unsigned used = (unsigned long long) (cend - coff) < left ? (cend - coff) : (unsigned) left;
+				// XpopNew[popIdx][i] = Xpop[indices[i]][i]  (:147-150): rank r is gene r % n of child r / n. One 64-bit division per
+				// chunk, 32-bit arithmetic per element
+				const long long r0 = (long long) (first + coff);
+				const long long child0 = r0 / n;
+				const unsigned gene0 = (unsigned) (r0 - child0 * n);
+				for (unsigned e0 = tid; e0 < used; e0 += 4 * kCrossThreads) {
+					// four independent chains (draw -> perm -> gene) per thread
+					int parent[4];
+					unsigned slot[4];
 #pragma unroll
-		for (int e = 0; e < kCrossPer; e++) {
-			if (idx[e]) {
-				s_idx[l] = idx[e];
-				if (prefix + l == (unsigned long long) need - 1) S->cross_last_trial = t0 + e;
-				l++;
+					for (int u = 0; u < 4; u++) {
+						const unsigned e = e0 + u * kCrossThreads;
+						parent[u] = 0;
+						if (e < used) {
+							const long long t = tb + (long long) c0 * 32 + s_list[e];
+							parent[u] = (int) round(st.u(pos + 2ULL * (unsigned long long) t) * Npop);
+							if (r0 + e == need - 1) S->cross_last_trial = t;
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < 4; u++) slot[u] = perm[parent[u]];
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const unsigned e = e0 + u * kCrossThreads;
+						if (e < used) {
+							sel[r0 + e] = parent[u];
+							const unsigned ge = gene0 + e, dc = ge / (unsigned) n;
+							const unsigned gene = ge - dc * (unsigned) n;
+							const long long row = row0 + child0 + dc;
+							if (row >= own_lo && row < own_hi) Xloc[(row - own_lo) * n + gene] = __ldcg(cur.row(slot[u]) + gene);
+						}
+					}
+				}
+				__syncthreads();
 			}
 		}
-		__syncthreads();
-		// ---- XpopNew[popIdx][i] = Xpop[indices[i]][i]  (:147-150): rank r is gene r % n of child r / n ----
-		const unsigned long long left = (unsigned long long) need - prefix;
-		const unsigned used = (unsigned long long) s_agg < left ? s_agg : (unsigned) left;
-		for (unsigned e = tid; e < used; e += kCrossThreads) {
-			const long long r = (long long) prefix + e;
-			const int parent = s_idx[e];
-			sel[r] = parent;
-			const long long child = r / n;
-			const int gene = (int) (r - child * n);
-			const long long row = row0 + child;
-			if (row >= own_lo && row < own_hi) Xloc[(row - own_lo) * n + gene] = __ldcg(cur.row(perm[parent]) + gene);
-		}
+		done += total;
+		if (done >= (unsigned long long) need) return;           // the same `total` in every CTA: uniform
+		grid.sync();                                             // cta_counts is rewritten by the next round
 	}
+	if (cta == 0 && tid == 0) atomicOr(&S->error, kGaErrCrossWindow);
 }
 
 // row hash (and a zero box count: every gene of a crossover child is a parent's gene, which is inside the box) of rows [lo, hi)
@@ -239,14 +303,16 @@ __global__ void __launch_bounds__(256)
 ga_rows_hash_kernel(const double * __restrict__ Xloc, long long own_lo, long long lo, long long hi, int n,
                     unsigned long long * __restrict__ hash_new, unsigned * __restrict__ bcount)
 {
-	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
-	if (row >= hi) return;
-	const double * x = Xloc + (row - own_lo) * n;
+	const long long row = lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int g = threadIdx.x % kRowLanes;
+	const bool live = row < hi;
 	unsigned long long h = 0;
-	for (int j = lane; j < n; j += 32) h += gene_hash(x[j], j);
-	for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-	if (lane == 0) { hash_new[row] = h; if (bcount) bcount[row] = 0; }
+	if (live) {
+		const double * x = Xloc + (row - own_lo) * n;
+		for (int j = g; j < n; j += kRowLanes) h += gene_hash(x[j], j);
+	}
+	h = group_sum(h);
+	if (live && g == 0) { hash_new[row] = h; if (bcount) bcount[row] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -272,7 +338,7 @@ __device__ __forceinline__ unsigned long long mut_stage_pos(const GaDevStatus * 
 __global__ void __launch_bounds__(kMutThreads)
 ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const double * __restrict__ ratio, int Npop, MutGeom G,
                      unsigned * __restrict__ accbits, int * __restrict__ sub_exit, int * __restrict__ sub_cnt,
-                     int * __restrict__ cta_exit, long long * __restrict__ cta_cnt)
+                     int * __restrict__ cta_exit, int * __restrict__ cta_cnt)
 {
 	extern __shared__ unsigned mut_sm[];
 	if (S->error) return;
@@ -283,11 +349,21 @@ ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const dou
 	int * t_cnt = t_exit + G.nsub * G.SD;                            // nsub x SD
 	const unsigned long long P1 = mut_stage_pos(S);
 	const long long cand0 = (long long) blockIdx.x * G.nsub * kMutSub;
-	for (int w = tid >> 5; w < words; w += kMutThreads / 32) {
-		const long long j = cand0 + (long long) w * 32 + lane;
-		const bool acc = pipe_trial(st, P1 + (unsigned long long) G.g * (unsigned long long) j, ratio, Npop) != 0;
-		const unsigned m = __ballot_sync(0xffffffffu, acc);
-		if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
+	if (st.values == nullptr) {
+		unsigned long long z = st.state(P1 + (unsigned long long) G.g * (unsigned long long) (cand0 + (long long) (tid >> 5) * 32 + lane));
+		const unsigned long long dz = (unsigned long long) (G.g * 32 * (kMutThreads / 32)) * StreamDev::kGamma;
+		for (int w = tid >> 5; w < words; w += kMutThreads / 32, z += dz) {
+			const bool acc = pipe_trial_state(st, z, ratio, Npop) != 0;
+			const unsigned m = __ballot_sync(0xffffffffu, acc);
+			if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
+		}
+	} else {
+		for (int w = tid >> 5; w < words; w += kMutThreads / 32) {
+			const long long j = cand0 + (long long) w * 32 + lane;
+			const bool acc = pipe_trial(st, P1 + (unsigned long long) G.g * (unsigned long long) j, ratio, Npop) != 0;
+			const unsigned m = __ballot_sync(0xffffffffu, acc);
+			if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
+		}
 	}
 	__syncthreads();
 	for (int e = tid; e < G.nsub * G.SD; e += kMutThreads) {
@@ -304,7 +380,7 @@ ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const dou
 	__syncthreads();
 	for (int d0 = tid; d0 < G.SD; d0 += kMutThreads) {
 		int d = d0;
-		long long cnt = 0;
+		int cnt = 0;
 		for (int sub = 0; sub < G.nsub; sub++) {
 			if (d >= kMutSub) { d -= kMutSub; continue; }            // a jump longer than a sub-block (n + 2 > 1024 g)
 			cnt += t_cnt[sub * G.SD + d];
@@ -315,24 +391,64 @@ ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const dou
 	}
 }
 
-// one thread: entry offset and first child of every CTA; children the window reaches
-__global__ void ga_mut_compose_kernel(GaDevStatus * __restrict__ S, MutGeom G, const int * __restrict__ cta_exit,
-                                      const long long * __restrict__ cta_cnt, int * __restrict__ cta_entry,
-                                      long long * __restrict__ cta_base, long long Nrand)
+// entry offset and first child of every CTA; children the window reaches. Composition of the CTA tables in two levels out of
+// shared memory: segments of 32 CTAs are composed for every entry offset in parallel, one thread walks the segments, then one
+// thread per segment walks its CTAs. (One thread walking all CTA tables in global memory paid an L2 round trip per CTA: 0.2 ms.)
+constexpr int kMutSeg = 32;
+__global__ void __launch_bounds__(1024)
+ga_mut_compose_kernel(GaDevStatus * __restrict__ S, MutGeom G, const int * __restrict__ cta_exit, const int * __restrict__ cta_cnt,
+                      int * __restrict__ cta_entry, long long * __restrict__ cta_base, long long Nrand, int in_smem)
 {
+	extern __shared__ int compose_sm[];
 	if (S->error) return;
-	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	int d = 0;
-	long long cnt = 0;
-	const long long span = (long long) G.nsub * kMutSub;
-	for (int c = 0; c < G.nctas; c++) {
-		cta_entry[c] = d; cta_base[c] = cnt;
-		if (d >= span || d >= G.SD) { d -= (int) span; if (d < 0) d = 0; continue; }     // unreachable: SD <= span by construction
-		cnt += cta_cnt[(size_t) c * G.SD + d];
-		d = cta_exit[(size_t) c * G.SD + d];
+	const size_t total = (size_t) G.nctas * G.SD;
+	const int nseg = (G.nctas + kMutSeg - 1) / kMutSeg;
+	int * s_cnt = compose_sm;                                        // nctas x SD   (only with in_smem)
+	int * s_exit = compose_sm + (in_smem ? total : 0);               // nctas x SD
+	int * g_exit = s_exit + (in_smem ? total : 0);                   // nseg x SD: segment tables
+	long long * g_cnt = (long long *) (g_exit + (((size_t) nseg * G.SD + 1) & ~(size_t) 1));      // nseg x SD
+	int * seg_entry = (int *) (g_cnt + (size_t) nseg * G.SD);        // nseg
+	long long * seg_base = (long long *) (seg_entry + ((nseg + 1) & ~1));                          // nseg
+	if (in_smem) {
+		for (size_t e = threadIdx.x; e < total; e += blockDim.x) { s_cnt[e] = cta_cnt[e]; s_exit[e] = cta_exit[e]; }
+		__syncthreads();
 	}
-	S->mut_children = cnt;
-	if (cnt < Nrand) atomicOr(&S->error, kGaErrMutWindow);
+	const int * cnt_t = in_smem ? s_cnt : cta_cnt;
+	const int * exit_t = in_smem ? s_exit : cta_exit;
+	const long long span = (long long) G.nsub * kMutSub;
+	// a jump longer than a CTA's span cannot happen: SD <= span by construction (ga_pipe_enqueue)
+	for (int e = threadIdx.x; e < nseg * G.SD; e += blockDim.x) {
+		const int seg = e / G.SD;
+		int d = e - seg * G.SD;
+		long long cnt = 0;
+		const int c1 = min(G.nctas, (seg + 1) * kMutSeg);
+		for (int c = seg * kMutSeg; c < c1; c++) { cnt += cnt_t[(size_t) c * G.SD + d]; d = exit_t[(size_t) c * G.SD + d]; }
+		g_exit[e] = d; g_cnt[e] = cnt;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int d = 0;
+		long long cnt = 0;
+		for (int seg = 0; seg < nseg; seg++) {
+			seg_entry[seg] = d; seg_base[seg] = cnt;
+			cnt += g_cnt[seg * G.SD + d];
+			d = g_exit[seg * G.SD + d];
+		}
+		S->mut_children = cnt;
+		if (cnt < Nrand) atomicOr(&S->error, kGaErrMutWindow);
+	}
+	__syncthreads();
+	for (int seg = threadIdx.x; seg < nseg; seg += blockDim.x) {
+		int d = seg_entry[seg];
+		long long cnt = seg_base[seg];
+		const int c1 = min(G.nctas, (seg + 1) * kMutSeg);
+		for (int c = seg * kMutSeg; c < c1; c++) {
+			cta_entry[c] = d; cta_base[c] = cnt;
+			cnt += cnt_t[(size_t) c * G.SD + d];
+			d = exit_t[(size_t) c * G.SD + d];
+		}
+	}
+	(void) span;
 }
 
 // every sub-block walks from its entry offset and records (stream offset of the accepted trial, parent index) of its children
@@ -344,28 +460,37 @@ ga_mut_emit_kernel(StreamDev st, GaDevStatus * __restrict__ S, int Npop, int n, 
 {
 	extern __shared__ int emit_sm[];
 	if (S->error) return;
+	const int words = G.nsub * (kMutSub / 32);
 	int * s_entry = emit_sm;                                         // nsub
-	long long * s_base = (long long *) (emit_sm + ((G.nsub + 1) & ~1));
+	long long * s_base = (long long *) (emit_sm + ((G.nsub + 1) & ~1));      // nsub
+	unsigned * s_bits = (unsigned *) (s_base + G.nsub);              // words
 	const long long base0 = cta_base[blockIdx.x];
 	if (base0 >= Nrand) return;
+	int * s_texit = (int *) (s_bits + words);                        // nsub x SD
+	int * s_tcnt = s_texit + G.nsub * G.SD;                          // nsub x SD
+	for (int w = threadIdx.x; w < words; w += kMutThreads) s_bits[w] = accbits[(size_t) blockIdx.x * words + w];
+	for (int e = threadIdx.x; e < G.nsub * G.SD; e += kMutThreads) {
+		s_texit[e] = sub_exit[(size_t) blockIdx.x * G.nsub * G.SD + e];
+		s_tcnt[e] = sub_cnt[(size_t) blockIdx.x * G.nsub * G.SD + e];
+	}
+	__syncthreads();
 	if (threadIdx.x == 0) {
+		// entry offsets of the sub-blocks: a serial walk, so out of shared memory (from global memory every step was an L2 round trip)
 		int d = cta_entry[blockIdx.x];
 		long long cnt = base0;
 		for (int sub = 0; sub < G.nsub; sub++) {
 			s_entry[sub] = d; s_base[sub] = cnt;
 			if (d >= kMutSub) { d -= kMutSub; continue; }
-			const size_t e = ((size_t) blockIdx.x * G.nsub + sub) * G.SD + d;
-			cnt += sub_cnt[e];
-			d = sub_exit[e];
+			cnt += s_tcnt[sub * G.SD + d];
+			d = s_texit[sub * G.SD + d];
 		}
 	}
 	__syncthreads();
 	const unsigned long long P1 = mut_stage_pos(S);
-	const int words = G.nsub * (kMutSub / 32);
 	for (int sub = threadIdx.x; sub < G.nsub; sub += kMutThreads) {
 		long long k = s_base[sub];
 		if (k >= Nrand) continue;
-		const unsigned * b = accbits + (size_t) blockIdx.x * words + sub * (kMutSub / 32);
+		const unsigned * b = s_bits + sub * (kMutSub / 32);
 		const long long cand0 = ((long long) blockIdx.x * G.nsub + sub) * kMutSub;
 		int j = s_entry[sub];
 		while (j < kMutSub && k < Nrand) {
@@ -394,25 +519,26 @@ ga_mut_apply_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable c
                     unsigned * __restrict__ bcount)
 {
 	if (S->error) return;
-	const long long k = k_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
-	if (k >= k_hi) return;
-	const unsigned long long P1 = mut_stage_pos(S);
-	const unsigned long long q = P1 + (unsigned long long) child_q[k] + 2ULL;
-	const double * src = cur.row(perm[child_idx[k]]);
-	const long long row = row0 + k;
-	double * dst = Xloc + (row - own_lo) * n;
+	const long long k = k_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int g = threadIdx.x % kRowLanes;
+	const bool live = k < k_hi;
 	unsigned long long h = 0;
 	unsigned oob = 0;
-	for (int j = lane; j < n; j += 32) {
-		const double mutation = spreadRatio * (ub[j] - lb[j]) * st.u(q + (unsigned long long) j);
-		const double v = __ldcg(src + j) + mutation;
-		dst[j] = v;
-		h += gene_hash(v, j);
-		oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+	const long long row = row0 + k;
+	if (live) {
+		const unsigned long long q = mut_stage_pos(S) + (unsigned long long) child_q[k] + 2ULL;
+		const double * src = cur.row(perm[child_idx[k]]);
+		double * dst = Xloc + (row - own_lo) * n;
+		for (int j = g; j < n; j += kRowLanes) {
+			const double mutation = spreadRatio * (ub[j] - lb[j]) * st.u(q + (unsigned long long) j);
+			const double v = __ldcg(src + j) + mutation;
+			dst[j] = v;
+			h += gene_hash(v, j);
+			oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+		}
 	}
-	for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); oob += __shfl_xor_sync(0xffffffffu, oob, o); }
-	if (lane == 0) { hash_new[row] = h; bcount[row] = oob; }
+	h = group_sum(h); oob = group_sum(oob);
+	if (live && g == 0) { hash_new[row] = h; bcount[row] = oob; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -426,26 +552,28 @@ ga_elite_mut_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable c
                     int * __restrict__ elite_idx)
 {
 	if (S->error) return;
-	const long long c = c_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
-	if (c >= c_hi) return;
-	const unsigned long long P2 = S->pos_elite;
+	const long long c = c_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int g = threadIdx.x % kRowLanes;
+	const bool live = c < c_hi;
 	const long long row = row0 + c;
-	double * dst = Xloc + (row - own_lo) * n;
 	unsigned long long h = 0;
 	unsigned oob = 0;
-	for (int j = lane; j < n; j += 32) {
-		const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
-		const int randomEliteIdx = (int) round(st.u(P2 + 2ULL * e) * Nelite);
-		const double mutation = eliteMutationSize * (ub[j] - lb[j]) * st.u(P2 + 2ULL * e + 1ULL);
-		const double v = __ldcg(cur.row(perm[randomEliteIdx]) + j) + mutation;
-		dst[j] = v;
-		elite_idx[e] = randomEliteIdx;
-		h += gene_hash(v, j);
-		oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+	if (live) {
+		const unsigned long long P2 = S->pos_elite;
+		double * dst = Xloc + (row - own_lo) * n;
+		for (int j = g; j < n; j += kRowLanes) {
+			const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
+			const int randomEliteIdx = (int) round(st.u(P2 + 2ULL * e) * Nelite);
+			const double mutation = eliteMutationSize * (ub[j] - lb[j]) * st.u(P2 + 2ULL * e + 1ULL);
+			const double v = __ldcg(cur.row(perm[randomEliteIdx]) + j) + mutation;
+			dst[j] = v;
+			elite_idx[e] = randomEliteIdx;
+			h += gene_hash(v, j);
+			oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+		}
 	}
-	for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); oob += __shfl_xor_sync(0xffffffffu, oob, o); }
-	if (lane == 0) { hash_new[row] = h; bcount[row] = oob; }
+	h = group_sum(h); oob = group_sum(oob);
+	if (live && g == 0) { hash_new[row] = h; bcount[row] = oob; }
 }
 
 // parent indices of ALL elite-mutation genes (pnol_ga_get_indices on a rank that only made its own children)
@@ -495,7 +623,7 @@ ga_dup_query_kernel(const unsigned long long * __restrict__ hash, long long Npop
 	const unsigned last = tmax[slot];                                // largest row with this hash
 	unsigned char flag = 0;
 	if (last > (unsigned) row) {
-		if (rows_equal(xnew.row(row), xnew.row(last), n)) flag = 1;
+		if (rows_equal(xnew.row((unsigned) row), xnew.row(last), n)) flag = 1;
 		else suspects[atomicAdd(&S->nsuspect, 1u)] = (unsigned) row;   // a later row shares the hash but differs: look at all of them
 	}
 	dupflag[row] = flag;
@@ -514,7 +642,7 @@ ga_dup_resolve_kernel(const unsigned long long * __restrict__ hash, long long Np
 		if (threadIdx.x == 0) found = 0;
 		__syncthreads();
 		for (long long k = (long long) row + 1 + threadIdx.x; k < Npop; k += blockDim.x)
-			if (hash[k] == h && rows_equal(xnew.row(row), xnew.row(k), n)) found = 1;
+			if (hash[k] == h && rows_equal(xnew.row(row), xnew.row((unsigned) k), n)) found = 1;
 		__syncthreads();
 		if (threadIdx.x == 0 && found) dupflag[row] = 1;
 		__syncthreads();
@@ -595,7 +723,7 @@ ga_pack_scan_kernel(const unsigned char * __restrict__ dupflag, const unsigned *
 	}
 }
 
-// replacement of duplicate rows and repair of out-of-box genes for the rows of this rank, one warp per row; evaluation flags
+// replacement of duplicate rows and repair of out-of-box genes for the rows of this rank (eight lanes per row); evaluation flags
 __global__ void __launch_bounds__(256)
 ga_fix_kernel(StreamDev st, const GaDevStatus * __restrict__ S, long long own_lo, long long own_hi, int n, int Nelite,
               long long NeliteMutGenes, const double * __restrict__ lb, const double * __restrict__ ub,
@@ -603,30 +731,27 @@ ga_fix_kernel(StreamDev st, const GaDevStatus * __restrict__ S, long long own_lo
               const unsigned long long * __restrict__ offs, double * __restrict__ Xloc, unsigned char * __restrict__ indicator)
 {
 	if (S->error) return;
-	const long long row = own_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
-	if (row >= own_hi) return;
-	const bool dup = dupflag[row] != 0;
-	const unsigned cnt = bcount[row];
-	if (lane == 0) indicator[row - own_lo] = (row >= Nelite || dup) ? 1 : 0;       // elites keep their value unless replaced (:116, :220)
-	if (!dup && cnt == 0) return;
-	const unsigned long long P3 = S->pos_elite + 2ULL * (unsigned long long) NeliteMutGenes;      // after the elite mutations
-	const unsigned long long o = offs[row];
-	double * x = Xloc + (row - own_lo) * n;
-	if (dup) {
-		// Xpop[i][j] = Xlb[j] + (Xub[j] - Xlb[j]) timeRand(), n draws per replaced row in row order (GeneticAlgorithm.cpp:335-338)
-		const unsigned long long k = P3 + (o >> 40) * (unsigned long long) n;
-		for (int j = lane; j < n; j += 32) x[j] = lb[j] + (ub[j] - lb[j]) * st.u(k + (unsigned long long) j);
-		return;
-	}
-	// one draw per out-of-box gene in row-major order (GeneticAlgorithm.cpp:352-361), after all the replacement draws
-	unsigned long long k = P3 + S->ndup * (unsigned long long) n + (o & ((1ULL << 40) - 1));
-	for (int j0 = 0; j0 < n; j0 += 32) {
-		const int j = j0 + lane;
-		const double v = j < n ? x[j] : 0.0;
-		const bool out = j < n && (v > ub[j] || v < lb[j]);
-		const unsigned m = __ballot_sync(0xffffffffu, out);
-		if (out) x[j] = lb[j] + (ub[j] - lb[j]) * st.u(k + (unsigned long long) __popc(m & ((1u << lane) - 1)));
+	const long long row = own_lo + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int lane = threadIdx.x & 31, g = lane % kRowLanes, gshift = lane - g;
+	const bool live = row < own_hi;
+	const bool dup = live && dupflag[row] != 0;
+	const unsigned cnt = live ? bcount[row] : 0;
+	if (live && g == 0) indicator[row - own_lo] = (row >= Nelite || dup) ? 1 : 0;      // elites keep their value unless replaced (:116, :220)
+	const bool work = dup || cnt != 0;
+	if (!__any_sync(0xffffffffu, work)) return;
+	const unsigned long long P3 = S->pos_elite + 2ULL * (unsigned long long) NeliteMutGenes;       // after the elite mutations
+	const unsigned long long o = work ? offs[row] : 0;
+	double * x = Xloc + (live ? (row - own_lo) * n : 0);
+	// one draw per out-of-box gene in row-major order (GeneticAlgorithm.cpp:352-361), after all the replacement draws;
+	// a replaced row takes n draws, Xpop[i][j] = Xlb[j] + (Xub[j] - Xlb[j]) timeRand(), rows in order (:335-338)
+	unsigned long long k = dup ? P3 + (o >> 40) * (unsigned long long) n : P3 + S->ndup * (unsigned long long) n + (o & ((1ULL << 40) - 1));
+	for (int j0 = 0; j0 < n; j0 += kRowLanes) {              // n is the same for every group: the ballots below are warp-uniform
+		const int j = j0 + g;
+		const bool in = work && j < n;
+		const double v = in && !dup ? x[j] : 0.0;
+		const bool out = in && (dup || v > ub[j] || v < lb[j]);
+		const unsigned m = (__ballot_sync(0xffffffffu, out) >> gshift) & ((1u << kRowLanes) - 1);     // this group's genes
+		if (out) x[j] = lb[j] + (ub[j] - lb[j]) * st.u(k + (unsigned long long) __popc(m & ((1u << g) - 1)));
 		k += (unsigned long long) __popc(m);
 	}
 }
@@ -664,30 +789,64 @@ ga_sort_kernel(const double * __restrict__ F, long long N, long long range, unsi
 		// ---- digit counts of this CTA's range ----
 		for (int e = tid; e < (kSortThreads / 32) * 256; e += kSortThreads) (&wcount[0][0])[e] = 0;
 		__syncthreads();
-		for (long long i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&wcount[warp & 7][(kin[i] >> shift) & 255], 1u);
+		// (warp-private counters, equal digits of a warp's 32 keys added once: the high bytes of the keys hold a handful of values,
+		// and 7000 shared-memory atomics on one address per CTA and pass were the longest phase of the sort)
+		for (long long c0 = lo; c0 < hi; c0 += kSortChunk) {
+			// (all loads of the chunk first: the warp-synchronous counting below would otherwise pay one L2 round trip per round)
+			unsigned dg[kSortPerThread];
+#pragma unroll
+			for (int r = 0; r < kSortPerThread; r++) {
+				const long long i = c0 + (long long) r * kSortThreads + tid;
+				dg[r] = i < hi ? (unsigned) ((kin[i] >> shift) & 255) : 256u;
+			}
+#pragma unroll
+			for (int r = 0; r < kSortPerThread; r++) {
+				const unsigned m = __match_any_sync(0xffffffffu, dg[r]);
+				if (dg[r] < 256u && (m & ((1u << lane) - 1)) == 0) wcount[warp][dg[r]] += __popc(m);
+				__syncwarp();
+			}
+		}
 		__syncthreads();
 		if (tid < 256) {
 			unsigned c = 0;
-			for (int w = 0; w < 8; w++) c += wcount[w][tid];
+			for (int w = 0; w < kSortThreads / 32; w++) c += wcount[w][tid];
 			counts[(size_t) tid * G + cta] = c;
 		}
 		grid.sync();
 		// ---- offsets of this range: total of the smaller digits + the same digit in the ranges before ----
-		if (tid < 256) {
-			unsigned long long tot = 0, before = 0;
-			const unsigned * c = counts + (size_t) tid * G;
-			for (int b = 0; b < G; b++) { const unsigned v = c[b]; tot += v; if (b < cta) before += v; }
-			dtot[tid] = tot;
-			dbase[tid] = before;
+		// (four threads per digit, loads issued in batches: one thread per digit adding G counts one after the other waited for
+		// an L2 round trip per count, 40 us per pass)
+		{
+			const int d = tid & 255, part = tid >> 8;                // kSortThreads / 256 = 4 parts
+			unsigned tot = 0, before = 0;
+			const unsigned * c = counts + (size_t) d * G;
+#pragma unroll 8
+			for (int b = part; b < G; b += kSortThreads / 256) { const unsigned v = c[b]; tot += v; before += b < cta ? v : 0u; }
+			wcount[part][d] = tot;
+			wcount[4 + part][d] = before;
 		}
 		if (tid == 0) s_skip = 0;
+		__syncthreads();
+		if (tid < 256) {
+			dtot[tid] = (unsigned long long) wcount[0][tid] + wcount[1][tid] + wcount[2][tid] + wcount[3][tid];
+			dbase[tid] = (unsigned long long) wcount[4][tid] + wcount[5][tid] + wcount[6][tid] + wcount[7][tid];
+		}
 		__syncthreads();
 		if (tid < 256 && dtot[tid] == (unsigned long long) N) s_skip = 1;      // one digit value holds every key: nothing moves
 		__syncthreads();
 		if (s_skip) { grid.sync(); continue; }                                 // uniform over the grid: all CTAs see the same totals
-		if (tid == 0) {
-			unsigned long long run = 0;
-			for (int d = 0; d < 256; d++) { const unsigned long long t = dtot[d]; dbase[d] += run; run += t; }
+		if (warp == 0) {
+			// dbase[d] += total of the smaller digits: lane l owns digits 8 l .. 8 l + 7 (a one-thread loop over 256 dependent
+			// shared-memory updates took 8 us per pass)
+			unsigned long long t[8], sum = 0;
+#pragma unroll
+			for (int e = 0; e < 8; e++) { t[e] = dtot[lane * 8 + e]; sum += t[e]; }
+			unsigned long long incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+			unsigned long long run = incl - sum;
+#pragma unroll
+			for (int e = 0; e < 8; e++) { dbase[lane * 8 + e] += run; run += t[e]; }
 		}
 		__syncthreads();
 		// ---- stable ranking and scatter, kSortChunk keys at a time ----
@@ -705,6 +864,11 @@ ga_sort_kernel(const double * __restrict__ F, long long N, long long range, unsi
 				const bool valid = i < hi;
 				k[r] = valid ? kin[i] : 0xFFFFFFFFFFFFFFFFULL;
 				v[r] = valid ? vin[i] : 0;
+			}
+#pragma unroll
+			for (int r = 0; r < kSortPerThread; r++) {
+				const long long i = base + r * 32 + lane;
+				const bool valid = i < hi;
 				const unsigned d = valid ? (unsigned) ((k[r] >> shift) & 255) : 256u;
 				const unsigned m = __match_any_sync(0xffffffffu, d);
 				const unsigned ahead = __popc(m & ((1u << lane) - 1));
@@ -760,12 +924,12 @@ __global__ void ga_finish_kernel(GaDevStatus * __restrict__ S, const double * __
 __global__ void __launch_bounds__(256)
 ga_gather_sorted_kernel(RowTable cur, const unsigned * __restrict__ perm, long long k0, long long k1, int n, double * __restrict__ dst)
 {
-	const long long k = k0 + (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-	const int lane = threadIdx.x & 31;
+	const long long k = k0 + (((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRowLanes);
+	const int g = threadIdx.x % kRowLanes;
 	if (k >= k1) return;
 	const double * s = cur.row(perm[k]);
 	double * d = dst + (k - k0) * n;
-	for (int j = lane; j < n; j += 32) d[j] = __ldcg(s + j);
+	for (int j = g; j < n; j += kRowLanes) d[j] = __ldcg(s + j);
 }
 
 __global__ void ga_iota_kernel(unsigned * __restrict__ perm, long long n)
@@ -803,7 +967,7 @@ struct GaPipe {
 	unsigned char * hb_send = nullptr, * hb_recv = nullptr;
 	double * f_recv = nullptr;
 	// crossover
-	unsigned long long * desc = nullptr; unsigned max_tiles = 0; unsigned tiles_dirty = 0;
+	unsigned long long * cross_counts = nullptr; int cross_grid = 0;
 	// mutation
 	void * mut_mem = nullptr; size_t mut_bytes = 0;
 	// duplicate table
@@ -914,7 +1078,7 @@ int ga_pipe_create(pnol_ga * ga)
 		PNOL_CHECK(pipe_alloc(ga, &P->hash[b], (size_t) P->per * R));
 		PNOL_CHECK(pipe_alloc(ga, &P->skeys[b], (size_t) Npop));
 		PNOL_CHECK(pipe_alloc(ga, &P->svals[b], (size_t) Npop));
-		P->table[b].per = P->per; P->table[b].n = n;
+		P->table[b].per = P->per; P->table[b].n = n; P->table[b].nranks = R;
 		for (int r = 0; r < kGaMaxRanks; r++) P->table[b].base[r] = nullptr;
 		P->table[b].base[0] = P->XL[b];
 	}
@@ -928,14 +1092,15 @@ int ga_pipe_create(pnol_ga * ga)
 	PNOL_CHECK(pipe_alloc(ga, &P->suspects, (size_t) Npop));
 	PNOL_CHECK(pipe_alloc(ga, &P->status, 1));
 	PNOL_CUDA(ctx, cudaMallocHost((void **) &P->status_host, sizeof(GaDevStatus)));
-	// crossover tiles: room for an acceptance rate down to 1/256 (a lower one ends in kGaErrCrossWindow)
+	// crossover: cooperative grid (all CTAs resident), one count per CTA
 	{
-		const long long need = (long long) ga->ncross * n;
-		long long tiles = need / kCrossTile * 256 + 1024;
-		if (tiles > (1LL << 24)) tiles = 1LL << 24;
-		P->max_tiles = (unsigned) tiles;
-		PNOL_CHECK(pipe_alloc(ga, &P->desc, (size_t) P->max_tiles));
-		PNOL_CUDA(ctx, cudaMemsetAsync(P->desc, 0, (size_t) P->max_tiles * 8, ctx->stream));
+		int per_sm = 0;
+		const size_t smem_max = (size_t) kCrossMaxWords * 8 + (size_t) kCrossChunkWords * 32 * 2;
+		PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max));
+		PNOL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ga_cross_kernel, kCrossThreads, smem_max));
+		PNOL_REQUIRE(ctx, per_sm >= 1, "ga: the crossover kernel does not fit an SM");
+		P->cross_grid = ctx->sm_count * std::min(per_sm, 4);
+		PNOL_CHECK(pipe_alloc(ga, &P->cross_counts, (size_t) P->cross_grid));
 	}
 	// duplicate table: at least 2 slots per row, power of two
 	{
@@ -1007,7 +1172,7 @@ int ga_pipe_reset(pnol_ga * ga)
 	PNOL_CUDA(ctx, cudaMemcpyAsync(P->Fs[0], ga->F, (size_t) Npop * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	PNOL_LAUNCH(ctx, ga_iota_kernel, blocks_for(Npop, 256), 256, 0, P->perm[0], Npop);
 	// hashes of all rows (the full sorted population is at hand on every rank right now)
-	PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for(Npop * 32, 256), 256, 0, ga->Xpop, 0LL, 0LL, Npop, n, P->hash[0], (unsigned *) nullptr);
+	PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for(Npop * kRowLanes, 256), 256, 0, ga->Xpop, 0LL, 0LL, Npop, n, P->hash[0], (unsigned *) nullptr);
 	PNOL_CHECK(pipe_refresh_replica(ga, 0));
 	P->elite_idx_complete = true;
 	return PNOL_OK;
@@ -1042,25 +1207,37 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 	};
 
 	// 0. fitness / ratios / status
-	if (P->tiles_dirty) PNOL_CUDA(ctx, cudaMemsetAsync(P->desc, 0, (size_t) std::min(P->tiles_dirty, P->max_tiles) * 8, ctx->stream));
 	{
 		TimerScope ts(ctx, "ga_prep");
 		PNOL_LAUNCH(ctx, ga_prep_kernel, blocks_for(Npop, 256), 256, 0, P->Fs[cur], Npop, (int) Nelite, ga->fitness, P->ratio, P->Fchild, S,
 		            (unsigned long long) ga->pos);
 		long long a, b;
 		clampr(0, Nelite, a, b);
-		if (b > a) PNOL_LAUNCH(ctx, ga_elite_copy_kernel, blocks_for((b - a) * 32, 256), 256, 0, T, P->perm[cur], P->hash[cur], a, b, n,
+		if (b > a) PNOL_LAUNCH(ctx, ga_elite_copy_kernel, blocks_for((b - a) * kRowLanes, 256), 256, 0, T, P->perm[cur], P->hash[cur], a, b, n,
 		                       Xloc + (a - lo) * n, P->hash[nxt], P->bcount);
 	}
 	// 1. crossover
 	if (Ncross > 0) {
 		TimerScope ts(ctx, "ga_crossover");
-		const long long need = Ncross * n;
-		PNOL_LAUNCH(ctx, ga_cross_kernel, ctx->sm_count * 6, kCrossThreads, 0, st, S, P->ratio, Npop, need, P->max_tiles, P->desc, ga->cross_idx,
-		            T, P->perm[cur], n, Xloc, lo, hi, Nelite);
+		long long need = Ncross * n;
+		// range length per CTA from the measured acceptance rate (+ 8 %); a short range costs another round, not an error
+		const double rate = std::max(P->accept_rate, 1.0 / 512);
+		int W = (int) std::min<double>(kCrossMaxWords, std::max(8.0, (double) need / rate * 1.08 / (32.0 * P->cross_grid) + 1.0));
+		int max_rounds = 1 << 16, npop_i = Npop, n_i = n;
+		long long own_lo = lo, own_hi = hi, row0 = Nelite;
+		const double * ratio = P->ratio;
+		unsigned long long * counts = P->cross_counts;
+		int * sel = ga->cross_idx;
+		const unsigned * perm_c = P->perm[cur];
+		RowTable Tc = T;
+		void * args[] = {(void *) &st, (void *) &S, (void *) &ratio, (void *) &npop_i, (void *) &need, (void *) &W, (void *) &max_rounds, (void *) &counts,
+		                 (void *) &sel, (void *) &Tc, (void *) &perm_c, (void *) &n_i, (void *) &Xloc, (void *) &own_lo, (void *) &own_hi, (void *) &row0};
+		const size_t smem = (size_t) W * 8 + (size_t) kCrossChunkWords * 32 * 2;
+		PNOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *) ga_cross_kernel, dim3(P->cross_grid), dim3(kCrossThreads), args, smem, ctx->stream));
+		ctx->launches++;
 		long long a, b;
 		clampr(Nelite, Nelite + Ncross, a, b);
-		if (b > a) PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for((b - a) * 32, 256), 256, 0, Xloc, lo, a, b, n, P->hash[nxt], P->bcount);
+		if (b > a) PNOL_LAUNCH(ctx, ga_rows_hash_kernel, blocks_for((b - a) * kRowLanes, 256), 256, 0, Xloc, lo, a, b, n, P->hash[nxt], P->bcount);
 	}
 	// 2. mutation
 	{
@@ -1077,7 +1254,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		PNOL_REQUIRE(ctx, nsub_max >= 1, "ga: n = %d is too large for the mutation tables", n);
 		long long subs = (long long) (cand / kMutSub) + 1;
 		const long long min_subs = ((long long) G.SD + kMutSub - 1) / kMutSub;            // a CTA spans at least the longest jump
-		int nsub = (int) std::max<long long>(min_subs, std::min<long long>(nsub_max, (subs + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count)));
+		int nsub = (int) std::max<long long>(min_subs, std::min<long long>(nsub_max, (subs + 6LL * ctx->sm_count - 1) / (6LL * ctx->sm_count)));
 		PNOL_REQUIRE(ctx, nsub <= nsub_max, "ga: n = %d is too large for the mutation tables", n);
 		G.nsub = nsub;
 		G.nctas = (int) ((subs + nsub - 1) / nsub);
@@ -1088,7 +1265,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		PNOL_CHECK(pipe_mut_reserve(ga, bytes));
 		unsigned char * p = (unsigned char *) P->mut_mem;
 		auto take = [&](size_t b) { void * r = p; p += (b + 255) & ~(size_t) 255; return r; };
-		long long * cta_cnt = (long long *) take(ctab * 8);
+		int * cta_cnt = (int *) take(ctab * 4);
 		long long * cta_base = (long long *) take((size_t) G.nctas * 8);
 		unsigned * accbits = (unsigned *) take(words * 4);
 		int * sub_exit = (int *) take(tabs * 4);
@@ -1098,14 +1275,23 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		const size_t smem1 = (size_t) nsub * (kMutSub / 32) * 4 + (size_t) nsub * G.SD * 8;
 		PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_mut_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1));
 		PNOL_LAUNCH(ctx, ga_mut_tables_kernel, G.nctas, kMutThreads, smem1, st, S, P->ratio, Npop, G, accbits, sub_exit, sub_cnt, cta_exit, cta_cnt);
-		PNOL_LAUNCH(ctx, ga_mut_compose_kernel, 1, 32, 0, S, G, cta_exit, cta_cnt, cta_entry, cta_base, Nrand);
-		const size_t smem3 = (size_t) ((nsub + 1) & ~1) * 4 + (size_t) nsub * 8;
+		{
+			const int nseg = (G.nctas + kMutSeg - 1) / kMutSeg;
+			const size_t seg_bytes = (size_t) nseg * G.SD * 12 + (size_t) nseg * 12 + 64;
+			const int in_smem = ctab * 8 + seg_bytes <= 200 * 1024 ? 1 : 0;
+			const size_t smem2 = (in_smem ? ctab * 8 : 0) + seg_bytes;
+			PNOL_REQUIRE(ctx, smem2 <= 200 * 1024, "ga: n = %d is too large for the mutation tables", n);
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_mut_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2));
+			PNOL_LAUNCH(ctx, ga_mut_compose_kernel, 1, 1024, smem2, S, G, cta_exit, cta_cnt, cta_entry, cta_base, Nrand, in_smem);
+		}
+		const size_t smem3 = (size_t) ((nsub + 1) & ~1) * 4 + (size_t) nsub * 8 + (size_t) nsub * (kMutSub / 32) * 4 + (size_t) nsub * G.SD * 8;
+		PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_mut_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem3));
 		PNOL_LAUNCH(ctx, ga_mut_emit_kernel, G.nctas, kMutThreads, smem3, st, S, Npop, n, G, accbits, sub_exit, sub_cnt, cta_entry, cta_base, Nrand,
 		            NeliteMut * n, ga->mut_pos, ga->mut_idx);
 		long long a, b;
 		clampr(Nelite + Ncross, Nelite + Ncross + Nrand, a, b);
 		if (b > a)
-			PNOL_LAUNCH(ctx, ga_mut_apply_kernel, blocks_for((b - a) * 32, 256), 256, 0, st, S, T, P->perm[cur], ga->mut_pos, ga->mut_idx,
+			PNOL_LAUNCH(ctx, ga_mut_apply_kernel, blocks_for((b - a) * kRowLanes, 256), 256, 0, st, S, T, P->perm[cur], ga->mut_pos, ga->mut_idx,
 			            a - (Nelite + Ncross), b - (Nelite + Ncross), Nelite + Ncross, lo, n, ga->lb, ga->ub, spreadRatio, Xloc, P->hash[nxt], P->bcount);
 	}
 	// 3. elite mutations
@@ -1115,7 +1301,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		long long a, b;
 		clampr(row0, row0 + NeliteMut, a, b);
 		if (b > a)
-			PNOL_LAUNCH(ctx, ga_elite_mut_kernel, blocks_for((b - a) * 32, 256), 256, 0, st, S, T, P->perm[cur], a - row0, b - row0, row0, lo, n,
+			PNOL_LAUNCH(ctx, ga_elite_mut_kernel, blocks_for((b - a) * kRowLanes, 256), 256, 0, st, S, T, P->perm[cur], a - row0, b - row0, row0, lo, n,
 			            (int) Nelite, ga->lb, ga->ub, ga->prm.elite_mutation_size, Xloc, P->hash[nxt], P->bcount, ga->elite_idx);
 	}
 	// hashes and box counts of all rows on every rank; the new rows where the duplicate check of another rank may look at them
@@ -1152,7 +1338,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		PNOL_LAUNCH(ctx, ga_pack_sums_kernel, nb, 256, 0, P->dupflag, P->bcount, (long long) Npop, P->block_sums);
 		PNOL_LAUNCH(ctx, ga_pack_scan_kernel, nb, 256, 0, P->dupflag, P->bcount, (long long) Npop, P->block_sums, nb, P->offs, S, NeliteMut * n, n);
 		if (hi > lo)
-			PNOL_LAUNCH(ctx, ga_fix_kernel, blocks_for((hi - lo) * 32, 256), 256, 0, st, S, lo, hi, n, (int) Nelite, NeliteMut * n, ga->lb, ga->ub,
+			PNOL_LAUNCH(ctx, ga_fix_kernel, blocks_for((hi - lo) * kRowLanes, 256), 256, 0, st, S, lo, hi, n, (int) Nelite, NeliteMut * n, ga->lb, ga->ub,
 			            P->dupflag, P->bcount, P->offs, Xloc, P->indicator);
 	}
 	// 6. the fitness sweep over this rank's rows (:217)
@@ -1194,7 +1380,6 @@ int ga_pipe_generation(pnol_ga * ga)
 		PNOL_CHECK(pipe_enqueue(ga, scale));
 		PNOL_CHECK(finish(ctx));
 		const GaDevStatus & H = *P->status_host;
-		P->tiles_dirty = H.cross_ticket;
 		if (H.error & kGaErrStream) {
 			PNOL_SET_ERR(ctx, "ga: the explicit random stream (%llu values) is exhausted", (unsigned long long) ga->stream.n_values);
 			return PNOL_ERR_STREAM;
@@ -1241,7 +1426,7 @@ int ga_pipe_get_population(pnol_ga * ga, double * xpop, double * F)
 	const int n = ga->n;
 	if (xpop) {
 		// sorted rows into the (otherwise idle) full-size buffer of the stage-by-stage path
-		PNOL_LAUNCH(ctx, ga_gather_sorted_kernel, blocks_for(Npop * 32, 256), 256, 0, P->table[P->cur], P->perm[P->cur], 0LL, Npop, n, ga->Xnew);
+		PNOL_LAUNCH(ctx, ga_gather_sorted_kernel, blocks_for(Npop * kRowLanes, 256), 256, 0, P->table[P->cur], P->perm[P->cur], 0LL, Npop, n, ga->Xnew);
 		PNOL_CUDA(ctx, cudaMemcpyAsync(xpop, ga->Xnew, (size_t) Npop * n * sizeof(double), cudaMemcpyDefault, ctx->stream));
 	}
 	if (F) PNOL_CUDA(ctx, cudaMemcpyAsync(F, P->Fs[P->cur], (size_t) Npop * sizeof(double), cudaMemcpyDefault, ctx->stream));
