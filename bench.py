@@ -175,13 +175,26 @@ def _run_port_lm(t, y, w, x0, steps):
     return (time.perf_counter() - t0) / steps
 
 
-def cpu_reference(m_total, K, steps, warmup, rows=REF_SAMPLE_ROWS):
-    """Times the reference's CPU implementation of the LM step on a row sample; returns (iters/s at full m, description)."""
+def _time_ref_shape(m, K, P):
+    """seconds per LM iteration of the verbatim reference at (m rows, n = 2K) -- a MEASUREMENT at that shape, no scaling"""
+    from parallelnonlinearoptimizationlibrary_b200 import problems
+    pr = problems.lorentz_problem(m, K)
+    return _run_ref_lm(pr["t"], pr["y"], pr["w"], pr["x0"], 1, 0, P)
+
+
+def cpu_reference(m_total, K, steps, warmup, rows=REF_SAMPLE_ROWS, scaled_shapes=True):
+    """Times the reference's CPU implementation of the LM step; returns (iters/s at full m, description).
+
+    The headline figure is the verbatim reference on a row sample of the cfg5 problem scaled by m / rows (every statement of the
+    iteration except the n^3 solve is linear in the rows) -- an EXTRAPOLATION, and the line says so. Beside it, measured without any
+    scaling: the verbatim reference at m = 4M, n = 16 and at m = 200k, n = 64, the exponent of n those two imply
+    for the cost per row, and what that law predicts for cfg5."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     pr, t, y = _sample_problem(m_total, K, rows)
     cores = os.cpu_count() or 1
-    scale = m_total / float(rows)                  # every O(m) statement of the iteration scales linearly in the rows
+    scale = m_total / float(rows)
+    extra = {}
     if O.have_ref():
         # the reference replicates the dense algebra on every rank and pays n+1 collectives of m doubles per Jacobian, so
         # more ranks are not always faster: calibrate P in {1, min(8, cores)} during warm-up and time the faster one
@@ -194,14 +207,29 @@ def cpu_reference(m_total, K, steps, warmup, rows=REF_SAMPLE_ROWS):
         kind, used = "reference", P
         note = "verbatim reference LevMarqMPI::findMin (oracle/_ref, mini-MPI ranks=%d; calibration s/iter %s)" % (
             P, {k: round(v, 3) for k, v in cal.items()})
+        if scaled_shapes:
+            try:
+                a = _time_ref_shape(4_000_000, 8, P)           # m = 4M, n = 16
+                b = _time_ref_shape(200_000, 32, P)            # m = 200k, n = 64
+                pa, pb = a / 4_000_000, b / 200_000            # seconds per row
+                expo = float(np.log(pb / pa) / np.log(64.0 / 16.0))
+                pred = pb * (2.0 * K / 64.0) ** expo * m_total
+                extra = {"measured_shapes": [{"m": 4_000_000, "n": 16, "s_per_iter": a, "ranks": P}, {"m": 200_000, "n": 64, "s_per_iter": b, "ranks": P}],
+                         "implied_exponent_of_n_per_row": expo,
+                         "cfg5_s_per_iter_predicted_by_that_law": pred,
+                         "cfg5_s_per_iter_from_the_row_sample": s_iter * scale}
+            except Exception as e:                          # reported, never required
+                extra = {"measured_shapes": "failed: %r" % (e,)}
     else:
         s_iter = _run_port_lm(t, y, pr["w"], pr["x0"], steps)
         kind, used = "port", 1
         note = "oracle restatement (oracle/libpnol_oracle.so), scalar"
     value = 1.0 / (s_iter * scale)
-    sample = ("%d of %d rows (every %d-th), n=%d, %d LM iteration(s); s/iter on the sample %.3f scaled by m/rows=%.1f; %s"
+    sample = ("EXTRAPOLATED from %d of %d rows (every %d-th), n=%d, %d LM iteration(s): s/iter on the sample %.3f scaled by m/rows=%.1f; %s"
               % (rows, m_total, m_total // rows, 2 * K, steps, s_iter, scale, note))
-    return value, dict(value=value, unit=UNIT, cores=used, kind=kind, sample=sample, host_cores=cores, s_per_iter_sample=s_iter)
+    d = dict(value=value, unit=UNIT, cores=used, kind=kind, sample=sample, host_cores=cores, s_per_iter_sample=s_iter, extrapolated=True)
+    d.update(extra)
+    return value, d
 
 
 def run_reference(args):
@@ -212,7 +240,7 @@ def run_reference(args):
     # every reference step costs about a second on the 8192-row sample: cap the timed steps so that the run ends within a few
     # minutes whatever K the caller asks for (the metric is a rate, the cap only bounds the averaging window)
     timed = max(1, min(args.steps, 40))
-    value, cb = cpu_reference(args.m, args.K, timed, args.warmup, rows=args.ref_rows)
+    value, cb = cpu_reference(args.m, args.K, timed, args.warmup, rows=args.ref_rows, scaled_shapes=not args.no_scaled_shapes)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -368,8 +396,112 @@ def run_ours(args):
     d2h = (calls * 2 * m_loc * 8 + args.steps * (n * 8 + 4 + 8) + calls * 8) / args.steps
     e2e_windows = (e0, e1)
 
+    # ---- parity: results of this very run against committed reference-derived fixtures, at every GPU count -----------------
+    # LM: 4 iterations from the start point at the FULL cfg5 size against the threaded oracle restatement of
+    # Source/LevenbergMarquardtMPI.cpp:12-173 (tests/golden/baseline_lm_golden.npz, case cfg5; the generating script proves that
+    # restatement bit-identical to the verbatim reference where the reference finishes). X must also be bit-identical on all ranks.
+    import hashlib
+    parity = {}
+    try:
+        GB = np.load(os.path.join(ROOT, "tests", "golden", "baseline_lm_golden.npz"))
+        if (m_total, K) == (int(GB["cfg5/m"]), int(GB["cfg5/K"])):
+            prob.start()
+            prob.step(int(GB["cfg5/maxiter"]))
+            want = GB["cfg5/X"]
+            rel_x = float(np.linalg.norm(prob.X - want) / np.linalg.norm(want))
+            chi_ref = float(GB["cfg5/chisq"])
+            xs = launch.gather_over_ranks(prob.X)
+            parity["lm"] = {"fixture": "tests/golden/baseline_lm_golden.npz:cfg5 (oracle restatement at m=4M, n=256, 4 iterations)",
+                            "rel_err_X": rel_x, "chisq": prob.chi, "chisq_ref": chi_ref, "lambda_equal": bool(prob.lam == float(GB["cfg5/lam"])),
+                            "X_bit_identical_on_all_ranks": bool(all(np.array_equal(xs[0], x) for x in xs)),
+                            "ok": bool(rel_x <= 1e-9 and prob.lam == float(GB["cfg5/lam"]) and all(np.array_equal(xs[0], x) for x in xs))}
+    except Exception as e:
+        parity["lm"] = {"ok": False, "error": repr(e)}
+
+    # ---- secondary: FD gradient with the coordinates split by column over the GPUs (cfg3's n = 4096; pnol_fd_gradient,
+    #      Source/PNOL_Objective.cpp:88-159), bit for bit against the oracle's gradient (tests/golden/bench_fixture.npz) --------
+    fdg = None
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_bench_fixture import GA_SHAPE, fdgrad_inputs, ga_fingerprint      # shapes / inputs only (no oracle import on this path)
+    BF = np.load(os.path.join(ROOT, "tests", "golden", "bench_fixture.npz"))
+    try:
+        xg, dxg = fdgrad_inputs()
+        frs = ctx.functor(capi.F_ROSENBROCK)
+        g, f0g = ctx.fd_gradient(frs, xg, dxg)
+        sync_all()
+        reps = 20
+        t0g = time.perf_counter()
+        for _ in range(reps):
+            g, f0g = ctx.fd_gradient(frs, xg, dxg)
+        sync_all()
+        ms_g = launch.max_over_ranks((time.perf_counter() - t0g) / reps * 1e3)
+        ok_g = bool(np.array_equal(g, BF["fdgrad4096/g"]) and f0g == float(BF["fdgrad4096/f0"]))
+        gs = launch.gather_over_ranks(g)
+        fdg = {"metric": "fd_gradient_n4096_column_split", "ms_per_gradient_host_call": ms_g, "evaluations": 4097, "columns_per_gpu": -(-4096 // world),
+               "bit_exact_vs_oracle": ok_g, "bit_identical_on_all_ranks": bool(all(np.array_equal(gs[0], x) for x in gs))}
+        parity["fd_gradient"] = {"ok": bool(ok_g and fdg["bit_identical_on_all_ranks"]), "fixture": "tests/golden/bench_fixture.npz:fdgrad4096 (oracle)"}
+    except Exception as e:
+        parity["fd_gradient"] = {"ok": False, "error": repr(e)}
+
+    # ---- secondary: the dense BFGS / LM pieces at the cfg3 / cfg5 sizes, one GPU each (north_star: they stay on one GPU) -------
+    dense = {}
+    if not args.no_dense:
+        try:
+            hbm_pk = hbm_peak_early
+            n3 = 4096
+            rngd = np.random.default_rng(9)
+            D = np.diag(rngd.uniform(0.5, 2.0, n3))
+            u3 = rngd.normal(size=(n3, 3)) / np.sqrt(n3)
+            D = D + u3 @ u3.T
+            g3 = rngd.normal(size=n3)
+            s3 = 0.1 * g3 + 0.05 * rngd.normal(size=n3)
+            Dd, gd, sd, pd = ctx.to_device(D), ctx.to_device(g3), ctx.to_device(s3), ctx.malloc(n3 * 8)
+
+            def timed_kernel(name, fn, reps, warm=3):
+                for _ in range(warm):
+                    fn()
+                ctx.sync()
+                ctx.timer_enable(True)
+                ctx.timer_reset()
+                for _ in range(reps):
+                    fn()
+                ms, cnt = ctx.timer_get(name)
+                ctx.timer_enable(False)
+                return launch.max_over_ranks(ms / max(cnt, 1))
+
+            # D (134 MB) exceeds the 126 MB L2; the update rewrites it between matvec calls in the real iteration
+            ms = timed_kernel("matvec_neg", lambda: ctx.matvec_neg(Dd, gd, n3, p=pd), 30)
+            by = n3 * n3 * 8.0
+            dense["matvec_neg"] = {"n": n3, "ms": ms, "bound": "hbm", "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                                   "peak": hbm_pk, "frac": by / (ms * 1e-3) / 1e9 / hbm_pk}
+            ms = timed_kernel("hinv_rank2", lambda: ctx.bfgs_update_hinv(Dd, gd, sd, n3, mode=capi.HINV_RANK2), 30)
+            by = 3.0 * n3 * n3 * 8.0
+            dense["hinv_rank2"] = {"n": n3, "ms": ms, "bound": "hbm", "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                                   "peak": hbm_pk, "frac": by / (ms * 1e-3) / 1e9 / hbm_pk,
+                                   "note": "D read twice (u = D g and v = D^T g in one pass, then the update pass) and written once"}
+            Dl = ctx.to_device(D)
+            ms = timed_kernel("hinv_literal", lambda: ctx.bfgs_update_hinv(Dl, gd, sd, n3, mode=capi.HINV_LITERAL), 3, warm=1)
+            fl = 4.0 * n3 ** 3
+            dense["gemm_nn_literal"] = {"n": n3, "ms": ms, "bound": "tensor", "algorithmic_flops": fl, "achieved": fl / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                        "peak": dmma_peak, "frac": fl / (ms * 1e-3) / 1e12 / dmma_peak,
+                                        "note": "updateHessianInv as the reference writes it: two n^3 products (DMMA) + the rank-1 terms"}
+            for q in (Dd, gd, sd, pd, Dl):
+                ctx.free(q)
+            ns = n
+            M = rngd.normal(size=(ns, ns))
+            A = M @ M.T / ns + np.eye(ns)
+            Ad, bd, xd = ctx.to_device(A), ctx.to_device(rngd.normal(size=ns)), ctx.malloc(ns * 8)
+            ms = timed_kernel("spd_solve", lambda: ctx.spd_solve(Ad, bd, ns, x=xd), 30)
+            dense["spd_solve"] = {"n": ns, "ms": ms, "bound": "latency", "algorithmic_flops": ns ** 3 / 3.0,
+                                  "note": "damped Cholesky solve of the LM step (replicated on every GPU): a dependency chain, reported in time only"}
+            for q in (Ad, bd, xd):
+                ctx.free(q)
+        except Exception as e:
+            dense["error"] = repr(e)
+
     # ---- secondary: GA at the cfg4 shape (Rastrigin, Npop = 1M x 32): the fitness sweep alone (this rank's shard) and whole
-    #      generations through the GA state machine (sweep sharded + all-gather of F when N > 1, other stages replicated) ----
+    #      generations through the GA state machine (rows sharded over the GPUs: every rank creates, repairs and evaluates its own
+    #      children; hashes and objective values all-gathered; selection scans and the sort replicated) ----
     ga = None
     if not args.no_ga:
         npop = 1_000_000
@@ -397,9 +529,9 @@ def run_ours(args):
               "hbm_frac_of_measured": (ghi - glo) * 33 * 8 / (gms * 1e-3) / 1e9 / hbm_peak_early}
         ctx.free(pts)
         ctx.free(fo)
-        gens = 10
-        gas = ctx.ga_create(fr, 32, np.full(32, -5.12), np.full(32, 5.12), npop, gens + 2, dict(seed=12345, scale=1.0 - 2.0 ** -20), nstatic=1e9)
-        gas.init(np.full(32, 2.5))
+        gens = GA_SHAPE["gens"]
+        gas = ctx.ga_create(fr, 32, np.full(32, -5.12), np.full(32, 5.12), npop, gens + 2, dict(seed=GA_SHAPE["seed"], scale=GA_SHAPE["scale"]), nstatic=1e9)
+        gas.init(np.full(32, GA_SHAPE["x0"]))
         gas.generation()
         sync_all()
         g0.record(stream)
@@ -409,7 +541,36 @@ def run_ours(args):
         sync_all()
         gen_ms = launch.max_over_ranks(g0.elapsed_time(g1)) / gens
         st = gas.status()
-        ga.update(ms_per_generation=gen_ms, evals_per_s_whole_generation=(npop - st.n_elite) / (gen_ms * 1e-3), f_best=st.f_best)
+        _, Fga = gas.population()
+        fp = ga_fingerprint(Fga, st.stream_pos)
+        fps = launch.gather_over_ranks(np.frombuffer(bytes.fromhex(fp), dtype=np.uint8).astype(np.float64))
+        want_fp = str(BF["ga/sha256"]) if "ga/sha256" in BF else None
+        parity["ga"] = {"sha256_F_and_stream_pos": fp, "fixture_sha256_from_the_1_gpu_run": want_fp,
+                        "identical_on_all_ranks": bool(all(np.array_equal(fps[0], x) for x in fps)),
+                        "ok": bool(want_fp is not None and fp == want_fp and all(np.array_equal(fps[0], x) for x in fps))}
+        # per-stage times of two more generations (CUDA-event scopes; they serialise the stages, so they are not part of gen_ms)
+        ctx.timer_enable(True)
+        ctx.timer_reset()
+        gas2 = ctx.ga_create(fr, 32, np.full(32, -5.12), np.full(32, 5.12), npop, gens + 2, dict(seed=GA_SHAPE["seed"], scale=GA_SHAPE["scale"]), nstatic=1e9)
+        gas2.init(np.full(32, GA_SHAPE["x0"]))
+        ctx.timer_reset()
+        for _ in range(3):
+            gas2.generation()
+        stages = {}
+        for name in ("ga_prep", "ga_crossover", "ga_mutation", "ga_elite_mutation", "ga_gather_hash", "ga_check_identical", "ga_check_bounds", "eval_batch",
+                     "ga_gather_f", "ga_pop_sort"):
+            ms, cnt = ctx.timer_get(name)
+            if cnt:
+                stages[name] = round(launch.max_over_ranks(ms / cnt), 5)
+        ctx.timer_enable(False)
+        # algorithmic HBM traffic of a generation: children written once (256 MB), parents read once (256 MB), one more read by
+        # the sweep; roofline time at the measured copy bandwidth
+        gen_bytes = 3.0 * npop * 32 * 8 / world
+        ga.update(ms_per_generation=gen_ms, evals_per_s_whole_generation=(npop - st.n_elite) / (gen_ms * 1e-3), f_best=st.f_best,
+                  stream_draws_per_generation=int(st.stream_pos) // (gens + 1), peer_mode=gas.peer_mode(), stage_ms=stages,
+                  hbm_frac_whole_generation=gen_bytes / (gen_ms * 1e-3) / 1e9 / hbm_peak_early,
+                  note="bound by the counter-based random stream (about 135 M draws of 64-bit integer mixing per generation), not by HBM")
+        gas2.close()
         gas.close()
 
     if sampler:
@@ -460,12 +621,14 @@ def run_ours(args):
                                 "ms": timers["residual"]["ms_avg"], "algorithmic_bytes": by, "peak_source": hbm_src}
         dominant = max(timers, key=lambda k: timers[k]["ms_avg"] * timers[k]["count"]) if timers else None
         roof = kern.get(dominant) or kern.get("syrk") or {}
-        roof = dict(roof, kernel=dominant)
+        roof = dict(roof, kernel=dominant,
+                    traffic_source=("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at this shape"
+                                    if roof.get("traffic") is not None else "not captured at this per-GPU shape (N > 1)"))
 
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                _, cb = cpu_reference(m_total, K, 1, 0, rows=args.ref_rows)
+                _, cb = cpu_reference(m_total, K, 1, 0, rows=args.ref_rows, scaled_shapes=not args.no_scaled_shapes)
             except Exception as e:                               # the baseline is reported, never required
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "failed: %r" % (e,)}
 
@@ -485,7 +648,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roof, "kernels": kern, "timers_ms": {k: round(v["ms_avg"], 5) for k, v in timers.items()},
             "jacobian_hbm_gbs": kern.get("fd_jacobian", {}).get("achieved"),
-            "cpu_baseline": cb, "secondary": ga,
+            "cpu_baseline": cb, "secondary": ga, "fd_gradient": fdg, "dense_kernels": dense, "parity": parity,
             "clocks": sampler.summary(windows) if sampler else None,
         }
         emit(out)
@@ -533,6 +696,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=REF_SAMPLE_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ga", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the cfg3 dense-kernel lines (matvec, rank-2 / literal update, solve)")
+    ap.add_argument("--no-scaled-shapes", action="store_true", help="cpu baseline: skip the measured m=4M,n=16 / m=200k,n=64 reference runs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

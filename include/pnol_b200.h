@@ -27,6 +27,7 @@
  *   PNOL_COPY_THREADS=k   host threads of the staged pageable <-> device copies (1..8, default 4)
  *   PNOL_FUSED_MB=x       MB of J per row block of pnol_lm_normal_eq_fused / J == NULL steps (read per call, default 512)
  *   PNOL_GA_LEGACY=1      genetic algorithm with the stage-by-stage generation of round 1 instead of the fused pipeline
+ *   PNOL_GA_NO_IPC=1      several GPUs: population replicas + all-gather instead of peer mappings (A/B runs, boxes without IPC)
  * and by the host classes (include/pnol/Runtime.hpp): PNOL_DEVICE, PNOL_POOL_WIDTH, PNOL_LM_JACOBIAN_CACHE.
  */
 #ifndef PNOL_B200_H_
@@ -207,11 +208,15 @@ int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const
                  double * Ftrial, double lambda, int jac_mode, int reuse_jtj, double * JTJ, double * sigma_out, double * x_trial_out,
                  double * sumsq_trial_out, int * spd_info_out);
 
-/* `iterations` LM iterations on device-resident state (J, F, Ftrial, JTJ as in pnol_lm_step), the accept / reject decision of
- * Source/LevenbergMarquardtMPI.cpp:107-141 on the host between them: chi^2 = pow(sqrt(sum Ftrial^2), 2); chi^2 >= previous or NaN ->
- * lambda *= factor, x and F stay; otherwise lambda /= factor, x = x_trial, F <-> Ftrial (pointer swap) and, with x_min_diff > 0, stop
- * once ||sigma||_2 < x_min_diff (:138-140). The Jacobian is recomputed in every iteration as in the reference (:60).
- *   x (host, n) in/out; lambda_inout, chisq_inout in/out; swapped_out: 1 when the current residuals ended in `Ftrial` */
+/* `iterations` LM iterations on device-resident state (J, F, Ftrial, JTJ as in pnol_lm_step) with the accept / reject decision of
+ * Source/LevenbergMarquardtMPI.cpp:107-141 taken ON THE DEVICE by two small kernels behind every step, so that the host enqueues a
+ * batch of iterations per synchronisation (all of them without a stopping rule, four at a time with one): chi^2 =
+ * pow(sqrt(sum Ftrial^2), 2); chi^2 >= previous or NaN -> lambda *= factor, x and F stay; otherwise lambda /= factor, x = x_trial,
+ * F = Ftrial (copied) and, with x_min_diff > 0, no further change once ||sigma||_2 < x_min_diff (:138-140). The arithmetic is the
+ * host rule's (IEEE square root, sequential sum), so pnol_lm_step + the rule on the host gives the same bits. The Jacobian is
+ * recomputed in every iteration as in the reference (:60).
+ *   x (host, n) in/out; lambda_inout, chisq_inout in/out; swapped_out: always 0 (kept for callers written against the pointer-
+ *   swapping host rule: the current residuals are in `F`) */
 int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const double * dx, int n, double * J, double * F, double * Ftrial,
                     double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
                     int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out);
@@ -302,6 +307,10 @@ int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out);
 /* one generation (GeneticAlgorithmMPI.cpp:87-249) */
 int pnol_ga_generation(pnol_ga * ga);
 int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * st);
+/* how the rows of the population are shared between the ranks of the context's communicator: 0 one rank (or the stage-by-stage
+ * generation), 1 rows stay with the rank that made them and are read by the others over NVLink (CUDA IPC peer mappings),
+ * 2 every rank keeps a replica refreshed by an all-gather per generation (peer mappings unavailable, or PNOL_GA_NO_IPC=1) */
+int pnol_ga_peer_mode(pnol_ga * ga);
 /* sorted population (npop x n) and objective values; either may be NULL */
 int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F);
 /* parent indices chosen in the last generation: crossover (n_cross x n), mutation (n_rand), elite mutation

@@ -276,6 +276,7 @@ int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out)
 	return st;
 }
 int pnol_ga_generation(pnol_ga * ga) { ga->generations++; return ga_replay(ga); }
+int pnol_ga_peer_mode(pnol_ga *) { return 0; }
 int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * st) { *st = ga->st; return PNOL_OK; }
 int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F)
 {

@@ -249,7 +249,8 @@ int launch_fd_jacobian(pnol_ctx * ctx, const pnol_functor * f, const double * x,
 
 int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed /* n*n + n */);
 int syrk_plan_selftest(long long m, int n, int sm_count, int with_f);
-int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs);
+int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs,
+                   const double * lambda_dev = nullptr);
 int launch_dgemm_nn(pnol_ctx * ctx, const double * A, const double * B, double * C, int M, int N, int K);
 int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev);
 int launch_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info_dev);

@@ -7,11 +7,12 @@ namespace pnol {
 // ---------------------------------------------------------------------------------------------------
 // a9: A = JTJ, A_ii = (1 + lambda) JTJ_ii ; rhs = -J^T F     (Source/LevenbergMarquardtMPI.cpp:66-85)
 // ---------------------------------------------------------------------------------------------------
-__global__ void lm_damp_kernel(const double * __restrict__ packed, int n, double lambda, double * __restrict__ JTJ,
-                               double * __restrict__ A, double * __restrict__ rhs)
+__global__ void lm_damp_kernel(const double * __restrict__ packed, int n, double lambda, const double * __restrict__ lambda_dev,
+                               double * __restrict__ JTJ, double * __restrict__ A, double * __restrict__ rhs)
 {
 	long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	long long total = (long long) n * n;
+	if (lambda_dev) lambda = *lambda_dev;           // device-resident LM loop (pnol_lm_iterate): lambda never visits the host
 	if (idx < total) {
 		double v = packed[idx];
 		if (JTJ) JTJ[idx] = v;
@@ -24,10 +25,11 @@ __global__ void lm_damp_kernel(const double * __restrict__ packed, int n, double
 	}
 }
 
-int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs)
+int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs,
+                   const double * lambda_dev)
 {
 	long long total = (long long) n * n + n;
-	PNOL_LAUNCH(ctx, lm_damp_kernel, (unsigned) ((total + 255) / 256), 256, 0, packed, n, lambda, JTJ, A, rhs);
+	PNOL_LAUNCH(ctx, lm_damp_kernel, (unsigned) ((total + 255) / 256), 256, 0, packed, n, lambda, lambda_dev, JTJ, A, rhs);
 	return PNOL_OK;
 }
 

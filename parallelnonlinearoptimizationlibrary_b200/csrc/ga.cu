@@ -1007,6 +1007,11 @@ extern "C" int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * s)
 	return PNOL_OK;
 }
 
+extern "C" int pnol_ga_peer_mode(pnol_ga * ga)
+{
+	return ga ? ga_pipe_peer_mode(ga) : 0;
+}
+
 extern "C" int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F)
 {
 	if (!ga) return PNOL_ERR_INVALID;

@@ -165,6 +165,7 @@ int ga_pipe_reset(pnol_ga * ga);                  // after pnol_ga_init: sorted 
 int ga_pipe_generation(pnol_ga * ga);
 int ga_pipe_get_population(pnol_ga * ga, double * xpop, double * F);
 int ga_pipe_get_indices(pnol_ga * ga, int * cross_idx, int * mut_idx, int * elite_idx);
+int ga_pipe_peer_mode(pnol_ga * ga);
 // comm.cu
 int comm_allgather_bytes_dev(pnol_ctx * ctx, const void * send, void * recv, size_t bytes_per_rank);
 }

@@ -1418,6 +1418,12 @@ int ga_pipe_generation(pnol_ga * ga)
 	}
 }
 
+int ga_pipe_peer_mode(pnol_ga * ga)
+{
+	if (!ga->pipe || ga->ctx->nranks <= 1) return 0;
+	return ga->pipe->use_ipc ? 1 : 2;
+}
+
 int ga_pipe_get_population(pnol_ga * ga, double * xpop, double * F)
 {
 	pnol_ctx * ctx = ga->ctx;

@@ -101,6 +101,20 @@ def max_over_ranks(value):
     return float(t.item())
 
 
+def gather_over_ranks(arr):
+    """list of every rank's copy of a float64 array (same shape on all ranks); [arr] without a process group"""
+    import torch
+    import torch.distributed as dist
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [a.copy()]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(a.copy()).to(dev)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.cpu().numpy() for o in out]
+
+
 def sum_over_ranks(arr):
     """element-wise float64 sum over ranks in torch.distributed (CPU tests of the sharded reductions)."""
     import torch

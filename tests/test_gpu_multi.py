@@ -96,6 +96,8 @@ def _worker(rank, world, port, out_dir):
     stream = dict(seed=4242, scale=1.0 - 1.0 / npop)
     fr = ctx.functor(capi.F_RASTRIGIN)
     ga = ctx.ga_create(fr, n, lb, ub, npop, gens, stream)
+    assert ga.peer_mode() == (2 if os.environ.get("PNOL_GA_NO_IPC") == "1" else ga.peer_mode()) and ga.peer_mode() in (1, 2)
+    np.save(os.path.join(out_dir, "peer_mode_%d.npy" % rank), np.array([ga.peer_mode()]))
     ga.init(x0)
     for gen in range(1, gens + 1):
         ga.generation()
@@ -117,12 +119,17 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_paths_match_the_reference(tmp_path, world):
+@pytest.mark.parametrize("world,no_ipc", [(2, 0), (2, 1), (4, 0), (8, 0), (8, 1)])
+def test_sharded_paths_match_the_reference(tmp_path, world, no_ipc, monkeypatch):
+    """no_ipc = 1: the GA rows are shared through replicas + all-gather (PNOL_GA_NO_IPC=1) instead of CUDA IPC peer mappings"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
+    monkeypatch.setenv("PNOL_GA_NO_IPC", str(no_ipc))
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    modes = {int(np.load(tmp_path / ("peer_mode_%d.npy" % r))[0]) for r in range(world)}
+    assert len(modes) == 1 and (no_ipc == 0 or modes == {2}), "every rank takes the same path"
+    print("GA peer mode at world %d: %s" % (world, modes))
     G = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden.npz"))
     GB = np.load(os.path.join(ROOT, "tests", "golden", "baseline_lm_golden.npz"))
     for tag, want, F0w in (("", G["lm_lorentz_K8/X"], G["lm_lorentz_K8/F0"]), ("K128_", GB["lm_K128/X"], GB["lm_K128/F0"])):

@@ -442,7 +442,8 @@ def test_lm_step_equals_the_separate_calls(ctx):
 
 
 def test_lm_iterate_equals_stepping_with_the_decision_in_python(ctx):
-    # pnol_lm_iterate = pnol_lm_step + the accept / reject rule of Source/LevenbergMarquardtMPI.cpp:107-141 in C++
+    # pnol_lm_iterate = the device work of pnol_lm_step + the accept / reject rule of Source/LevenbergMarquardtMPI.cpp:107-141 as
+    # two small kernels ON THE DEVICE (batches of iterations per synchronisation); here against the same rule taken in Python
     pr = problems.lorentz_problem(2000, 8)
     n, m = pr["n"], pr["m"]
     f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
@@ -470,7 +471,7 @@ def test_lm_iterate_equals_stepping_with_the_decision_in_python(ctx):
 
     J, F, Ft, JTJ, chi0 = fresh()
     X2, lam2, chi2, acc2, rej2, swapped = ctx.lm_iterate(f, pr["x0"], dx, n, J, F, Ft, JTJ, 1e-3, chi0, factor, iters)
-    assert (acc2, rej2) == (acc, rej) and acc > 0 and swapped == acc % 2
+    assert (acc2, rej2) == (acc, rej) and acc > 0 and swapped == 0      # accepted residuals are copied into F on the device
     assert np.array_equal(X2, X) and lam2 == lam and chi2 == chi
     assert np.array_equal(ctx.to_host(Ft if swapped else F, m), Fpy)
     # the stopping rule: with a huge x_min_diff the run ends after the first accepted step
