@@ -27,6 +27,7 @@
  *   PNOL_COPY_THREADS=k   host threads of the staged pageable <-> device copies (1..8, default 4)
  *   PNOL_FUSED_MB=x       MB of J per row block of pnol_lm_normal_eq_fused / J == NULL steps (read per call, default 512)
  *   PNOL_GA_LEGACY=1      genetic algorithm with the stage-by-stage generation of round 1 instead of the fused pipeline
+ *   PNOL_GA_SHARD=rows|sweep   overrides pnol_ga_set_sharding
  *   PNOL_GA_NO_IPC=1      several GPUs: population replicas + all-gather instead of peer mappings (A/B runs, boxes without IPC)
  * and by the host classes (include/pnol/Runtime.hpp): PNOL_DEVICE, PNOL_POOL_WIDTH, PNOL_LM_JACOBIAN_CACHE.
  */
@@ -307,9 +308,18 @@ int pnol_ga_init(pnol_ga * ga, const double * x0, double * f0_out);
 /* one generation (GeneticAlgorithmMPI.cpp:87-249) */
 int pnol_ga_generation(pnol_ga * ga);
 int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * st);
-/* how the rows of the population are shared between the ranks of the context's communicator: 0 one rank (or the stage-by-stage
- * generation), 1 rows stay with the rank that made them and are read by the others over NVLink (CUDA IPC peer mappings),
- * 2 every rank keeps a replica refreshed by an all-gather per generation (peer mappings unavailable, or PNOL_GA_NO_IPC=1) */
+/* How pnol_ga_create splits a generation over the ranks of the context's communicator (set before pnol_ga_create):
+ *   PNOL_GA_SHARD_ROWS   rank r owns child rows [r per, (r+1) per): it creates, repairs and evaluates them; parents are read from
+ *                        their owners over NVLink (CUDA IPC peer mappings; replicas refreshed by an all-gather when those are
+ *                        unavailable); row hashes / box counts and objective values are all-gathered. Memory per GPU ~ 1 / ranks.
+ *   PNOL_GA_SHARD_SWEEP  every rank keeps the population and makes all children; the fitness sweep is split and the objective values
+ *                        are all-gathered (the reference's evaluatePopulationParallel, Source/GeneticAlgorithmMPI.cpp:283-414).
+ *   PNOL_GA_SHARD_AUTO   sweep while the population fits one GPU comfortably, rows beyond (default).
+ * Results are bit-identical in every mode and at every rank count. */
+enum { PNOL_GA_SHARD_AUTO = 0, PNOL_GA_SHARD_ROWS = 1, PNOL_GA_SHARD_SWEEP = 2 };
+int pnol_ga_set_sharding(pnol_ctx * ctx, int mode);
+/* what a GA object does: 0 one rank (or the stage-by-stage generation), 1 rows sharded + peer mappings, 2 rows sharded + replicas
+ * (peer mappings unavailable, or PNOL_GA_NO_IPC=1), 3 rows replicated + sweep sharded */
 int pnol_ga_peer_mode(pnol_ga * ga);
 /* sorted population (npop x n) and objective values; either may be NULL */
 int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F);

@@ -82,6 +82,7 @@ const char * pnol_last_error(pnol_ctx * ctx) { return ctx ? ctx->err.c_str() : "
 int pnol_comm_rank(pnol_ctx *) { return 0; }
 int pnol_comm_size(pnol_ctx *) { return 1; }
 int pnol_comm_set_local(pnol_ctx *, int) { return 0; }
+int pnol_ga_set_sharding(pnol_ctx *, int) { return PNOL_OK; }
 int pnol_comm_broadcast(pnol_ctx *, double *, size_t, int) { return PNOL_OK; }
 int pnol_comm_allreduce_sum(pnol_ctx *, double *, size_t) { return PNOL_OK; }
 int pnol_comm_allgather(pnol_ctx *, const double * send, double * recv, size_t n) { std::memmove(recv, send, n * sizeof(double)); return PNOL_OK; }

@@ -87,7 +87,7 @@ EXPORTS = [
     "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve", "pnol_lu_inverse",
     "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
-    "pnol_ga_status_get", "pnol_ga_peer_mode", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
+    "pnol_ga_status_get", "pnol_ga_set_sharding", "pnol_ga_peer_mode", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
     "pnol_ga_check_identical", "pnol_measure_dmma_peak", "pnol_measure_copy_bandwidth", "pnol_timer_enable",
     "pnol_timer_get", "pnol_timer_reset", "pnol_selftest_exact_div", "pnol_selftest_fast_div", "pnol_selftest_syrk_plan",
 ]
@@ -489,6 +489,10 @@ class Context:
         h = C.c_void_p()
         self.check(self.lib.pnol_ga_create(self.h, f.handle, C.byref(prm), int(n), _ptr(lb), _ptr(ub), C.byref(sd), C.byref(h)))
         return GA(self, h, int(npop), int(n), keep, f)
+
+    def ga_set_sharding(self, mode):
+        """0 auto, 1 rows sharded over the ranks, 2 rows replicated + sweep sharded (before ga_create)"""
+        self.check(self.lib.pnol_ga_set_sharding(self.h, int(mode)))
 
     def ga_pop_sort(self, xpop, F):
         xpop, F = _f64(xpop).copy(), _f64(F).copy()

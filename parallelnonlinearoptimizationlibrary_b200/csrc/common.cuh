@@ -55,6 +55,8 @@ struct pnol_ctx {
 	int comm_rank = 0;
 	int comm_nranks = 1;
 
+	int ga_sharding = 0;           // pnol_ga_set_sharding: 0 auto, 1 rows, 2 sweep
+
 	// timers
 	bool timers_on = false;
 	std::map<std::string, PnolTimerEntry> timers;

@@ -1007,6 +1007,14 @@ extern "C" int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * s)
 	return PNOL_OK;
 }
 
+extern "C" int pnol_ga_set_sharding(pnol_ctx * ctx, int mode)
+{
+	if (!ctx) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, mode >= 0 && mode <= 2, "ga_set_sharding: mode %d (0 auto, 1 rows, 2 sweep)", mode);
+	ctx->ga_sharding = mode;
+	return PNOL_OK;
+}
+
 extern "C" int pnol_ga_peer_mode(pnol_ga * ga)
 {
 	return ga ? ga_pipe_peer_mode(ga) : 0;

@@ -954,6 +954,8 @@ struct GaPipe {
 	void * peer_maps[2][kGaMaxRanks] = {};           // IPC mappings to close
 	double * replica[2] = {nullptr, nullptr};        // fallback without peer mappings: full copies refreshed by all-gather
 	bool use_ipc = false;
+	int R = 1;                                        // row partitions: the communicator's ranks (rows sharded) or 1 (rows replicated, sweep sharded)
+	long long eper = 0;                               // rows replicated: rows of the fitness sweep per rank
 	// replicated per-row arrays (sorted order: Fs, ratio, perm; child order: hash, bcount, dupflag, Fchild, offs)
 	unsigned * perm[2] = {nullptr, nullptr};
 	double * Fs[2] = {nullptr, nullptr};
@@ -1064,13 +1066,31 @@ int ga_pipe_create(pnol_ga * ga)
 {
 	pnol_ctx * ctx = ga->ctx;
 	const long long Npop = ga->prm.npop;
-	const int n = ga->n, R = ctx->nranks;
-	PNOL_REQUIRE(ctx, R <= kGaMaxRanks, "ga: at most %d ranks", kGaMaxRanks);
+	const int n = ga->n;
+	PNOL_REQUIRE(ctx, ctx->nranks <= kGaMaxRanks, "ga: at most %d ranks", kGaMaxRanks);
 	GaPipe * P = new GaPipe();
 	ga->pipe = P;
+	// Several GPUs, two ways to split a generation (pnol_ga_set_sharding; PNOL_GA_SHARD=rows|sweep overrides):
+	//   rows  : rank r owns child rows [r per, (r+1) per): it creates, repairs and evaluates them, parents are read from their
+	//           owners over NVLink. Memory per GPU falls with the GPU count; at 1M x 32 the gene-wise parent reads (8 bytes each,
+	//           millions of them per rank) are latency-bound on the link and the generation is SLOWER than on one GPU
+	//           (1.41 against 1.09 ms at 2 GPUs, profiles/).
+	//   sweep : every rank keeps the whole population and makes all children (no row ever crosses a link); the fitness sweep
+	//           is split and the objective values are all-gathered, as in the reference's evaluatePopulationParallel.
+	// auto = sweep while two copies of the population fit in a quarter of the GPU's memory, rows beyond.
+	int mode = ctx->ga_sharding;
+	if (const char * e = getenv("PNOL_GA_SHARD")) { if (!strcmp(e, "rows")) mode = 1; else if (!strcmp(e, "sweep")) mode = 2; }
+	if (mode == 0) {
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		mode = ((size_t) Npop * n * 16 > total_b / 4) ? 1 : 2;
+	}
+	const int R = (ctx->nranks > 1 && mode == 1) ? ctx->nranks : 1;
+	P->R = R;
 	P->per = (Npop + R - 1) / R;
-	P->lo = std::min<long long>(P->per * ctx->rank, Npop);
-	P->hi = std::min<long long>(P->lo + P->per, Npop);
+	P->lo = R > 1 ? std::min<long long>(P->per * ctx->rank, Npop) : 0;
+	P->hi = R > 1 ? std::min<long long>(P->lo + P->per, Npop) : Npop;
+	P->eper = (Npop + ctx->nranks - 1) / ctx->nranks;
 	for (int b = 0; b < 2; b++) {
 		PNOL_CHECK(pipe_alloc(ga, &P->XL[b], (size_t) P->per * n));
 		PNOL_CHECK(pipe_alloc(ga, &P->perm[b], (size_t) Npop));
@@ -1083,7 +1103,7 @@ int ga_pipe_create(pnol_ga * ga)
 		P->table[b].base[0] = P->XL[b];
 	}
 	PNOL_CHECK(pipe_alloc(ga, &P->ratio, (size_t) Npop));
-	PNOL_CHECK(pipe_alloc(ga, &P->Fchild, (size_t) P->per * R));
+	PNOL_CHECK(pipe_alloc(ga, &P->Fchild, std::max((size_t) P->per * R, (size_t) P->eper * ctx->nranks)));
 	PNOL_CHECK(pipe_alloc(ga, &P->bcount, (size_t) P->per * R));
 	PNOL_CHECK(pipe_alloc(ga, &P->dupflag, (size_t) Npop));
 	PNOL_CHECK(pipe_alloc(ga, &P->indicator, (size_t) P->per));
@@ -1122,10 +1142,10 @@ int ga_pipe_create(pnol_ga * ga)
 		P->sort_grid = (int) ((Npop + range - 1) / range);
 		PNOL_CHECK(pipe_alloc(ga, &P->scounts, (size_t) 256 * P->sort_grid));
 	}
+	if (ctx->nranks > 1) PNOL_CHECK(pipe_alloc(ga, &P->f_recv, std::max((size_t) P->per * R, (size_t) P->eper * ctx->nranks)));
 	if (R > 1) {
 		PNOL_CHECK(pipe_alloc(ga, &P->hb_send, (size_t) P->per * 12));
 		PNOL_CHECK(pipe_alloc(ga, &P->hb_recv, (size_t) P->per * 12 * R));
-		PNOL_CHECK(pipe_alloc(ga, &P->f_recv, (size_t) P->per * R));
 		P->use_ipc = pipe_open_peers(ga);
 		if (!P->use_ipc) {
 			for (int b = 0; b < 2; b++) {
@@ -1155,7 +1175,7 @@ void ga_pipe_destroy(pnol_ga * ga)
 static int pipe_refresh_replica(pnol_ga * ga, int b)
 {
 	GaPipe * P = ga->pipe;
-	if (ga->ctx->nranks <= 1 || P->use_ipc) return PNOL_OK;
+	if (P->R <= 1 || P->use_ipc) return PNOL_OK;
 	return comm_allgather_dev(ga->ctx, P->XL[b], P->replica[b], (size_t) P->per * ga->n);
 }
 
@@ -1193,7 +1213,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 {
 	pnol_ctx * ctx = ga->ctx;
 	GaPipe * P = ga->pipe;
-	const int Npop = ga->prm.npop, n = ga->n, R = ctx->nranks;
+	const int Npop = ga->prm.npop, n = ga->n, R = P->R;
 	const long long Nelite = ga->nelite, Ncross = ga->ncross, Nrand = ga->nrand, NeliteMut = ga->nelmut;
 	const int cur = P->cur, nxt = cur ^ 1;
 	const RowTable & T = P->table[cur];
@@ -1342,7 +1362,15 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 			            P->dupflag, P->bcount, P->offs, Xloc, P->indicator);
 	}
 	// 6. the fitness sweep over this rank's rows (:217)
-	if (hi > lo) PNOL_CHECK(launch_eval_batch(ctx, ga->f, Xloc, hi - lo, n, n, P->indicator, P->Fchild + lo));
+	if (R == 1 && ctx->nranks > 1) {
+		// rows replicated: this rank sweeps individuals [r eper, (r+1) eper) and the objective values are all-gathered
+		// (GeneticAlgorithmMPI::evaluatePopulationParallel, Source/GeneticAlgorithmMPI.cpp:283-414)
+		const long long elo = std::min<long long>(P->eper * ctx->rank, Npop), ehi = std::min<long long>(elo + P->eper, Npop);
+		if (ehi > elo) PNOL_CHECK(launch_eval_batch(ctx, ga->f, Xloc + elo * n, ehi - elo, n, n, P->indicator + elo, P->Fchild + elo));
+		TimerScope ts(ctx, "ga_gather_f");
+		PNOL_CHECK(comm_allgather_dev(ctx, P->Fchild + elo, P->f_recv, (size_t) P->eper));
+		PNOL_CUDA(ctx, cudaMemcpyAsync(P->Fchild, P->f_recv, (size_t) Npop * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+	} else if (hi > lo) PNOL_CHECK(launch_eval_batch(ctx, ga->f, Xloc, hi - lo, n, n, P->indicator, P->Fchild + lo));
 	if (R > 1) {
 		TimerScope ts(ctx, "ga_gather_f");
 		// rows that were not evaluated (elites) already hold the same value on every rank, so gathering whole blocks is exact
@@ -1405,7 +1433,7 @@ int ga_pipe_generation(pnol_ga * ga)
 			(void) g;
 		}
 		P->pos_elite_last = H.pos_elite;
-		P->elite_idx_complete = ctx->nranks <= 1;
+		P->elite_idx_complete = P->R <= 1;
 		P->cur ^= 1;
 		ga->pos = H.pos_end;
 		const double Fbest = H.fbest;
@@ -1421,6 +1449,7 @@ int ga_pipe_generation(pnol_ga * ga)
 int ga_pipe_peer_mode(pnol_ga * ga)
 {
 	if (!ga->pipe || ga->ctx->nranks <= 1) return 0;
+	if (ga->pipe->R <= 1) return 3;
 	return ga->pipe->use_ipc ? 1 : 2;
 }
 

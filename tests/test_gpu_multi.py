@@ -36,7 +36,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, shard):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -47,6 +47,7 @@ def _worker(rank, world, port, out_dir):
     launch.init_process_group("nccl")
     ctx = capi.Context(rank)
     assert launch.attach_communicator(ctx) == world and ctx.comm_size() == world and ctx.comm_rank() == rank
+    ctx.ga_set_sharding(shard)                     # 1: GA rows sharded over the ranks, 2: rows replicated + sweep sharded
     # raw all-reduce
     buf = np.arange(5, dtype=np.float64) + rank
     ctx.allreduce_sum(buf, 5)
@@ -96,7 +97,7 @@ def _worker(rank, world, port, out_dir):
     stream = dict(seed=4242, scale=1.0 - 1.0 / npop)
     fr = ctx.functor(capi.F_RASTRIGIN)
     ga = ctx.ga_create(fr, n, lb, ub, npop, gens, stream)
-    assert ga.peer_mode() == (2 if os.environ.get("PNOL_GA_NO_IPC") == "1" else ga.peer_mode()) and ga.peer_mode() in (1, 2)
+    assert ga.peer_mode() == (3 if shard == 2 else (2 if os.environ.get("PNOL_GA_NO_IPC") == "1" else ga.peer_mode())) and ga.peer_mode() in (1, 2, 3)
     np.save(os.path.join(out_dir, "peer_mode_%d.npy" % rank), np.array([ga.peer_mode()]))
     ga.init(x0)
     for gen in range(1, gens + 1):
@@ -119,16 +120,18 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,no_ipc", [(2, 0), (2, 1), (4, 0), (8, 0), (8, 1)])
-def test_sharded_paths_match_the_reference(tmp_path, world, no_ipc, monkeypatch):
-    """no_ipc = 1: the GA rows are shared through replicas + all-gather (PNOL_GA_NO_IPC=1) instead of CUDA IPC peer mappings"""
+@pytest.mark.parametrize("world,shard,no_ipc", [(2, 1, 0), (2, 1, 1), (2, 2, 0), (4, 1, 0), (8, 1, 0), (8, 1, 1), (8, 2, 0)])
+def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, monkeypatch):
+    """shard = 1: GA rows sharded over the ranks (no_ipc = 1: through replicas + all-gather, PNOL_GA_NO_IPC=1, instead of CUDA IPC
+    peer mappings); shard = 2: GA rows replicated, fitness sweep sharded"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     monkeypatch.setenv("PNOL_GA_NO_IPC", str(no_ipc))
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shard), nprocs=world, join=True)
     modes = {int(np.load(tmp_path / ("peer_mode_%d.npy" % r))[0]) for r in range(world)}
-    assert len(modes) == 1 and (no_ipc == 0 or modes == {2}), "every rank takes the same path"
+    assert len(modes) == 1, "every rank takes the same path"
+    assert modes == ({3} if shard == 2 else ({2} if no_ipc else modes)) and modes <= {1, 2, 3}
     print("GA peer mode at world %d: %s" % (world, modes))
     G = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden.npz"))
     GB = np.load(os.path.join(ROOT, "tests", "golden", "baseline_lm_golden.npz"))
