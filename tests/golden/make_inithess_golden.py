@@ -47,12 +47,19 @@ def main():
         ev = np.linalg.eigvalsh(0.5 * (B + B.T))
         assert ev.min() < 0 < ev.max(), "the start point must have an indefinite FD Hessian"
         r = O.ref_cli(variant, arrays=arrays, obj=obj, maxiter=iters, inithess=1, nprocs=nprocs, **prm)
-        r1 = O.ref_cli(variant, arrays=dict(arrays, x=np.nextafter(x0, x0 + 1.0) * np.array([1] + [0] * (n - 1)) + x0 * np.array([0] + [1] * (n - 1))),
-                       obj=obj, maxiter=iters, inithess=1, nprocs=nprocs, **prm)
+        # the reference's own sensitivity: every start coordinate moved by one ulp, up and down (one coordinate alone can sit in a
+        # flat direction: coordinate 0 of X0 moves the iterates by 5e-17, coordinate 1 by 3e-8)
+        twins = []
+        for j in range(n):
+            for d in (1.0, -1.0):
+                xt = x0.copy()
+                xt[j] = np.nextafter(xt[j], xt[j] + d)
+                twins.append(O.ref_cli(variant, arrays=dict(arrays, x=xt), obj=obj, maxiter=iters, inithess=1, nprocs=nprocs, **prm)["X"])
+        sens = np.array([np.linalg.norm(t - r["X"]) / np.linalg.norm(r["X"]) for t in twins])
         G[name + "/x0"], G[name + "/X"], G[name + "/f0"], G[name + "/fOpt"], G[name + "/B"] = x0, r["X"], r["f0"], r["fOpt"], B
-        G[name + "/X_ulp"] = r1["X"]
-        print(name, "eig(B) in [%.3g, %.3g]" % (ev.min(), ev.max()), "fOpt", r["fOpt"], "X", r["X"], "ulp twin moves X by",
-              np.linalg.norm(r1["X"] - r["X"]) / np.linalg.norm(r["X"]))
+        G[name + "/X_ulp"] = twins[int(np.argmax(sens))]
+        G[name + "/sens_all"] = sens
+        print(name, "eig(B) in [%.3g, %.3g]" % (ev.min(), ev.max()), "fOpt", r["fOpt"], "X", r["X"], "one-ulp twins move X by", sens)
     out = os.path.join(HERE, "inithess_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out)
