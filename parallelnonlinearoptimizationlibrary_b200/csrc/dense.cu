@@ -401,11 +401,66 @@ matvec_kernel(const double * __restrict__ D, const double * __restrict__ g, int 
 	if (lane == 0) out[row] = scale * s;
 }
 
+// 256-bit global loads (one full 32-byte sector per lane and load). D is streamed (134 MB at n = 4096: larger than L2), so it
+// bypasses L1; the vectors (g, s, v: 32 KB each) are re-read by every warp and stay in L1.
+__device__ __forceinline__ void ldg256_stream(const double * p, double (&v)[4])
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_cached(const double * p, double (&v)[4])
+{
+	asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// n a multiple of 4, D 32-byte aligned: one warp per row, every lane keeps kMvUnroll 256-bit loads of the row in flight (4 KB per
+// warp and batch) and four independent FMA chains. The first version read one double per lane and load (256 B per warp in
+// flight per dependent step) and ran at 0.53 of the HBM roofline at n = 4096; blocks of 64 threads so that the 4096 rows spread
+// evenly over the 148 SMs (512 blocks of 8 warps left 4 : 3 blocks per SM).
+constexpr int kMvUnroll = 4;
+constexpr int kMvThreads = 64;
+
+__global__ void __launch_bounds__(kMvThreads)
+matvec_v4_kernel(const double * __restrict__ D, const double * __restrict__ g, int n, double scale, double * __restrict__ out)
+{
+	const int row = (int) (((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (row >= n) return;
+	const double * Dr = D + (long long) row * n;
+	double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+	for (int k0 = lane * 4; k0 < n; k0 += 128 * kMvUnroll) {
+		double d[kMvUnroll][4], gv[kMvUnroll][4];
+#pragma unroll
+		for (int q = 0; q < kMvUnroll; q++) {
+			const int k = k0 + 128 * q;
+			if (k < n) ldg256_stream(Dr + k, d[q]);
+		}
+#pragma unroll
+		for (int q = 0; q < kMvUnroll; q++) {
+			const int k = k0 + 128 * q;
+			if (k < n) ldg256_cached(g + k, gv[q]);
+		}
+#pragma unroll
+		for (int q = 0; q < kMvUnroll; q++) {
+			const int k = k0 + 128 * q;
+			if (k < n) {
+				s0 = fma(d[q][0], gv[q][0], s0); s1 = fma(d[q][1], gv[q][1], s1);
+				s2 = fma(d[q][2], gv[q][2], s2); s3 = fma(d[q][3], gv[q][3], s3);
+			}
+		}
+	}
+	double s = (s0 + s1) + (s2 + s3);
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if (lane == 0) out[row] = scale * s;
+}
+
 int launch_matvec_neg(pnol_ctx * ctx, const double * D, const double * g, int n, double * p)
 {
 	TimerScope ts(ctx, "matvec_neg");
 	long long threads = (long long) n * 32;
-	PNOL_LAUNCH(ctx, matvec_kernel, (unsigned) ((threads + 255) / 256), 256, 0, D, g, n, -1.0, p);
+	if (n % 4 == 0 && (((size_t) D) & 31) == 0 && (((size_t) g) & 31) == 0)
+		PNOL_LAUNCH(ctx, matvec_v4_kernel, (unsigned) ((threads + kMvThreads - 1) / kMvThreads), kMvThreads, 0, D, g, n, -1.0, p);
+	else
+		PNOL_LAUNCH(ctx, matvec_kernel, (unsigned) ((threads + 255) / 256), 256, 0, D, g, n, -1.0, p);
 	return PNOL_OK;
 }
 
@@ -512,9 +567,179 @@ hinv_pass2_scalar_kernel(double * __restrict__ D, const double * __restrict__ s,
 	}
 }
 
+// ---- fast path of the rank-2 form (n a multiple of 4, D 32-byte aligned): three launches, 256-bit loads -------------------------
+// pass 1: tile = R rows x 256 columns per block of 8 warps (R a multiple of 4, chosen by the launcher so that the grid is a whole
+// number of waves). A lane owns 8 columns (two groups of four) and keeps their column sums v in REGISTERS over the rows of its warp
+// (the first version kept them in shared memory: one LDS + one STS per element of D); a warp takes four rows per batch, i.e. eight
+// 256-bit loads per lane in flight. The warps' column sums are added in warp order in shared memory: one partial row per block.
+// Partials: upart[column block][row], vpart[row block][column].
+constexpr int kR4Cols = 256;
+
+__global__ void __launch_bounds__(256, 2)
+hinv_pass1_v4_kernel(const double * __restrict__ D, const double * __restrict__ g, int n, int R, double * __restrict__ upart,
+                     double * __restrict__ vpart)
+{
+	__shared__ double vs[8][kR4Cols];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int r0 = blockIdx.x * R, r1 = min(n, r0 + R);
+	const int c0 = blockIdx.y * kR4Cols + lane * 4;
+	double v[2][4], gc[2][4];
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+#pragma unroll
+		for (int e = 0; e < 4; e++) { v[q][e] = 0; gc[q][e] = 0; }
+		if (c0 + 128 * q < n) ldg256_cached(g + c0 + 128 * q, gc[q]);
+	}
+	for (int row = r0 + warp * 4; row < r1; row += 32) {
+		const double * Dr = D + (long long) row * n + c0;
+		double d[4][2][4];
+#pragma unroll
+		for (int h = 0; h < 4; h++)
+#pragma unroll
+			for (int q = 0; q < 2; q++)
+				if (row + h < r1 && c0 + 128 * q < n) ldg256_stream(Dr + (long long) h * n + 128 * q, d[h][q]);
+#pragma unroll
+		for (int h = 0; h < 4; h++) {
+			if (row + h >= r1) break;
+			const double gi = g[row + h];
+			double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+			for (int q = 0; q < 2; q++) {
+				if (c0 + 128 * q < n) {
+					s0 = fma(d[h][q][0], gc[q][0], s0); s1 = fma(d[h][q][1], gc[q][1], s1);
+					s2 = fma(d[h][q][2], gc[q][2], s2); s3 = fma(d[h][q][3], gc[q][3], s3);
+#pragma unroll
+					for (int e = 0; e < 4; e++) v[q][e] = fma(gi, d[h][q][e], v[q][e]);
+				}
+			}
+			double s = (s0 + s1) + (s2 + s3);
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			if (lane == 0) upart[(size_t) blockIdx.y * n + row + h] = s;
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < 2; q++)
+		*reinterpret_cast<double4 *>(&vs[warp][lane * 4 + 128 * q]) = make_double4(v[q][0], v[q][1], v[q][2], v[q][3]);
+	__syncthreads();
+	const int c = blockIdx.y * kR4Cols + threadIdx.x;
+	if (c < n) {
+		double t = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) t = t + vs[w][threadIdx.x];
+		vpart[(size_t) blockIdx.x * n + c] = t;
+	}
+}
+
+// finish: out[k] = sum over parts, fixed order. A block takes 32 columns x 8 part groups (all loads of a thread independent), the
+// eight group sums of a column are added in order. blockIdx.y = 0: v from vpart, 1: u from upart.
+__global__ void __launch_bounds__(256)
+hinv_finish_v4_kernel(const double * __restrict__ vpart, int nvparts, const double * __restrict__ upart, int nuparts, int n,
+                      double * __restrict__ v, double * __restrict__ u)
+{
+	__shared__ double red[8][33];
+	const double * part = blockIdx.y ? upart : vpart;
+	const int nparts = blockIdx.y ? nuparts : nvparts;
+	double * out = blockIdx.y ? u : v;
+	const int c = threadIdx.x & 31, pg = threadIdx.x >> 5;
+	const int k = blockIdx.x * 32 + c;
+	const int per = (nparts + 7) / 8;
+	double s = 0;
+	if (k < n) {
+		const int p1 = min(nparts, (pg + 1) * per);
+#pragma unroll 8
+		for (int p = pg * per; p < p1; p++) s = s + part[(size_t) p * n + k];
+	}
+	red[pg][c] = s;
+	__syncthreads();
+	if (pg == 0 && k < n) {
+		double t = 0;
+#pragma unroll
+		for (int q = 0; q < 8; q++) t = t + red[q][c];
+		out[k] = t;
+	}
+}
+
+// pass 2: D_ij += -rho s_i v_j - rho u_i s_j + (rho^2 gamma + rho) s_i s_j, products associated as in hinv_pass2_kernel (same bits).
+// Every block first computes g.s and g.u itself (fixed-order tree over 256 threads: identical in every block; saves the one-block
+// dot-product launch), then walks (row, 1024-column chunk) items, four items' 256-bit loads in flight per thread.
+__global__ void __launch_bounds__(256)
+hinv_pass2_v4_kernel(double * __restrict__ D, const double * __restrict__ g, const double * __restrict__ s, const double * __restrict__ u,
+                     const double * __restrict__ v, int n, double * __restrict__ scal_out)
+{
+	__shared__ double r0[256], r1[256];
+	{
+		double a = 0, b = 0;
+		for (int k = threadIdx.x; k < n; k += 256) { a = fma(g[k], s[k], a); b = fma(g[k], u[k], b); }
+		r0[threadIdx.x] = a; r1[threadIdx.x] = b;
+		__syncthreads();
+		for (int o = 128; o > 0; o >>= 1) {
+			if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
+			__syncthreads();
+		}
+	}
+	const double gs = r0[0], gu = r1[0];
+	if (blockIdx.x == 0 && threadIdx.x == 0 && scal_out) { scal_out[0] = gs; scal_out[1] = gu; }
+	const double rho = 1.0 / gs;
+	const double cc = rho * rho * gu + rho;
+	const int chunks = (n + 1023) / 1024;
+	const long long items = (long long) n * chunks;
+	const int col = threadIdx.x * 4;
+	for (long long it0 = blockIdx.x; it0 < items; it0 += (long long) gridDim.x * 4) {
+		double d[4][4];
+		int row[4], cj[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const long long it = it0 + (long long) q * gridDim.x;
+			row[q] = (int) (it / chunks);
+			cj[q] = (int) (it - (long long) row[q] * chunks) * 1024 + col;
+			if (it >= items || cj[q] >= n) row[q] = -1;
+			if (row[q] >= 0) ldg256_stream(D + (long long) row[q] * n + cj[q], d[q]);
+		}
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if (row[q] < 0) continue;
+			const double si = s[row[q]], ui = u[row[q]];
+			const double a = -rho * si, b = rho * ui, c = cc * si;
+			double sv[4], vv[4];
+			ldg256_cached(s + cj[q], sv);
+			ldg256_cached(v + cj[q], vv);
+			double o[4];
+#pragma unroll
+			for (int e = 0; e < 4; e++) o[e] = d[q][e] + (a * vv[e] - b * sv[e] + c * sv[e]);
+			*reinterpret_cast<double4 *>(D + (long long) row[q] * n + cj[q]) = make_double4(o[0], o[1], o[2], o[3]);
+		}
+	}
+}
+
 int launch_hinv_rank2(pnol_ctx * ctx, double * D, const double * g, const double * s, int n)
 {
 	TimerScope ts(ctx, "hinv_rank2");
+	if (n % 4 == 0 && (((size_t) D) & 31) == 0 && (((size_t) g) & 31) == 0 && (((size_t) s) & 31) == 0) {
+		// row blocks: about 112 rows each, rounded so that the grid is a whole number of waves of 2 resident blocks per SM
+		const int ncb = (n + kR4Cols - 1) / kR4Cols;
+		const int wave = ctx->sm_count * 2;
+		int nrb = (n + 111) / 112;
+		const long long waves = ((long long) nrb * ncb + wave / 2) / wave;
+		if (waves >= 1) nrb = (int) ((waves * wave) / ncb);
+		if (nrb < 1) nrb = 1;
+		int R = ((n + nrb - 1) / nrb + 3) & ~3;
+		nrb = (n + R - 1) / R;
+		const int nvparts = nrb;
+		const size_t n4 = ((size_t) n + 3) & ~(size_t) 3;
+		PNOL_CHECK(ws_reserve(ctx, 1, (2 * n4 + 4 + (size_t) nvparts * n + (size_t) ncb * n) * sizeof(double)));
+		double * u = (double *) ctx->ws[1];
+		double * v = u + n4;
+		double * scal = v + n4;
+		double * vpart = scal + 4;
+		double * upart = vpart + (size_t) nvparts * n;
+		PNOL_LAUNCH(ctx, hinv_pass1_v4_kernel, dim3(nrb, ncb), 256, 0, D, g, n, R, upart, vpart);
+		PNOL_LAUNCH(ctx, hinv_finish_v4_kernel, dim3((n + 31) / 32, 2), 256, 0, vpart, nvparts, upart, ncb, n, v, u);
+		const long long items = (long long) n * ((n + 1023) / 1024);
+		long long grid = (long long) ctx->sm_count * 2 * 4;      // 2 resident blocks per SM (86 registers): four whole waves
+		if (grid > items) grid = items;
+		PNOL_LAUNCH(ctx, hinv_pass2_v4_kernel, (unsigned) grid, 256, 0, D, g, s, u, v, n, scal);
+		return PNOL_OK;
+	}
 	int nrb = (n + kR2Rows - 1) / kR2Rows;
 	int ncb = (n + kR2Cols - 1) / kR2Cols;
 	size_t need = ((size_t) 2 * n + 2 + (size_t) nrb * n + (size_t) ncb * n) * sizeof(double);
