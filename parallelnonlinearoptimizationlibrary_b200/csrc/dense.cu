@@ -4,6 +4,18 @@
 
 namespace pnol {
 
+// 256-bit global loads (one full 32-byte sector per lane and load). D is streamed (134 MB at n = 4096: larger than L2), so it
+// bypasses L1; the vectors (g, s, v: 32 KB each) are re-read by every warp and stay in L1.
+__device__ __forceinline__ void ldg256_stream(const double * p, double (&v)[4])
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_cached(const double * p, double (&v)[4])
+{
+	asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+
 // ---------------------------------------------------------------------------------------------------
 // a9: A = JTJ, A_ii = (1 + lambda) JTJ_ii ; rhs = -J^T F     (Source/LevenbergMarquardtMPI.cpp:66-85)
 // ---------------------------------------------------------------------------------------------------
@@ -37,17 +49,24 @@ int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, 
 // a9: SPD solve  A x = b  by right-looking blocked Cholesky on ONE thread-block cluster of 8 CTAs.
 // Replaces luSolve (Source/LevenbergMarquardtMPI.cpp:88).
 //
-// The work is 5.6 MFLOP at n = 256 -- nothing; the cost is the length of the dependency chain. The first version ran in
-// one CTA (0.56 ms: a 30 us serial rank-1 loop per diagonal block and read-modify-write round trips to L2 in the trailing
-// update). Here:
+// The work is 5.6 MFLOP at n = 256 -- nothing; the cost is the length of the dependency chain and the number of L2 round trips
+// on it. History: one CTA 0.56 ms; 8-CTA cluster with a shuffle Cholesky of the diagonal block 0.183 ms, of which (phase
+// timestamps, tools/solve_stamps.py) 65 us were the eight 32 x 32 diagonal factorisations (485 cycles per pivot: MUFU.RSQ64H,
+// three Newton steps, a correction of the root and 31 64-bit shuffles, all behind one another), 31 us trailing updates and 13 us
+// the copy into the work matrix (both waiting for L2 once per loop trip), 26 us the back substitution (ditto). Now:
 //   * the matrix W is (n+1) x n in global memory (L2 resident): rows 0..n-1 the lower triangle of A, row n = b. Carrying b
 //     as an extra row makes the forward substitution L y = b fall out of the factorisation (the panel solve of that row IS
 //     y_k = L_kk^-1 (b_k - ...), its trailing update IS the forward-substitution update), so only L^T x = y remains;
-//   * per 32-column block step: every CTA factors the 32 x 32 diagonal block redundantly (one warp, one matrix row per lane in
-//     REGISTERS, shuffles instead of shared-memory round trips), so no barrier separates it from the panel solve; panel rows
-//     (one thread per row) and the trailing update (one warp per row, lanes along the columns, the whole panel staged in
-//     shared memory) are spread over the 8 x 256 threads of the cluster; two cluster barriers per step order the phases;
-//   * CTA 0 finishes with the blocked back substitution.
+//   * per 32-column block step every CTA factors the 32 x 32 diagonal block redundantly (one warp, one matrix row per lane in
+//     REGISTERS) as L' D L'^T: the chain per pivot is one broadcast, one reciprocal (MUFU.RCP64H + 5 FMA) and two FMA; the
+//     column values the update needs are shuffled BEFORE the reciprocal is known. 1/sqrt(d) is taken for all 32 pivots at once
+//     at the end (L = L' sqrt(D));
+//   * panel rows: one thread per row, right-looking unit-triangular substitution (one FMA per step on the chain) with L' read as
+//     shared-memory broadcasts; trailing update: one warp per row (fixed owner: row mod 64), lanes along the columns, the whole
+//     panel staged in shared memory; every global load of a phase is issued before its first use (256-bit where aligned);
+//   * two cluster barriers per step order the phases;
+//   * CTA 0 finishes with the blocked back substitution; the block row of L the next step needs is copied into shared memory
+//     (cp.async) while the current step computes.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kCholNB = 32;
 constexpr int kCholThreads = 256;
@@ -81,178 +100,417 @@ __device__ __forceinline__ double rsqrt_nr(double d)
 	return y;
 }
 
-// Cholesky of a 32 x 32 block by one warp: lane r holds row r (lower part) in registers. On return row[] holds L (lane r:
-// L[r][0..r]) and inv_diag the reciprocal of this lane's diagonal entry; bad_col is the first non-positive pivot (1-based
-// inside the block, 0 = none). Rows / columns past the block's real size must have been padded with the identity.
-// (one template instantiation per column: a doubly nested `#pragma unroll` is only partially honoured at 496 bodies, and a
-// dynamic index would push row[] into local memory)
-template <int J> struct CholColumn {
-	__device__ __forceinline__ static void run(double (&row)[kCholNB], int lane, int & bad_col, double & inv_diag)
+// 1/d for a positive normal d: MUFU.RCP64H seed, one cubic and one quadratic step (the sequence nvcc itself emits in front of a
+// division), five dependent FMA
+__device__ __forceinline__ double rcp_nr(double d)
+{
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+	double e = fma(-d, y, 1.0);
+	e = fma(e, e, e);
+	y = fma(y, e, y);
+	e = fma(-d, y, 1.0);
+	return fma(y, e, y);
+}
+
+// L' D L'^T of a 32 x 32 block by one warp: lane r holds row r (lower part) in registers. On return row[c], c < r, holds L'[r][c]
+// (unit lower triangle) and d_mine the pivot d_r of this lane; bad_col is the first non-positive pivot (1-based inside the
+// block, 0 = none; the arithmetic goes on with it, the caller discards the result). Rows / columns past the block's real size
+// must have been padded with the identity. Entries above the diagonal (row[c], c > lane) take meaningless updates and are
+// never read by a valid lane.
+// Column J's values a'[.][J] travel through row J of a 32 x 32 shared-memory array (one STS, one __syncwarp, broadcast LDS)
+// rather than through shuffles: the warp runs under `if (warp == 0)`, where the compiler cannot prove convergence and brackets
+// every __shfl_sync with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE (measured: 485 cycles per pivot with 31 shuffles per column; all
+// eight warps factoring redundantly at the top level, plain SHFL: 326 cycles, issue-bound).
+// Two levels: inside a group of 8 columns a pivot is followed only by the updates of the group's own columns, the next column
+// first and out to shared memory at once (the chain: LDS, MUFU.RCP64H + 5 FMA, one multiply, one FMA, STS); the columns right of
+// the group take the group's eight updates in one bulk pass. (With all 31 - J updates behind every pivot ptxas put the
+// store that the next pivot waits for behind them: 330 cycles per pivot.)
+// (template recursion: a doubly nested `#pragma unroll` is only partially honoured at 496 bodies, and a dynamic index would
+// push row[] into local memory)
+constexpr int kLdlGroup = 8;
+
+template <int J> struct LdlColumn {
+	// on entry row J of bc holds column J (a'[r][J] of every lane r), published by the previous column / bulk pass / caller
+	__device__ __forceinline__ static void run(double (&row)[kCholNB], int lane, int & bad_col, double & d_mine, double * bc)
 	{
-		double d = __shfl_sync(0xffffffffu, row[J], J);
-		const bool okp = d > 0.0 && d < 0x1p1000;          // false for NaN / inf too
-		if (!okp) { if (bad_col == 0) bad_col = J + 1; d = 1.0; }
-		const double inv = rsqrt_nr(d);
-		double sd = d * inv;
-		sd = fma(fma(-sd, sd, d), 0.5 * inv, sd);          // one correction step on the square root itself
-		const double lj = (lane == J) ? sd : row[J] * inv; // column J of L (meaningful for lane >= J)
-		if (lane == J) inv_diag = inv;
-		row[J] = lj;
-#pragma unroll
-		for (int c = J + 1; c < kCholNB; c++) {
-			const double v = __shfl_sync(0xffffffffu, lj, c);  // L[c][J]
-			row[c] = (lane >= c) ? fma(-lj, v, row[c]) : row[c];
+		constexpr int kEnd = (J / kLdlGroup + 1) * kLdlGroup;      // first column right of J's group
+		const double * col = bc + J * kCholNB;
+		const double d = col[J];                                   // the pivot
+		if (!(d > 0.0 && d < 0x1p1000) && bad_col == 0) bad_col = J + 1;
+		if (lane == J) d_mine = d;
+		const double l = row[J] * rcp_nr(d);                       // L'[r][J] (meaningful for lane > J)
+		if (J + 1 < kEnd) {
+			constexpr int N = J + 1 < kCholNB ? J + 1 : J;
+			row[N] = fma(-l, col[N], row[N]);
+			bc[N * kCholNB + lane] = row[N];
+			__syncwarp();
 		}
-		CholColumn<J + 1>::run(row, lane, bad_col, inv_diag);
+#pragma unroll
+		for (int c = J + 2; c < kEnd; c++) row[c] = fma(-l, col[c], row[c]);
+		row[J] = l;
+		if (J + 1 == kEnd && kEnd < kCholNB) {
+			// bulk pass: the columns right of the group take its kLdlGroup updates (independent chains of 8 FMA)
+#pragma unroll
+			for (int c = kEnd; c < kCholNB; c++) {
+#pragma unroll
+				for (int t = kEnd - kLdlGroup; t < kEnd; t++) row[c] = fma(-row[t], bc[t * kCholNB + c], row[c]);
+				if (c == kEnd) {
+					bc[(kEnd < kCholNB ? kEnd : 0) * kCholNB + lane] = row[c];
+					__syncwarp();
+				}
+			}
+		}
+		LdlColumn<J + 1>::run(row, lane, bad_col, d_mine, bc);
 	}
 };
-template <> struct CholColumn<kCholNB> {
-	__device__ __forceinline__ static void run(double (&)[kCholNB], int, int &, double &) {}
+template <> struct LdlColumn<kCholNB> {
+	__device__ __forceinline__ static void run(double (&)[kCholNB], int, int &, double &, double *) {}
 };
-__device__ __forceinline__ void warp_chol32(double (&row)[kCholNB], int lane, int & bad_col, double & inv_diag)
+
+__device__ __forceinline__ void dmma_8x8x4_acc(double & d0, double & d1, double a, double b)
 {
-	bad_col = 0;
-	inv_diag = 1.0;
-	CholColumn<0>::run(row, lane, bad_col, inv_diag);
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+// tuning aid (-DPNOL_SOLVE_STAMPS, tools/build_variants.sh): CTA 0 / thread 0 writes %globaltimer at the phase boundaries into x
+#ifdef PNOL_SOLVE_STAMPS
+#define SOLVE_STAMP() do { if (cta == 0 && tid == 0 && nstamp < 200) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[nstamp++] = t_; } } while (0)
+#else
+#define SOLVE_STAMP() do { } while (0)
+#endif
+
+__device__ __forceinline__ void ld256(const double * p, double (&v)[4])       // coherent (not .nc): W is rewritten between phases
+{
+	asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc)
+{
+	const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kBsP = kCholNB + 2;      // pitch of the staged diagonal block in the back substitution (rows 16-byte aligned)
+
+// back substitution: stage block row kb of L (diagonal block -> Dd, pitch kBsP; rows kb..kb+nbk-1, columns [0, kb) -> Pd, pitch `pitch`)
+__device__ __forceinline__ void backsub_stage(const double * W, int n, int kb, int nbk, double * Dd, double * Pd, int pitch, bool async_ok, int tid)
+{
+	if (async_ok && nbk == kCholNB) {
+		for (int e = tid; e < kCholNB * (kCholNB / 2); e += kCholThreads) {
+			const int r = e >> 4, c2 = e & 15;
+			cp_async16(Dd + r * kBsP + 2 * c2, W + (long long) (kb + r) * n + kb + 2 * c2);
+		}
+		const int per_row = kb >> 1;                            // 16-byte pieces per row (kb is a multiple of 32)
+		for (int e = tid; e < nbk * per_row; e += kCholThreads) {
+			const int t = e / per_row, c2 = e - t * per_row;
+			cp_async16(Pd + (size_t) t * pitch + 2 * c2, W + (long long) (kb + t) * n + 2 * c2);
+		}
+	} else {
+		for (int e = tid; e < nbk * kCholNB; e += kCholThreads) {
+			const int r = e >> 5, c = e & 31;
+			if (c <= r) Dd[r * kBsP + c] = W[(long long) (kb + r) * n + kb + c];
+		}
+		for (int e = tid; e < nbk * kb; e += kCholThreads) {
+			const int t = e / kb, c = e - t * kb;
+			Pd[(size_t) t * pitch + c] = W[(long long) (kb + t) * n + c];
+		}
+	}
+}
+
+constexpr int kPnP = kCholNB + 4;      // pitch of the staged panel: 8 rows x 4 doubles of a DMMA fragment load hit 32 distinct bank pairs
 
 __global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
 spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs, int n, double * __restrict__ W,
-                 double * __restrict__ x, int * __restrict__ info)
+                 double * __restrict__ x, int * __restrict__ info, int nbuf)
 {
 	extern __shared__ double sm[];
 	constexpr int P = kCholNB + 1;
-	double * Dk = sm;                               // 32 x 33: factored diagonal block
-	double * Dinv = sm + kCholNB * P;               // 32: reciprocals of its diagonal
-	double * Pn = Dinv + kCholNB;                   // up to (n + 1 - 32) x 33: the panel below it (incl. the b row)
+	double * LpT = sm;                              // 32 x 32: LpT[t * 32 + c] = L'[c][t], c > t (unit lower factor of the diagonal block)
+	double * Rsd = sm + kCholNB * kCholNB;          // 32: 1 / sqrt(d)
+	double * Bc = Rsd + kCholNB;                    // 32 x 32: Bc[J * 32 + r] = a'[r][J], the columns of the diagonal factorisation
+	double * Pn = Bc + kCholNB * kCholNB;           // up to round8(n + 1 - 32) x kPnP: the panel below it (incl. the b row)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int cta = (int) cluster_ctarank();
-	const int gtid = tid * kCholCluster + cta;      // cluster-wide thread index, interleaved over the CTAs
-	const int gthreads = kCholThreads * kCholCluster;
+	// the grid is exactly one cluster: blockIdx.x IS the CTA's rank in it
+	const int cta = (int) blockIdx.x;
 	const int gwarp = warp * kCholCluster + cta, gwarps = (kCholThreads / 32) * kCholCluster;
+	const bool vec = (n & 3) == 0 && ((((size_t) A) | ((size_t) W) | ((size_t) rhs)) & 31) == 0;
 	int bad = 0;
+#ifdef PNOL_SOLVE_STAMPS
+	__shared__ unsigned long long stamps[200];
+	int nstamp = 0;
+#endif
+	SOLVE_STAMP();
 
-	// W = [lower(A); b]
-	for (long long e = gtid; e < (long long) n * n; e += gthreads) {
-		const int i = (int) (e / n), j = (int) (e - (long long) i * n);
-		W[e] = (j <= i) ? A[e] : 0.0;
-	}
-	for (int i = gtid; i < n; i += gthreads) W[(long long) n * n + i] = rhs[i];
-	cluster_sync_all();
-
+	// The work matrix W (global, L2-resident) is (n + 1) x n: rows 0..n-1 the lower triangle, row n the right-hand side. Step 0
+	// reads A and rhs themselves (no copy pass): every entry of W that a later step reads has been written by then.
 	for (int kb = 0; kb < n; kb += kCholNB) {
 		const int nbk = min(kCholNB, n - kb);
 		const int r0 = kb + nbk;                    // first row below the diagonal block
 		const int below = n + 1 - r0;               // rows below, b row included
 		const int cbelow = n - r0;                  // columns to the right
-		// ---- A: diagonal block, factored by warp 0 of EVERY CTA (no barrier needed before the panel solve) ----
+		const bool first = kb == 0;
+		const bool vblk = vec && nbk == kCholNB;
+		auto rowsrc = [&](int i) -> const double * { return first ? (i < n ? A + (long long) i * n : rhs) : W + (long long) i * n; };
+
+		// ---- panel rows: warps 1..7, one thread per row; their loads are on the way while warp 0 factors the diagonal block ----
+		const int pri = tid >= 32 ? (tid - 32) * kCholCluster + cta : -1;
+		double v[kCholNB];
+		static_assert(kCholMaxN + 1 <= (kCholThreads - 32) * kCholCluster, "one panel row per thread of warps 1..7");
+		if (pri >= 0 && pri < below) {
+			const double * wsrc = rowsrc(r0 + pri) + kb;
+			if (vblk) {
+#pragma unroll
+				for (int c4 = 0; c4 < kCholNB / 4; c4++) {
+					double t4[4];
+					ld256(wsrc + 4 * c4, t4);
+#pragma unroll
+					for (int e = 0; e < 4; e++) v[4 * c4 + e] = t4[e];
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < kCholNB; c++) v[c] = c < nbk ? wsrc[c] : 0.0;
+			}
+		}
+		// ---- A: diagonal block, factored by warp 0 of EVERY CTA (no cluster barrier needed before the panel solve) ----
 		if (warp == 0) {
 			double row[kCholNB];
+			const double * wr = rowsrc(kb + min(lane, nbk - 1)) + kb;
+			if (vblk) {
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++)
-				row[c] = (lane < nbk && c < nbk) ? (c <= lane ? W[(long long) (kb + lane) * n + kb + c] : 0.0) : (c == lane ? 1.0 : 0.0);
-			int bc;
-			double invd;
-			warp_chol32(row, lane, bc, invd);
+				for (int c4 = 0; c4 < kCholNB / 4; c4++) {
+					double t4[4];
+					ld256(wr + 4 * c4, t4);
+#pragma unroll
+					for (int e = 0; e < 4; e++) row[4 * c4 + e] = (4 * c4 + e <= lane) ? t4[e] : 0.0;
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < kCholNB; c++)
+					row[c] = (lane < nbk && c < nbk) ? (c <= lane ? wr[c] : 0.0) : (c == lane ? 1.0 : 0.0);
+			}
+			int bc = 0;
+			double dm = 1.0;
+#ifdef PNOL_SOLVE_STAMPS
+			if (row[0] == 123.456) bad = 7;      // the loads have landed
+			SOLVE_STAMP();
+#endif
+			Bc[lane] = row[0];
+			__syncwarp();
+			LdlColumn<0>::run(row, lane, bc, dm, Bc);
+#ifdef PNOL_SOLVE_STAMPS
+			if (row[31] == 123.456) bad = 7;
+			SOLVE_STAMP();
+#endif
 			if (bc != 0 && bc <= nbk && bad == 0) bad = kb + bc;
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++) Dk[lane * P + c] = row[c];
-			Dinv[lane] = invd;
+			for (int c = 0; c < kCholNB; c++) LpT[c * kCholNB + lane] = (c < lane) ? row[c] : 0.0;
+			Rsd[lane] = rsqrt_nr(dm);
 		}
 		__syncthreads();
-		// ---- B: panel solve, one thread per row:  X L_kk^T = W[row][kb .. kb+nbk) ----
-		for (int ri = gtid; ri < below; ri += gthreads) {
-			double * wrow = W + (long long) (r0 + ri) * n + kb;
-			double v[kCholNB];
+		SOLVE_STAMP();
+		// ---- B: panel solve  X L_kk^T = W[row][kb .. kb+nbk),  L_kk = L' sqrt(D) ----
+		if (pri >= 0 && pri < below) {
+			// right-looking: once x_t is final every later entry takes its contribution (one FMA on the chain per step)
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++) v[c] = c < nbk ? wrow[c] : 0.0;
+			for (int t = 0; t < kCholNB - 1; t++) {
+				const double xt = v[t];
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++) {
-				double s0 = v[c], s1 = 0;                  // two chains: the dependent FMA latency is what this loop costs
-#pragma unroll
-				for (int t = 0; t + 1 < c; t += 2) { s0 = fma(-v[t], Dk[c * P + t], s0); s1 = fma(-v[t + 1], Dk[c * P + t + 1], s1); }
-				if (c & 1) s0 = fma(-v[c - 1], Dk[c * P + c - 1], s0);
-				v[c] = (s0 + s1) * Dinv[c];
+				for (int c = t + 1; c < kCholNB; c++) v[c] = fma(-xt, LpT[t * kCholNB + c], v[c]);
 			}
 #pragma unroll
-			for (int c = 0; c < kCholNB; c++)
-				if (c < nbk) wrow[c] = v[c];
+			for (int c = 0; c < kCholNB; c++) v[c] = v[c] * Rsd[c];
+			double * wrow = W + (long long) (r0 + pri) * n + kb;
+			if (vblk) {
+#pragma unroll
+				for (int c4 = 0; c4 < kCholNB / 4; c4++)
+					*reinterpret_cast<double4 *>(wrow + 4 * c4) = make_double4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+			} else {
+#pragma unroll
+				for (int c = 0; c < kCholNB; c++)
+					if (c < nbk) wrow[c] = v[c];
+			}
 		}
+		SOLVE_STAMP();
 		cluster_sync_all();
-		// every CTA is past its read of the unfactored diagonal block: CTA 0 may now store the factor (back substitution needs it)
+		SOLVE_STAMP();
+		// CTA 0 stores the factor of the diagonal block for the back substitution (strict lower triangle: L'; diagonal: 1 / sqrt(d))
 		if (cta == 0) {
 			for (int e = tid; e < nbk * kCholNB; e += kCholThreads) {
 				const int r = e >> 5, c = e & 31;
-				if (c <= r) W[(long long) (kb + r) * n + kb + c] = Dk[r * P + c];
+				if (c < r) W[(long long) (kb + r) * n + kb + c] = LpT[c * kCholNB + r];
+				else if (c == r) W[(long long) (kb + r) * n + kb + c] = Rsd[r];
 			}
 		}
-		// ---- C: trailing update  W[i][j] -= sum_t L[i][t] L[j][t]  for r0 <= j <= i (i runs over the b row too) ----
-		for (int e = tid; e < below * kCholNB; e += kCholThreads) {
-			const int ri = e >> 5, c = e & 31;
-			Pn[ri * P + c] = c < nbk ? W[(long long) (r0 + ri) * n + kb + c] : 0.0;
+		// ---- C: trailing update  W[i][j] -= sum_t L[i][t] L[j][t]  for r0 <= j <= i (i runs over the b row too), on the FP64
+		// tensor cores: an item is 8 rows x 32 columns (four m8n8k4 accumulators, the A fragment shared), items dealt round-robin to
+		// the 64 warps of the cluster. The old values of a warp's items are requested before the panel is staged / while the previous
+		// item computes, so that the L2 round trips overlap. (One thread per entry with DFMA: 32 LDS.64 per 32 FMA, shared-memory
+		// bound -- 52 us of a 140 us solve.)
+		const int TA = (below + 7) >> 3;                        // 8-row tiles
+		const int Gf = TA >> 2;
+		const int n_items = 2 * Gf * (Gf + 1) + (TA & 3) * (Gf + 1);
+		const int fr = lane >> 2, fk = lane & 3;                // fragment row / k index (A, B); C: row fr, columns 2 fk, 2 fk + 1
+		auto decode = [&](int id, int & ta, int & c4) {
+			int g = 0;
+			while (2 * (g + 1) * (g + 2) <= id) g++;
+			const int rem = id - 2 * g * (g + 1);
+			ta = 4 * g + rem / (g + 1);
+			c4 = rem - (rem / (g + 1)) * (g + 1);
+		};
+		auto load_c = [&](int id, double (&c)[4][2]) {
+			int ta, c4;
+			decode(id, ta, c4);
+			const int ri = 8 * ta + fr;
+			const int jmax = min(ri, cbelow - 1);
+			const double * wsrc = rowsrc(r0 + min(ri, below - 1)) + r0;
+#pragma unroll
+			for (int nt = 0; nt < 4; nt++) {
+				const int j = 32 * c4 + 8 * nt + 2 * fk;
+				c[nt][0] = c[nt][1] = 0.0;
+				if (ri < below && j <= jmax) {
+					if (vec && j + 1 <= jmax) {
+						const double2 t2 = *reinterpret_cast<const double2 *>(wsrc + j);
+						c[nt][0] = t2.x; c[nt][1] = t2.y;
+					} else {
+						c[nt][0] = wsrc[j];
+						if (j + 1 <= jmax) c[nt][1] = wsrc[j + 1];
+					}
+				}
+			}
+		};
+		double ccur[4][2], cnxt[4][2];
+		int item = gwarp;
+		if (item < n_items) load_c(item, ccur);
+		if (vblk) {
+			const int pieces = below * 8;               // 32-byte pieces of the panel
+			for (int e0 = tid; e0 < pieces; e0 += kCholThreads * 8) {
+				double t8[8][4];
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int e = e0 + q * kCholThreads;
+					if (e < pieces) ld256(W + (long long) (r0 + (e >> 3)) * n + kb + 4 * (e & 7), t8[q]);
+				}
+#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					const int e = e0 + q * kCholThreads;
+					if (e < pieces)
+						*reinterpret_cast<double4 *>(Pn + (e >> 3) * kPnP + 4 * (e & 7)) = make_double4(t8[q][0], t8[q][1], t8[q][2], t8[q][3]);
+				}
+			}
+		} else {
+			for (int e = tid; e < below * kCholNB; e += kCholThreads) {
+				const int ri = e >> 5, c = e & 31;
+				Pn[ri * kPnP + c] = c < nbk ? W[(long long) (r0 + ri) * n + kb + c] : 0.0;
+			}
 		}
 		__syncthreads();
-		for (int ri = gwarp; ri < below; ri += gwarps) {
-			const int jmax = min(ri, cbelow - 1);   // columns 0..jmax (relative to r0)
-			double li[kCholNB];
+		for (; item < n_items; item += gwarps) {
+			const bool more = item + gwarps < n_items;
+			if (more) load_c(item + gwarps, cnxt);
+			int ta, c4;
+			decode(item, ta, c4);
+			const int ri = 8 * ta + fr;
+			const double * pa = Pn + ri * kPnP + fk;
+			const double * pb = Pn + (32 * c4 + fr) * kPnP + fk;
+			const int ntmax = min(3, (8 * ta + 7 - 32 * c4) >> 3);       // column tiles at or below the diagonal (warp-uniform)
 #pragma unroll
-			for (int t = 0; t < kCholNB; t++) li[t] = Pn[ri * P + t];
+			for (int t0 = 0; t0 < kCholNB; t0 += 4) {
+				const double av = -pa[t0];
+#pragma unroll
+				for (int nt = 0; nt < 4; nt++)
+					if (nt <= ntmax) dmma_8x8x4_acc(ccur[nt][0], ccur[nt][1], av, pb[nt * 8 * kPnP + t0]);
+			}
+			const int jmax = min(ri, cbelow - 1);
 			double * wrow = W + (long long) (r0 + ri) * n + r0;
-			for (int j = lane; j <= jmax; j += 32) {
-				const double w0 = wrow[j];
-				double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-				for (int t = 0; t < kCholNB; t += 4) {
-					s0 = fma(li[t], Pn[j * P + t], s0);
-					s1 = fma(li[t + 1], Pn[j * P + t + 1], s1);
-					s2 = fma(li[t + 2], Pn[j * P + t + 2], s2);
-					s3 = fma(li[t + 3], Pn[j * P + t + 3], s3);
+			for (int nt = 0; nt < 4; nt++) {
+				const int j = 32 * c4 + 8 * nt + 2 * fk;
+				if (ri < below && j <= jmax) {
+					if (vec && j + 1 <= jmax) *reinterpret_cast<double2 *>(wrow + j) = make_double2(ccur[nt][0], ccur[nt][1]);
+					else {
+						wrow[j] = ccur[nt][0];
+						if (j + 1 <= jmax) wrow[j + 1] = ccur[nt][1];
+					}
 				}
-				wrow[j] = w0 - ((s0 + s1) + (s2 + s3));
+			}
+			if (more) {
+#pragma unroll
+				for (int nt = 0; nt < 4; nt++) { ccur[nt][0] = cnxt[nt][0]; ccur[nt][1] = cnxt[nt][1]; }
 			}
 		}
+		SOLVE_STAMP();
 		cluster_sync_all();
+		SOLVE_STAMP();
 	}
 
-	// ---- back substitution L^T x = y (y = row n of W), CTA 0 ----
+	// ---- back substitution L^T x = y (y = row n of W), CTA 0.  L_kk = L' sqrt(D): L'^T x_k = (y_k - ...) / sqrt(d) ----
 	if (cta == 0) {
-		double * yv = Pn;                           // reuse: n doubles
-		for (int i = tid; i < n; i += kCholThreads) yv[i] = W[(long long) n * n + i];
+		// shared memory: Bb (32: broadcast slots) | yv (n) | nbuf x { Dd 32 x kBsP | Pd 32 x pitch }
+		const int last = ((n - 1) / kCholNB) * kCholNB;
+		const int pitch = last > 0 ? last : 2;
+		double * Bb = sm;
+		double * yv = sm + kCholNB;
+		const size_t buf_doubles = (size_t) kCholNB * kBsP + (size_t) kCholNB * pitch;
+		double * buf0 = yv + (((size_t) n + 1) & ~(size_t) 1);
+		const bool async_ok = (n & 1) == 0 && (((size_t) W) & 15) == 0;
 		__syncthreads();
-		for (int kb = ((n - 1) / kCholNB) * kCholNB; kb >= 0; kb -= kCholNB) {
+		for (int i = tid; i < n; i += kCholThreads) yv[i] = W[(long long) n * n + i];
+		backsub_stage(W, n, last, n - last, buf0, buf0 + kCholNB * kBsP, pitch, async_ok, tid);
+		int cur = 0;
+		for (int kb = last; kb >= 0; kb -= kCholNB) {
 			const int nbk = min(kCholNB, n - kb);
-			for (int e = tid; e < kCholNB * kCholNB; e += kCholThreads) {
-				const int r = e >> 5, c = e & 31;
-				Dk[r * P + c] = (r < nbk && c <= r) ? W[(long long) (kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
+			double * Dd = buf0 + (size_t) cur * buf_doubles;
+			double * Pd = Dd + kCholNB * kBsP;
+			cp_async_wait_all();
+			__syncthreads();
+			// next block row on its way while this one computes
+			if (nbuf == 2 && kb > 0) {
+				double * Dn = buf0 + (size_t) (cur ^ 1) * buf_doubles;
+				backsub_stage(W, n, kb - kCholNB, kCholNB, Dn, Dn + kCholNB * kBsP, pitch, async_ok, tid);
 			}
-			__syncthreads();
-			if (tid < kCholNB) Dinv[tid] = 1.0 / Dk[tid * P + tid];
-			__syncthreads();
 			if (warp == 0) {
-				// lane r holds y_r; solve the 32 x 32 upper-triangular system L_kk^T x = y from the last unknown up
-				double yr = lane < nbk ? yv[kb + lane] : 0.0;
+				// lane r holds z_r = y_r / sqrt(d_r); unit upper-triangular solve from the last unknown up; x_k travels through
+				// shared memory (see LdlColumn on shuffles under a divergent branch)
+				double z = lane < nbk ? yv[kb + lane] * Dd[lane * kBsP + lane] : 0.0;
+				double lk[kCholNB];
 #pragma unroll
-				for (int k = kCholNB - 1; k >= 0; k--) {
-					const double xk = __shfl_sync(0xffffffffu, yr, k) * Dinv[k];
-					yr = (lane == k) ? xk : ((lane < k) ? fma(-Dk[k * P + lane], xk, yr) : yr);
+				for (int k = 1; k < kCholNB; k++) lk[k] = (k < nbk && lane < k) ? Dd[k * kBsP + lane] : 0.0;
+#pragma unroll
+				for (int k = kCholNB - 1; k >= 1; k--) {
+					if (lane == k) Bb[k] = z;
+					__syncwarp();
+					z = fma(-lk[k], Bb[k], z);
 				}
-				if (lane < nbk) yv[kb + lane] = yr;
+				if (lane < nbk) yv[kb + lane] = z;
 			}
 			__syncthreads();
 			for (int i = tid; i < kb; i += kCholThreads) {
-				double s = yv[i];
-				for (int t = 0; t < nbk; t++) s = fma(-W[(long long) (kb + t) * n + i], yv[kb + t], s);
-				yv[i] = s;
+				double s0 = yv[i], s1 = 0, s2 = 0, s3 = 0;
+				if (nbk == kCholNB) {
+#pragma unroll
+					for (int t = 0; t < kCholNB; t += 4) {
+						s0 = fma(-Pd[(size_t) t * pitch + i], yv[kb + t], s0);
+						s1 = fma(-Pd[(size_t) (t + 1) * pitch + i], yv[kb + t + 1], s1);
+						s2 = fma(-Pd[(size_t) (t + 2) * pitch + i], yv[kb + t + 2], s2);
+						s3 = fma(-Pd[(size_t) (t + 3) * pitch + i], yv[kb + t + 3], s3);
+					}
+				} else {
+					for (int t = 0; t < nbk; t++) s0 = fma(-Pd[(size_t) t * pitch + i], yv[kb + t], s0);
+				}
+				yv[i] = (s0 + s1) + (s2 + s3);
 			}
 			__syncthreads();
+			if (nbuf == 2) cur ^= 1;
+			else if (kb > 0) backsub_stage(W, n, kb - kCholNB, kCholNB, Dd, Pd, pitch, async_ok, tid);
 		}
 		for (int i = tid; i < n; i += kCholThreads) x[i] = yv[i];
-		if (warp == 0) {
-			// every CTA saw the same pivots; report CTA 0's
-			int b = bad;
-			b = __shfl_sync(0xffffffffu, b, 0);
-			if (lane == 0) *info = b;
-		}
+#ifdef PNOL_SOLVE_STAMPS
+		__syncthreads();
+		SOLVE_STAMP();
+		if (tid == 0) for (int q = 0; q < nstamp && q < n; q++) x[q] = (double) (stamps[q] - stamps[0]);
+#endif
+		if (tid == 0) *info = bad;         // warp 0 of every CTA saw the same pivots
 	}
 }
 
@@ -261,13 +519,18 @@ int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n
 	PNOL_REQUIRE(ctx, n >= 1 && n <= kCholMaxN, "spd_solve: n = %d outside [1, %d]", n, kCholMaxN);
 	TimerScope ts(ctx, "spd_solve");
 	PNOL_CHECK(ws_reserve(ctx, 1, ((size_t) n + 1) * n * sizeof(double)));
-	const int prows = n + 1 > kCholNB ? n + 1 - kCholNB : 1;
-	size_t pn = (size_t) prows * (kCholNB + 1);
-	if (pn < (size_t) n) pn = n;                     // the panel buffer doubles as y in the back substitution
-	size_t smem = ((size_t) kCholNB * (kCholNB + 1) + kCholNB + pn) * sizeof(double);
+	const int prows = ((n + 1 > kCholNB ? n + 1 - kCholNB : 1) + 7) & ~7;                          // whole 8-row DMMA tiles
+	const size_t fact = (size_t) 2 * kCholNB * kCholNB + kCholNB + (size_t) (prows + 32) * kPnP;   // LpT | Rsd | Bc | Pn (B fragments read up to 31 rows past a tile row)
+	const int last = ((n - 1) / kCholNB) * kCholNB;
+	const size_t buf = (size_t) kCholNB * kBsP + (size_t) kCholNB * (last > 0 ? last : 2);         // one staged block row of L
+	const size_t yv = kCholNB + (((size_t) n + 1) & ~(size_t) 1);
+	int nbuf = 2;
+	size_t doubles = fact > yv + 2 * buf ? fact : yv + 2 * buf;
+	if (doubles * sizeof(double) > ctx->smem_optin) { nbuf = 1; doubles = fact > yv + buf ? fact : yv + buf; }
+	const size_t smem = doubles * sizeof(double);
 	PNOL_REQUIRE(ctx, smem <= ctx->smem_optin, "spd_solve: n = %d needs %zu bytes of shared memory", n, smem);
 	PNOL_CUDA(ctx, cudaFuncSetAttribute(spd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	PNOL_LAUNCH(ctx, spd_solve_kernel, kCholCluster, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev);
+	PNOL_LAUNCH(ctx, spd_solve_kernel, kCholCluster, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev, nbuf);
 	return PNOL_OK;
 }
 
@@ -399,17 +662,6 @@ matvec_kernel(const double * __restrict__ D, const double * __restrict__ g, int 
 	for (int k = lane; k < n; k += 32) s = fma(Dr[k], g[k], s);
 	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 	if (lane == 0) out[row] = scale * s;
-}
-
-// 256-bit global loads (one full 32-byte sector per lane and load). D is streamed (134 MB at n = 4096: larger than L2), so it
-// bypasses L1; the vectors (g, s, v: 32 KB each) are re-read by every warp and stay in L1.
-__device__ __forceinline__ void ldg256_stream(const double * p, double (&v)[4])
-{
-	asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void ldg256_cached(const double * p, double (&v)[4])
-{
-	asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
 // n a multiple of 4, D 32-byte aligned: one warp per row, every lane keeps kMvUnroll 256-bit loads of the row in flight (4 KB per
