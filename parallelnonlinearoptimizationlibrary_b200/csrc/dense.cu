@@ -131,20 +131,30 @@ __device__ __forceinline__ double rcp_nr(double d)
 constexpr int kLdlGroup = 8;
 
 template <int J> struct LdlColumn {
-	// on entry row J of bc holds column J (a'[r][J] of every lane r), published by the previous column / bulk pass / caller
+	// on entry row J of bc holds column J (a'[r][J] of every lane r), published by the previous column / bulk pass / caller.
+	// A column is published twice, at bc[J][r] and, shifted by one, at bs[J][r + 1]: the pivot a'[J][J] and a'[J + 1][J], which the
+	// next pivot waits for, then sit in one aligned 16-byte pair for even J in the first and for odd J in the second copy
+	// (one LDS.128 at the head of the chain instead of an LDS.64 behind the reciprocal).
+	__device__ __forceinline__ static void publish(double * bc, int lane, double v)
+	{
+		bc[J * kCholNB + lane] = v;
+		bc[kCholNB * kCholNB + J * (kCholNB + 2) + lane + 1] = v;
+		__syncwarp();
+	}
 	__device__ __forceinline__ static void run(double (&row)[kCholNB], int lane, int & bad_col, double & d_mine, double * bc)
 	{
 		constexpr int kEnd = (J / kLdlGroup + 1) * kLdlGroup;      // first column right of J's group
 		const double * col = bc + J * kCholNB;
-		const double d = col[J];                                   // the pivot
+		const double2 head = (J & 1) ? *reinterpret_cast<const double2 *>(bc + kCholNB * kCholNB + J * (kCholNB + 2) + J + 1)
+		                             : *reinterpret_cast<const double2 *>(col + J);
+		const double d = head.x;                                   // the pivot
 		if (!(d > 0.0 && d < 0x1p1000) && bad_col == 0) bad_col = J + 1;
 		if (lane == J) d_mine = d;
 		const double l = row[J] * rcp_nr(d);                       // L'[r][J] (meaningful for lane > J)
 		if (J + 1 < kEnd) {
 			constexpr int N = J + 1 < kCholNB ? J + 1 : J;
-			row[N] = fma(-l, col[N], row[N]);
-			bc[N * kCholNB + lane] = row[N];
-			__syncwarp();
+			row[N] = fma(-l, head.y, row[N]);
+			LdlColumn<N>::publish(bc, lane, row[N]);
 		}
 #pragma unroll
 		for (int c = J + 2; c < kEnd; c++) row[c] = fma(-l, col[c], row[c]);
@@ -155,10 +165,7 @@ template <int J> struct LdlColumn {
 			for (int c = kEnd; c < kCholNB; c++) {
 #pragma unroll
 				for (int t = kEnd - kLdlGroup; t < kEnd; t++) row[c] = fma(-row[t], bc[t * kCholNB + c], row[c]);
-				if (c == kEnd) {
-					bc[(kEnd < kCholNB ? kEnd : 0) * kCholNB + lane] = row[c];
-					__syncwarp();
-				}
+				if (c == kEnd) LdlColumn<(kEnd < kCholNB ? kEnd : 0)>::publish(bc, lane, row[c]);
 			}
 		}
 		LdlColumn<J + 1>::run(row, lane, bad_col, d_mine, bc);
@@ -228,8 +235,8 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 	constexpr int P = kCholNB + 1;
 	double * LpT = sm;                              // 32 x 32: LpT[t * 32 + c] = L'[c][t], c > t (unit lower factor of the diagonal block)
 	double * Rsd = sm + kCholNB * kCholNB;          // 32: 1 / sqrt(d)
-	double * Bc = Rsd + kCholNB;                    // 32 x 32: Bc[J * 32 + r] = a'[r][J], the columns of the diagonal factorisation
-	double * Pn = Bc + kCholNB * kCholNB;           // up to round8(n + 1 - 32) x kPnP: the panel below it (incl. the b row)
+	double * Bc = Rsd + kCholNB;                    // 32 x 32 + 32 x 34: the columns of the diagonal factorisation and their shifted copy (LdlColumn)
+	double * Pn = Bc + kCholNB * kCholNB + kCholNB * (kCholNB + 2);           // up to round8(n + 1 - 32) x kPnP: the panel below it (incl. the b row)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	// the grid is exactly one cluster: blockIdx.x IS the CTA's rank in it
 	const int cta = (int) blockIdx.x;
@@ -295,8 +302,7 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 			if (row[0] == 123.456) bad = 7;      // the loads have landed
 			SOLVE_STAMP();
 #endif
-			Bc[lane] = row[0];
-			__syncwarp();
+			LdlColumn<0>::publish(Bc, lane, row[0]);
 			LdlColumn<0>::run(row, lane, bc, dm, Bc);
 #ifdef PNOL_SOLVE_STAMPS
 			if (row[31] == 123.456) bad = 7;
@@ -446,10 +452,9 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 
 	// ---- back substitution L^T x = y (y = row n of W), CTA 0.  L_kk = L' sqrt(D): L'^T x_k = (y_k - ...) / sqrt(d) ----
 	if (cta == 0) {
-		// shared memory: Bb (32: broadcast slots) | yv (n) | nbuf x { Dd 32 x kBsP | Pd 32 x pitch }
+		// shared memory: (32 unused) | yv (n) | nbuf x { Dd 32 x kBsP | Pd 32 x pitch }
 		const int last = ((n - 1) / kCholNB) * kCholNB;
 		const int pitch = last > 0 ? last : 2;
-		double * Bb = sm;
 		double * yv = sm + kCholNB;
 		const size_t buf_doubles = (size_t) kCholNB * kBsP + (size_t) kCholNB * pitch;
 		double * buf0 = yv + (((size_t) n + 1) & ~(size_t) 1);
@@ -469,20 +474,18 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 				double * Dn = buf0 + (size_t) (cur ^ 1) * buf_doubles;
 				backsub_stage(W, n, kb - kCholNB, kCholNB, Dn, Dn + kCholNB * kBsP, pitch, async_ok, tid);
 			}
-			if (warp == 0) {
-				// lane r holds z_r = y_r / sqrt(d_r); unit upper-triangular solve from the last unknown up; x_k travels through
-				// shared memory (see LdlColumn on shuffles under a divergent branch)
+			{
+				// lane r holds z_r = y_r / sqrt(d_r); unit upper-triangular solve from the last unknown up. EVERY warp does it (the
+				// branch around this block is uniform for the compiler -- blockIdx -- so the shuffles are plain SHFL, 24 cycles per
+				// step; under `if (warp == 0)` each would be a WARPSYNC.COLLECTIVE bracket); warp 0 stores
 				double z = lane < nbk ? yv[kb + lane] * Dd[lane * kBsP + lane] : 0.0;
 				double lk[kCholNB];
 #pragma unroll
 				for (int k = 1; k < kCholNB; k++) lk[k] = (k < nbk && lane < k) ? Dd[k * kBsP + lane] : 0.0;
 #pragma unroll
-				for (int k = kCholNB - 1; k >= 1; k--) {
-					if (lane == k) Bb[k] = z;
-					__syncwarp();
-					z = fma(-lk[k], Bb[k], z);
-				}
-				if (lane < nbk) yv[kb + lane] = z;
+				for (int k = kCholNB - 1; k >= 1; k--) z = fma(-lk[k], __shfl_sync(0xffffffffu, z, k), z);
+				__syncthreads();           // every warp has read y_k
+				if (warp == 0 && lane < nbk) yv[kb + lane] = z;
 			}
 			__syncthreads();
 			for (int i = tid; i < kb; i += kCholThreads) {
@@ -520,7 +523,7 @@ int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n
 	TimerScope ts(ctx, "spd_solve");
 	PNOL_CHECK(ws_reserve(ctx, 1, ((size_t) n + 1) * n * sizeof(double)));
 	const int prows = ((n + 1 > kCholNB ? n + 1 - kCholNB : 1) + 7) & ~7;                          // whole 8-row DMMA tiles
-	const size_t fact = (size_t) 2 * kCholNB * kCholNB + kCholNB + (size_t) (prows + 32) * kPnP;   // LpT | Rsd | Bc | Pn (B fragments read up to 31 rows past a tile row)
+	const size_t fact = (size_t) 3 * kCholNB * kCholNB + 3 * kCholNB + (size_t) (prows + 32) * kPnP;   // LpT | Rsd | Bc | Pn (B fragments read up to 31 rows past a tile row)
 	const int last = ((n - 1) / kCholNB) * kCholNB;
 	const size_t buf = (size_t) kCholNB * kBsP + (size_t) kCholNB * (last > 0 ? last : 2);         // one staged block row of L
 	const size_t yv = kCholNB + (((size_t) n + 1) & ~(size_t) 1);
