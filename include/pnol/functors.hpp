@@ -24,13 +24,9 @@
 
 namespace pnol {
 
-/* parameters of a functor as the kernels see them (POD, passed by value as a kernel argument) */
-struct FunctorParams {
-	double scalars[PNOL_MAX_SCALARS];
-	long long ints[PNOL_MAX_INTS];
-	const double * col[PNOL_MAX_COLUMNS];   /* data columns (device pointers on the device side) */
-	long long m;
-};
+/* parameters of a functor as the kernels see them (POD, passed by value as a kernel argument): scalars[PNOL_MAX_SCALARS],
+ * ints[PNOL_MAX_INTS], col[PNOL_MAX_COLUMNS] (data columns; device pointers on the device side), m -- the C struct of pnol_b200.h */
+typedef pnol_functor_params FunctorParams;
 
 /* ---- accessors ---- */
 struct PtrAcc {                      /* plain array */

@@ -125,9 +125,62 @@ typedef struct {
 	long long m;                                 /* number of data rows held by THIS context (its shard) */
 } pnol_functor_desc;
 
+/* ---- open functor table: objectives that are not built in (Source/PNOL_Objective.hpp:29, :57 let a user plug in any objEval) ----
+ * A user objective brings its own instantiations of the library's kernel templates (include/pnol/device/functor_kernels.cuh, compiled
+ * out of tree by the user's nvcc) and registers their launchers under a kind of its choice:
+ *     kinds [PNOL_F_USER_SCALAR_BASE, +1000)   scalar objectives  (eval_batch, fd_points, fd_hessian, alpha_pool)
+ *     kinds [PNOL_F_USER_RESIDUAL_BASE, +1000) residual models    (residual, fd_jacobian)
+ * pnol_functor_create and every entry point that takes a functor then work for that kind as for the built-ins; libpnol_b200.so is not
+ * rebuilt. PNOL_REGISTER_SCALAR_FUNCTOR / PNOL_REGISTER_RESIDUAL_FUNCTOR in that header fill the table and call pnol_register_functor
+ * at load time. INTEGRATION.md section A shows the whole recipe; tests/test_gpu_user_functor.py does it end to end. */
+#define PNOL_F_USER_SCALAR_BASE 1000
+#define PNOL_F_USER_RESIDUAL_BASE 2000
+#define PNOL_FUNCTOR_ABI 1
+
+/* parameters of a functor as the kernels see them (POD, passed by value as a kernel argument; pnol::FunctorParams) */
+typedef struct pnol_functor_params {
+	double scalars[PNOL_MAX_SCALARS];
+	long long ints[PNOL_MAX_INTS];
+	const double * col[PNOL_MAX_COLUMNS];        /* data columns (device pointers) */
+	long long m;
+} pnol_functor_params;
+
+/* what a launcher needs from the calling context */
+typedef struct pnol_launch_env {
+	void * stream;                               /* cudaStream_t of the context: launch here */
+	int sm_count;
+	size_t smem_optin;                           /* opt-in shared memory per block */
+	unsigned long long * launches;               /* ++ per kernel launch (pnol_ctx_launches) */
+	char * err;                                  /* error text buffer (pnol_last_error) */
+	size_t err_len;
+} pnol_launch_env;
+
+/* launch table of one functor kind; every pointer argument is a DEVICE pointer, every call only enqueues on env->stream */
+typedef struct pnol_functor_vtable {
+	int abi_version;                             /* PNOL_FUNCTOR_ABI */
+	int n_columns;                               /* data columns the functor expects in pnol_functor_desc */
+	int (*eval_batch)(const pnol_launch_env *, const pnol_functor_params *, const double * pts, long long B, int n, long long ld,
+	                  const unsigned char * indicator, double * f_out);
+	int (*fd_points)(const pnol_launch_env *, const pnol_functor_params *, const double * xfull, int nfull, const int * pos,
+	                 const double * dx, int i0, int i1, double * fdx_out, double * f0_out);
+	int (*fd_hessian)(const pnol_launch_env *, const pnol_functor_params *, const double * x, const double * dx, int n,
+	                  const double * fdx, const double * f0, double * B);
+	int (*alpha_pool)(const pnol_launch_env *, const pnol_functor_params *, const double * xfull, const double * pfull,
+	                  const unsigned char * is_const, int nfull, const double * alpha, int npool, double dalpha,
+	                  const unsigned char * eval_ind, int want_shifted, double * vals /* 2 * npool */);
+	int (*residual)(const pnol_launch_env *, const pnol_functor_params *, const double * x, int n, double * F);
+	int (*fd_jacobian)(const pnol_launch_env *, const pnol_functor_params *, const double * x, const double * dx, int n, double * J,
+	                   double * F /* may be NULL */);
+} pnol_functor_vtable;
+
+/* registers (or replaces) the launch table of a user kind; the table must outlive its use. Thread-safe; callable before any context
+ * exists (static initialisers). Returns PNOL_OK, or PNOL_ERR_INVALID for a kind outside the user ranges, a missing launcher or another ABI. */
+int pnol_register_functor(int kind, const pnol_functor_vtable * vt);
+int pnol_functor_registered(int kind);                     /* 1 for built-in and registered kinds */
+
 int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * desc, pnol_functor ** out);
 void pnol_functor_destroy(pnol_functor * f);
-int pnol_functor_is_residual(const pnol_functor * f);     /* 1 for kinds >= 100 */
+int pnol_functor_is_residual(const pnol_functor * f);     /* 1 for the built-in kinds >= 100 and the user residual range */
 long long pnol_functor_rows(const pnol_functor * f);      /* m of a residual functor, 0 otherwise */
 
 /* ---------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@ LIB_PATH = os.environ.get("PNOL_B200_LIB") or os.path.join(_HERE, "lib", "libpno
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libpnol_b200_host.so")
 
 PNOL_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NO_FUNCTOR = 1, 2, 3
+F_USER_SCALAR_BASE, F_USER_RESIDUAL_BASE = 1000, 2000      # open functor table (pnol_register_functor)
 ERR_NAMES = {1: "INVALID", 2: "CUDA", 3: "NO_FUNCTOR", 4: "NONFINITE", 5: "NOT_SPD", 6: "COMM", 7: "STREAM"}
 
 # functor kinds (include/pnol_b200.h)
@@ -81,7 +83,7 @@ EXPORTS = [
     "pnol_ctx_create", "pnol_ctx_destroy", "pnol_last_error", "pnol_ctx_device", "pnol_ctx_stream", "pnol_ctx_sync",
     "pnol_ctx_sm_count", "pnol_ctx_launches", "pnol_version", "pnol_malloc", "pnol_free", "pnol_memcpy", "pnol_memset",
     "pnol_host_alloc", "pnol_host_free", "pnol_comm_unique_id", "pnol_comm_init", "pnol_comm_rank", "pnol_comm_size",
-    "pnol_comm_set_local", "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_functor_create",
+    "pnol_comm_set_local", "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_register_functor", "pnol_functor_registered", "pnol_functor_create",
     "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
     "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
     "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve", "pnol_lu_inverse",

@@ -1,6 +1,8 @@
 // capi.cu -- extern "C" glue of include/pnol_b200.h: context, memory, functors, and the evaluation / LM / BFGS
 // entry points (the GA entry points live in ga.cu, the communicator in comm.cu).
 #include "common.cuh"
+
+#include <mutex>
 #include <vector>
 #include <thread>
 #include "exact_div.cuh"
@@ -102,7 +104,12 @@ extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 	delete ctx;
 }
 
-extern "C" const char * pnol_last_error(pnol_ctx * ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" const char * pnol_last_error(pnol_ctx * ctx)
+{
+	if (!ctx) return "null context";
+	if (ctx->errbuf[0]) { ctx->err = ctx->errbuf; ctx->errbuf[0] = 0; }      // text of a launcher from include/pnol/device (newer than err)
+	return ctx->err.c_str();
+}
 extern "C" int pnol_ctx_device(pnol_ctx * ctx) { return ctx ? ctx->device : -1; }
 extern "C" void * pnol_ctx_stream(pnol_ctx * ctx) { return ctx ? (void *) ctx->stream : nullptr; }
 extern "C" int pnol_ctx_sm_count(pnol_ctx * ctx) { return ctx ? ctx->sm_count : 0; }
@@ -270,6 +277,49 @@ extern "C" int pnol_timer_reset(pnol_ctx * ctx)
 // ---------------------------------------------------------------------------------------------------
 // functors
 // ---------------------------------------------------------------------------------------------------
+// ---- open functor table (include/pnol_b200.h: pnol_register_functor) ----
+namespace {
+struct FunctorRegistry {
+	std::mutex mu;
+	std::map<int, const pnol_functor_vtable *> table;
+};
+FunctorRegistry & registry()
+{
+	static FunctorRegistry * r = new FunctorRegistry();      // never destroyed: registrations come from static initialisers of other modules
+	return *r;
+}
+} // namespace
+
+const pnol_functor_vtable * pnol::user_vtable(int kind)
+{
+	if (!is_user_kind(kind)) return nullptr;
+	FunctorRegistry & r = registry();
+	std::lock_guard<std::mutex> lock(r.mu);
+	auto it = r.table.find(kind);
+	return it == r.table.end() ? nullptr : it->second;
+}
+
+extern "C" int pnol_register_functor(int kind, const pnol_functor_vtable * vt)
+{
+	if (!vt || vt->abi_version != PNOL_FUNCTOR_ABI || !pnol::is_user_kind(kind)) return PNOL_ERR_INVALID;
+	if (vt->n_columns < 0 || vt->n_columns > PNOL_MAX_COLUMNS) return PNOL_ERR_INVALID;
+	const bool residual = pnol::is_residual_kind(kind);
+	if (residual ? !(vt->residual && vt->fd_jacobian) : !(vt->eval_batch && vt->fd_points && vt->fd_hessian && vt->alpha_pool)) return PNOL_ERR_INVALID;
+	FunctorRegistry & r = registry();
+	std::lock_guard<std::mutex> lock(r.mu);
+	r.table[kind] = vt;
+	return PNOL_OK;
+}
+
+extern "C" int pnol_functor_registered(int kind)
+{
+	switch (kind) {
+		case PNOL_F_ROSENBROCK: case PNOL_F_POWER: case PNOL_F_BOOTH: case PNOL_F_GOLDSTEIN: case PNOL_F_RASTRIGIN: case PNOL_F_EXPCURVE_SINGLE:
+		case PNOL_F_EXPCURVE: case PNOL_F_CUBIC: case PNOL_F_LORENTZ_SUM: return 1;
+		default: return pnol::user_vtable(kind) != nullptr;
+	}
+}
+
 extern "C" int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * desc, pnol_functor ** out)
 {
 	if (!ctx || !desc || !out) return PNOL_ERR_INVALID;
@@ -280,7 +330,14 @@ extern "C" int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * des
 		case PNOL_F_ROSENBROCK: case PNOL_F_POWER: case PNOL_F_BOOTH: case PNOL_F_GOLDSTEIN: case PNOL_F_RASTRIGIN: need_cols = 0; break;
 		case PNOL_F_EXPCURVE_SINGLE: case PNOL_F_EXPCURVE: case PNOL_F_LORENTZ_SUM: need_cols = 2; break;
 		case PNOL_F_CUBIC: need_cols = 3; break;
-		default: PNOL_SET_ERR(ctx, "unknown functor kind %d", desc->kind); return PNOL_ERR_NO_FUNCTOR;
+		default: {
+			const pnol_functor_vtable * vt = user_vtable(desc->kind);
+			if (!vt) {
+				PNOL_SET_ERR(ctx, "unknown functor kind %d (user kinds must be registered first: pnol_register_functor)", desc->kind);
+				return PNOL_ERR_NO_FUNCTOR;
+			}
+			need_cols = vt->n_columns;
+		}
 	}
 	PNOL_REQUIRE(ctx, desc->n_columns == need_cols, "functor kind %d needs %d data columns, got %d", desc->kind, need_cols, desc->n_columns);
 	PNOL_REQUIRE(ctx, need_cols == 0 || desc->m >= 0, "functor: bad row count");
@@ -318,8 +375,8 @@ extern "C" void pnol_functor_destroy(pnol_functor * f)
 	delete f;
 }
 
-extern "C" int pnol_functor_is_residual(const pnol_functor * f) { return f && f->kind >= 100; }
-extern "C" long long pnol_functor_rows(const pnol_functor * f) { return f && f->kind >= 100 ? f->params.m : 0; }
+extern "C" int pnol_functor_is_residual(const pnol_functor * f) { return f && is_residual_kind(f->kind); }
+extern "C" long long pnol_functor_rows(const pnol_functor * f) { return f && is_residual_kind(f->kind) ? f->params.m : 0; }
 
 // ---------------------------------------------------------------------------------------------------
 // scalar-objective entry points
@@ -658,7 +715,7 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	if (!ctx || !f) return PNOL_ERR_INVALID;
 	PNOL_REQUIRE(ctx, x && dx && F && Ftrial && JTJ && n >= 1, "lm_step: bad arguments");
 	PNOL_REQUIRE(ctx, (!J || is_device_ptr(J)) && is_device_ptr(F) && is_device_ptr(Ftrial) && is_device_ptr(JTJ), "lm_step: J, F, Ftrial and JTJ must be device memory");
-	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_step: the functor is not a residual model");
+	PNOL_REQUIRE(ctx, is_residual_kind(f->kind), "lm_step: the functor is not a residual model");
 	DevIn<double> dx_, ddx;
 	PNOL_CHECK(dx_.init(ctx, x, n));
 	PNOL_CHECK(ddx.init(ctx, dx, n));
@@ -740,7 +797,7 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 	PNOL_REQUIRE(ctx, !is_device_ptr(x), "lm_iterate: x is the host's in/out parameter vector");
 	PNOL_REQUIRE(ctx, F && Ftrial && JTJ && (!J || is_device_ptr(J)) && is_device_ptr(F) && is_device_ptr(Ftrial) && is_device_ptr(JTJ),
 	             "lm_iterate: J, F, Ftrial and JTJ must be device memory");
-	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_iterate: the functor is not a residual model");
+	PNOL_REQUIRE(ctx, is_residual_kind(f->kind), "lm_iterate: the functor is not a residual model");
 	PNOL_REQUIRE(ctx, ((((size_t) F) | ((size_t) Ftrial)) & 15) == 0, "lm_iterate: F and Ftrial must be 16-byte aligned");
 	const long long m = f->params.m;
 	DevIn<double> ddx;
@@ -869,7 +926,7 @@ extern "C" int pnol_lm_normal_eq_fused(pnol_ctx * ctx, const pnol_functor * f, c
 {
 	if (!ctx || !f) return PNOL_ERR_INVALID;
 	PNOL_REQUIRE(ctx, x && dx && n >= 1, "lm_normal_eq_fused: bad arguments");
-	PNOL_REQUIRE(ctx, f->kind >= 100, "lm_normal_eq_fused: the functor is not a residual model");
+	PNOL_REQUIRE(ctx, is_residual_kind(f->kind), "lm_normal_eq_fused: the functor is not a residual model");
 	const long long m = f->params.m;
 	DevIn<double> dx_, ddx; DevOut<double> oJTJ, oA, orhs, oF;
 	PNOL_CHECK(dx_.init(ctx, x, n));

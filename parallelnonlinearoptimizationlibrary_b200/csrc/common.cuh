@@ -26,6 +26,7 @@ struct pnol_ctx {
 	int sm_count = 0;
 	size_t smem_optin = 0;
 	std::string err;
+	char errbuf[512] = {0};        // text written by the header launchers (pnol_launch_env::err); pnol_last_error reads it when err is empty
 	uint64_t launches = 0;
 
 	// grow-only scratch buffers (device)
@@ -74,7 +75,7 @@ struct pnol_functor {
 	do {                                                          \
 		char _buf[512];                                           \
 		snprintf(_buf, sizeof _buf, __VA_ARGS__);                 \
-		if (ctx) (ctx)->err = _buf;                               \
+		if (ctx) { (ctx)->err = _buf; (ctx)->errbuf[0] = 0; }     \
 	} while (0)
 
 #define PNOL_CUDA(ctx, call)                                                                       \
@@ -207,6 +208,22 @@ class TimerScope {
 	const char * name_ = nullptr;
 	cudaEvent_t a_ = nullptr, b_ = nullptr;
 };
+
+// ---- open functor table (pnol_register_functor): launch table of a user kind, nullptr for the built-ins / unknown kinds ----
+const pnol_functor_vtable * user_vtable(int kind);
+inline bool is_user_kind(int kind) { return kind >= PNOL_F_USER_SCALAR_BASE && kind < PNOL_F_USER_RESIDUAL_BASE + 1000; }
+inline bool is_residual_kind(int kind) { return (kind >= 100 && kind < PNOL_F_USER_SCALAR_BASE) || (kind >= PNOL_F_USER_RESIDUAL_BASE && kind < PNOL_F_USER_RESIDUAL_BASE + 1000); }
+inline pnol_launch_env make_env(pnol_ctx * ctx)
+{
+	pnol_launch_env env;
+	env.stream = (void *) ctx->stream;
+	env.sm_count = ctx->sm_count;
+	env.smem_optin = ctx->smem_optin;
+	env.launches = (unsigned long long *) &ctx->launches;
+	env.err = ctx->errbuf;
+	env.err_len = sizeof ctx->errbuf;
+	return env;
+}
 
 // ---- functor dispatch: calls fn(Functor{}) for the functor's kind ----
 template <class Fn> int dispatch_scalar(pnol_ctx * ctx, int kind, Fn && fn)
