@@ -54,7 +54,7 @@ struct GaDevStatus {
 	int pad1;
 	unsigned int nsuspect;              // rows whose hash matched a later row that is NOT equal (exhaustive check)
 	int sort_result_in_alt;             // which buffer the radix sort ended in
-	int pad;
+	int sort_fallback;                  // bucket sort: a bucket outgrew one CTA, the radix kernel sorts instead
 };
 
 // index of the selection trial at stream position q (Source/GeneticAlgorithmMPI.cpp:134-144): round(u(q) Npop); 0 = rejected.
@@ -99,7 +99,7 @@ ga_prep_kernel(const double * __restrict__ Fs, int Npop, int Nelite, double * __
 		S->ndup = 0; S->noob = 0; S->pos_end = 0; S->fbest = 0; S->max_fitness = maxFitness;
 		// every trial would compare against NaN / inf: the reference spins forever in its while loops
 		S->error = (!(maxFitness > 0) || isinf(maxFitness)) ? kGaErrDegenerate : 0;
-		S->nsuspect = 0; S->sort_result_in_alt = 0;
+		S->nsuspect = 0; S->sort_result_in_alt = 0; S->sort_fallback = 1;      // cleared by the bucket sort when it takes the sort
 	}
 }
 
@@ -773,6 +773,7 @@ ga_sort_kernel(const double * __restrict__ F, long long N, long long range, unsi
                unsigned * __restrict__ perm_out)
 {
 	cg::grid_group grid = cg::this_grid();
+	if (!S->sort_fallback) return;                                   // the bucket sort has produced Fsorted / perm_out (uniform over the grid)
 	__shared__ unsigned wcount[kSortThreads / 32][256];              // 32 KB
 	__shared__ unsigned long long dbase[256];
 	__shared__ unsigned long long dtot[256];
@@ -908,6 +909,214 @@ ga_sort_kernel(const double * __restrict__ F, long long N, long long range, unsi
 	if (cta == 0 && tid == 0) S->sort_result_in_alt = (kin != keys0);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 6'. popSort at large Npop: splitter buckets + one shared-memory sort per bucket, four short launches instead of the seven
+// passes (fourteen grid barriers) of the radix kernel above (0.27 ms at 1M keys). The PREVIOUS generation's sorted objective values
+// are the splitters (every Npop / 4096-th one): the distribution moves slowly from one generation to the next, so the buckets come
+// out balanced (about 250 keys each; a CTA of four warps sorts up to kBsCap = 1024, a second launch the few buckets up to 8192). Keys are (key(F), row), unique, so the order inside a bucket
+// before its sort does not matter and the result is the stable sort of the radix kernel, bit for bit. A bucket that outgrows
+// kBsCapLarge (a population collapsing onto few values, a distribution that jumped) sets GaDevStatus::sort_fallback and the radix
+// kernel, which is always enqueued behind and otherwise returns at once, redoes the sort.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBsBuckets = 4096;
+constexpr int kBsLog2 = 12;
+constexpr int kBsCap = 1024;       // keys of a bucket the small-bucket instantiation sorts
+constexpr int kBsCapLarge = 8192;  // ... and the large-bucket one
+constexpr int kBsCountThreads = 1024;
+
+// bucket of a key = number of splitters <= key; tag[i] = bucket | rank inside (CTA, bucket) << kBsLog2; totals[bucket] += CTA counts
+__global__ void __launch_bounds__(kBsCountThreads)
+ga_bsort_count_kernel(const double * __restrict__ F, long long N, const double * __restrict__ Fs_old, unsigned * __restrict__ tag,
+                      unsigned * __restrict__ totals)
+{
+	extern __shared__ unsigned long long bs_smem[];
+	unsigned long long * spl = bs_smem;                            // spl[b], b >= 1: lower end of bucket b
+	unsigned * hist = reinterpret_cast<unsigned *>(bs_smem + kBsBuckets);
+	for (int b = threadIdx.x; b < kBsBuckets; b += kBsCountThreads) {
+		spl[b] = b ? double_to_key(Fs_old[(long long) b * N / kBsBuckets]) : 0ULL;
+		hist[b] = 0;
+	}
+	__syncthreads();
+	const long long per = (N + gridDim.x - 1) / gridDim.x;
+	const long long lo = min(N, (long long) blockIdx.x * per), hi = min(N, lo + per);
+	const int lane = threadIdx.x & 31;
+	for (long long i = lo + threadIdx.x; i < hi; i += kBsCountThreads) {
+		const unsigned long long k = double_to_key(F[i]);
+		int b = 0;                                                 // largest b with spl[b] <= k (spl[0] = 0)
+#pragma unroll
+		for (int step = kBsBuckets / 2; step > 0; step >>= 1)
+			if (spl[b + step] <= k) b += step;
+		// one atomic per distinct bucket of the warp: the elite rows arrive sorted, 32 neighbours share a bucket, and 6000 atomics of
+		// one CTA on a few dozen addresses were the longest part of this kernel
+		const unsigned act = __activemask();
+		const unsigned m = __match_any_sync(act, b);
+		const int leader = __ffs(m) - 1;
+		unsigned base = 0;
+		if (lane == leader) base = atomicAdd(&hist[b], (unsigned) __popc(m));
+		base = __shfl_sync(act, base, leader);
+		tag[i] = (unsigned) b | ((base + (unsigned) __popc(m & ((1u << lane) - 1))) << kBsLog2);
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < kBsBuckets; b += kBsCountThreads)
+		if (hist[b]) atomicAdd(&totals[b], hist[b]);
+}
+
+// bucket starts (exclusive scan of the totals), scatter cursors = starts, totals cleared for the next sort
+__global__ void __launch_bounds__(1024)
+ga_bsort_scan_kernel(unsigned * __restrict__ totals, unsigned * __restrict__ bstart /* kBsBuckets + 1 */, unsigned * __restrict__ cursor,
+                     GaDevStatus * __restrict__ S)
+{
+	__shared__ unsigned wsum[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned c[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++) c[q] = totals[4 * tid + q];
+	const unsigned mine = c[0] + c[1] + c[2] + c[3];
+	unsigned incl = mine;
+	for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+	if (lane == 31) wsum[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		unsigned w = wsum[lane], wi = w;
+		for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+		wsum[lane] = wi - w;
+	}
+	__syncthreads();
+	unsigned run = wsum[warp] + incl - mine;
+#pragma unroll
+	for (int q = 0; q < 4; q++) { bstart[4 * tid + q] = run; cursor[4 * tid + q] = run; run += c[q]; totals[4 * tid + q] = 0; }
+	if (tid == 1023) bstart[kBsBuckets] = run;
+	const int overflow = __syncthreads_or(c[0] > (unsigned) kBsCapLarge || c[1] > (unsigned) kBsCapLarge || c[2] > (unsigned) kBsCapLarge || c[3] > (unsigned) kBsCapLarge);
+	if (tid == 0) S->sort_fallback = overflow;
+}
+static_assert(kBsBuckets == 4096 && (1 << kBsLog2) == kBsBuckets, "ga_bsort_scan_kernel scans four buckets per thread of one 1024-thread CTA");
+
+// (key, row) of every entry to its bucket's region; a CTA reserves its share of a bucket with one atomic on the bucket's cursor
+__global__ void __launch_bounds__(kBsCountThreads)
+ga_bsort_scatter_kernel(const double * __restrict__ F, long long N, const unsigned * __restrict__ tag, unsigned * __restrict__ cursor,
+                        unsigned long long * __restrict__ keys, unsigned * __restrict__ vals)
+{
+	__shared__ unsigned base[kBsBuckets];
+	for (int b = threadIdx.x; b < kBsBuckets; b += kBsCountThreads) base[b] = 0;
+	__syncthreads();
+	const long long per = (N + gridDim.x - 1) / gridDim.x;          // the same ranges as ga_bsort_count_kernel (same grid)
+	const long long lo = min(N, (long long) blockIdx.x * per), hi = min(N, lo + per);
+	for (long long i = lo + threadIdx.x; i < hi; i += kBsCountThreads) atomicAdd(&base[tag[i] & (kBsBuckets - 1)], 1u);
+	__syncthreads();
+	for (int b = threadIdx.x; b < kBsBuckets; b += kBsCountThreads) {
+		const unsigned c = base[b];
+		base[b] = c ? atomicAdd(&cursor[b], c) : 0u;
+	}
+	__syncthreads();
+	for (long long i = lo + threadIdx.x; i < hi; i += kBsCountThreads) {
+		const unsigned t = tag[i];
+		const unsigned p = base[t & (kBsBuckets - 1)] + (t >> kBsLog2);
+		keys[p] = double_to_key(F[i]);
+		vals[p] = (unsigned) i;
+	}
+}
+
+// one CTA per bucket. The keys of a bucket lie between two neighbouring splitters, spread about evenly: a second, interpolating
+// bucket pass inside the CTA (sub-bucket = floor((key - min) * nsub / (max - min + 1)), monotone in the key, about one key per
+// sub-bucket) leaves almost nothing to compare -- every key counts the smaller (key, row) pairs of its own sub-bucket and that is
+// its place. (A bitonic network over the bucket in shared memory: 2700 instructions per key, 78 us for the 4096 buckets.)
+// Two instantiations: <128, 8> takes the buckets of up to 1024 keys (nearly all of them: 16 KB of shared memory, 13 CTAs per SM), <512, 16>
+// the ones between 1025 and kBsCapLarge = 8192 keys (the first generations after a start, when the distribution still moves: the
+// good children of a generation pile up below the old 10 % mark). Every CTA looks at its bucket's size and leaves if it is not its.
+template <int kThreads, int kPer>
+__global__ void __launch_bounds__(kThreads)
+ga_bsort_bucket_kernel(const unsigned long long * __restrict__ keys, const unsigned * __restrict__ vals, const unsigned * __restrict__ bstart,
+                       const GaDevStatus * __restrict__ S, double * __restrict__ Fsorted, unsigned * __restrict__ perm_out, unsigned min_cnt)
+{
+	constexpr int kCap = kThreads * kPer;
+	extern __shared__ unsigned long long bs_smem[];
+	unsigned long long * sk = bs_smem;                                   // kCap
+	unsigned * sv = reinterpret_cast<unsigned *>(bs_smem + kCap);      // kCap
+	unsigned * sstart = sv + kCap;                                       // kCap + 1: sub-bucket counts, then starts
+	__shared__ unsigned long long red[2][kThreads / 32];
+	__shared__ unsigned wtot[kThreads / 32];
+	if (S->sort_fallback) return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned b0 = bstart[blockIdx.x], cnt = bstart[blockIdx.x + 1] - b0;
+	if (cnt <= min_cnt || cnt > (unsigned) kCap) return;
+	unsigned nsub = 32;
+	while (nsub < cnt) nsub <<= 1;                      // <= kCap
+	unsigned long long k[kPer];
+	unsigned v[kPer], sub[kPer], slot[kPer];
+	unsigned long long kmin = ~0ULL, kmax = 0ULL;
+#pragma unroll
+	for (int q = 0; q < kPer; q++) {
+		const unsigned e = tid + q * kThreads;
+		k[q] = e < cnt ? keys[b0 + e] : 0ULL;
+		v[q] = e < cnt ? vals[b0 + e] : 0u;
+		if (e < cnt) { kmin = min(kmin, k[q]); kmax = max(kmax, k[q]); }
+	}
+	for (unsigned e = tid; e <= nsub; e += kThreads) sstart[e] = 0;
+	for (int o = 16; o > 0; o >>= 1) { kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
+	if (lane == 0) { red[0][warp] = kmin; red[1][warp] = kmax; }
+	__syncthreads();
+#pragma unroll
+	for (int w = 0; w < kThreads / 32; w++) { kmin = min(kmin, red[0][w]); kmax = max(kmax, red[1][w]); }
+	const double scale = (double) nsub / ((double) (kmax - kmin) + 1.0);
+#pragma unroll
+	for (int q = 0; q < kPer; q++) {
+		const unsigned e = tid + q * kThreads;
+		if (e < cnt) {
+			const unsigned sb = (unsigned) min((double) (nsub - 1), (double) (k[q] - kmin) * scale);      // monotone in the key
+			sub[q] = sb;
+			slot[q] = atomicAdd(&sstart[sb], 1u);
+		}
+	}
+	__syncthreads();
+	// exclusive scan of the nsub counts: thread t owns entries [t per, (t + 1) per)
+	{
+		const unsigned per = nsub / kThreads > 0 ? nsub / kThreads : 1;      // nsub >= 32; with fewer entries than threads the tail threads idle
+		unsigned c[kPer], mine = 0;
+#pragma unroll
+		for (int q = 0; q < kPer; q++) {
+			const unsigned e = tid * per + q;
+			c[q] = (q < (int) per && e < nsub) ? sstart[e] : 0u;
+			mine += c[q];
+		}
+		unsigned incl = mine;
+		for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+		if (lane == 31) wtot[warp] = incl;
+		__syncthreads();
+		unsigned run = incl - mine;
+#pragma unroll
+		for (int w = 0; w < kThreads / 32; w++) run += w < warp ? wtot[w] : 0u;
+#pragma unroll
+		for (int q = 0; q < kPer; q++) {
+			const unsigned e = tid * per + q;
+			if (q < (int) per && e < nsub) { sstart[e] = run; run += c[q]; }
+		}
+		if (tid == 0) sstart[nsub] = cnt;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < kPer; q++) {
+		const unsigned e = tid + q * kThreads;
+		if (e < cnt) { const unsigned p = sstart[sub[q]] + slot[q]; sk[p] = k[q]; sv[p] = v[q]; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < kPer; q++) {
+		const unsigned e = tid + q * kThreads;
+		if (e < cnt) {
+			const unsigned s0 = sstart[sub[q]], s1 = sstart[sub[q] + 1];
+			unsigned smaller = 0;
+			for (unsigned j = s0; j < s1; j++) {
+				const unsigned long long kj = sk[j];
+				smaller += (kj < k[q] || (kj == k[q] && sv[j] < v[q])) ? 1u : 0u;
+			}
+			Fsorted[b0 + s0 + smaller] = key_to_double(k[q]);
+			perm_out[b0 + s0 + smaller] = v[q];
+		}
+	}
+}
+constexpr size_t bsort_bucket_smem(int cap) { return (size_t) cap * 12 + ((size_t) cap + 1) * 4 + 8; }
+
+
 // end of the generation: stream position, best objective. The kernels above read the stream speculatively (trial windows), so
 // exhaustion of an explicit stream is decided here: the sequential algorithm consumed exactly the draws [0, pos_end)
 __global__ void ga_finish_kernel(GaDevStatus * __restrict__ S, const double * __restrict__ Fsorted, long long NeliteMutGenes, int n,
@@ -977,6 +1186,7 @@ struct GaPipe {
 	// sort
 	unsigned long long * skeys[2] = {nullptr, nullptr}; unsigned * svals[2] = {nullptr, nullptr}; unsigned * scounts = nullptr;
 	int sort_grid = 0; long long sort_range = 0;
+	unsigned * bs_tag = nullptr, * bs_totals = nullptr, * bs_start = nullptr, * bs_cursor = nullptr; bool bs_on = false; int bs_grid = 0;
 	// status
 	GaDevStatus * status = nullptr; GaDevStatus * status_host = nullptr;
 	unsigned long long pos_elite_last = 0;           // start of the last generation's elite-mutation stage (for get_indices)
@@ -1141,6 +1351,20 @@ int ga_pipe_create(pnol_ga * ga)
 		P->sort_range = range;
 		P->sort_grid = (int) ((Npop + range - 1) / range);
 		PNOL_CHECK(pipe_alloc(ga, &P->scounts, (size_t) 256 * P->sort_grid));
+		// bucket sort in front of it at large Npop (PNOL_GA_SORT=radix: radix kernel only -- A/B runs and the equivalence test)
+		const char * sort_env = getenv("PNOL_GA_SORT");              // read per pnol_ga_create
+		const bool radix_only = sort_env && strcmp(sort_env, "radix") == 0;
+		P->bs_on = !radix_only && Npop >= 65536;
+		if (P->bs_on) {
+			P->bs_grid = 2 * ctx->sm_count;                          // two 1024-thread CTAs per SM (count: 48 KB, scatter: 16 KB of shared memory)
+			PNOL_CHECK(pipe_alloc(ga, &P->bs_tag, (size_t) Npop));
+			PNOL_CHECK(pipe_alloc(ga, &P->bs_totals, (size_t) kBsBuckets));
+			PNOL_CHECK(pipe_alloc(ga, &P->bs_start, (size_t) kBsBuckets + 1));
+			PNOL_CHECK(pipe_alloc(ga, &P->bs_cursor, (size_t) kBsBuckets));
+			PNOL_CUDA(ctx, cudaMemsetAsync(P->bs_totals, 0, kBsBuckets * sizeof(unsigned), ctx->stream));
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_bsort_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBsBuckets * 12));
+			PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_bsort_bucket_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bsort_bucket_smem(kBsCapLarge)));
+		}
 	}
 	if (ctx->nranks > 1) PNOL_CHECK(pipe_alloc(ga, &P->f_recv, std::max((size_t) P->per * R, (size_t) P->eper * ctx->nranks)));
 	if (R > 1) {
@@ -1386,6 +1610,15 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		unsigned long long * k0 = P->skeys[0], * k1 = P->skeys[1];
 		unsigned * v0 = P->svals[0], * v1 = P->svals[1], * sc = P->scounts, * po = P->perm[nxt];
 		double * Fo = P->Fs[nxt];
+		if (P->bs_on) {
+			PNOL_LAUNCH(ctx, ga_bsort_count_kernel, P->bs_grid, kBsCountThreads, kBsBuckets * 12, Fc, N, (const double *) P->Fs[cur], P->bs_tag, P->bs_totals);
+			PNOL_LAUNCH(ctx, ga_bsort_scan_kernel, 1, 1024, 0, P->bs_totals, P->bs_start, P->bs_cursor, S);
+			PNOL_LAUNCH(ctx, ga_bsort_scatter_kernel, P->bs_grid, kBsCountThreads, 0, Fc, N, (const unsigned *) P->bs_tag, P->bs_cursor, k0, v0);
+			PNOL_LAUNCH(ctx, (ga_bsort_bucket_kernel<128, 8>), kBsBuckets, 128, bsort_bucket_smem(kBsCap), (const unsigned long long *) k0, (const unsigned *) v0,
+			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, 0u);
+			PNOL_LAUNCH(ctx, (ga_bsort_bucket_kernel<512, 16>), kBsBuckets, 512, bsort_bucket_smem(kBsCapLarge), (const unsigned long long *) k0, (const unsigned *) v0,
+			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, (unsigned) kBsCap);
+		}
 		void * args[] = {(void *) &Fc, (void *) &N, (void *) &range, (void *) &k0, (void *) &v0, (void *) &k1, (void *) &v1, (void *) &sc, (void *) &S,
 		                 (void *) &Fo, (void *) &po};
 		PNOL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *) ga_sort_kernel, dim3(P->sort_grid), dim3(kSortThreads), args, 0, ctx->stream));

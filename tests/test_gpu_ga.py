@@ -120,3 +120,29 @@ def test_ga_static_stop_and_invalid_fractions(ctx):
     assert st.stopped == 1 and st.generation == want["iters"] == 2
     X, F = ga.population()
     assert np.array_equal(F, want["F"]) and np.array_equal(X, want["xpop"])
+
+
+@pytest.mark.parametrize("npop", [70_000, 300_000])
+def test_bucket_sort_equals_radix_sort(ctx, npop):
+    """popSort at large Npop runs as splitter buckets + per-bucket shared-memory sorts (csrc/ga_pipeline.cu, 6'); PNOL_GA_SORT=radix
+    keeps the cooperative radix kernel, which the small-population tests above pin to the oracle. Same generations, same bits:
+    objective values, permutation (through the materialised population) and stream position."""
+    import os
+    n = 8
+    f = ctx.functor(capi.F_RASTRIGIN)
+    out = []
+    for mode in ("radix", None):
+        if mode:
+            os.environ["PNOL_GA_SORT"] = mode
+        else:
+            os.environ.pop("PNOL_GA_SORT", None)
+        ga = ctx.ga_create(f, n, np.full(n, -5.12), np.full(n, 5.12), npop, 12, dict(seed=99, scale=1.0 - 2.0 ** -20), nstatic=1e9)
+        ga.init(np.full(n, 0.7))
+        for _ in range(6):
+            ga.generation()
+        X, F = ga.population()
+        out.append((X, F, ga.status().stream_pos))
+        ga.close()
+    os.environ.pop("PNOL_GA_SORT", None)
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0]) and out[0][2] == out[1][2]
+    assert np.all(np.diff(out[1][1]) >= 0)
