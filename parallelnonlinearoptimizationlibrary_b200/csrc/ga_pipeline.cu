@@ -57,23 +57,47 @@ struct GaDevStatus {
 	int sort_fallback;                  // bucket sort: a bucket outgrew one CTA, the radix kernel sorts instead
 };
 
+// Acceptance test of a selection trial, selectValue <= fitness[randomIndex] / maxFitness (Source/GeneticAlgorithmMPI.cpp:141), without
+// the look-up for all but one trial in a thousand. The population is sorted by objective value, so ratio[k] = fitness[k] / maxFitness
+// falls with k, and "ratio[k] >= s" holds exactly for k below a threshold. ga_prep_kernel tabulates K[b] = #{k : ratio[k] >= b / B},
+// b = 0 .. B (B = kAccBuckets, stored behind the ratio array); for s in [b / B, (b + 1) / B):
+//     k <  K[b + 1]  =>  ratio[k] >= (b + 1) / B > s   accepted,
+//     k >= K[b]      =>  ratio[k] <  b / B <= s        rejected,
+// and only K[b + 1] <= k < K[b] -- a fraction 1 / B of the trials -- reads ratio[k] itself. The table is 4 KB and stays in L1; the
+// ratio array is 8 MB, and its 44 M random 8-byte reads per generation (one 32-byte L2 sector each) were what bounded the trial scans.
+constexpr int kAccBuckets = 1024;
+
+// K: the threshold table (global: behind the ratio array, read through L1; or a shared-memory copy). Branch-free up to the rare
+// look-up: both thresholds are loaded unconditionally and only the ambiguous band touches ratio[].
+__device__ __forceinline__ bool pipe_accept(double selectValue, int randomIndex, const double * __restrict__ ratio, const unsigned * K)
+{
+	const bool in01 = selectValue >= 0.0 && selectValue < 1.0;                                      // a draw of a [0, 1) stream
+	const int b = in01 ? (int) (selectValue * kAccBuckets) : 0;
+	const unsigned k_hi = K[b], k_lo = K[b + 1];
+	bool acc = (unsigned) randomIndex < k_lo;
+	if (!in01 || ((unsigned) randomIndex >= k_lo && (unsigned) randomIndex < k_hi)) acc = selectValue <= ratio[randomIndex];
+	return acc;
+}
+__device__ __forceinline__ const unsigned * pipe_thresholds(const double * __restrict__ ratio, int Npop) { return reinterpret_cast<const unsigned *>(ratio + Npop); }
+
 // index of the selection trial at stream position q (Source/GeneticAlgorithmMPI.cpp:134-144): round(u(q) Npop); 0 = rejected.
 // ratio[k] = fitness[k] / maxFitness is tabulated once per generation (the same IEEE division, 1M instead of ~40M times)
-__device__ __forceinline__ int pipe_trial(const StreamDev & st, unsigned long long q, const double * __restrict__ ratio, int Npop)
+__device__ __forceinline__ int pipe_trial(const StreamDev & st, unsigned long long q, const double * __restrict__ ratio, int Npop, const unsigned * K)
 {
 	const int randomIndex = (int) round(st.u(q) * Npop);
 	const double selectValue = st.u(q + 1);
 	if (randomIndex <= 0 || randomIndex >= Npop) return 0;
-	return (selectValue <= ratio[randomIndex]) ? randomIndex : 0;
+	return pipe_accept(selectValue, randomIndex, ratio, K) ? randomIndex : 0;
 }
 
 // the same for a counter stream whose state at position q is at hand (the second draw's state is one increment on)
-__device__ __forceinline__ int pipe_trial_state(const StreamDev & st, unsigned long long z, const double * __restrict__ ratio, int Npop)
+__device__ __forceinline__ int pipe_trial_state(const StreamDev & st, unsigned long long z, const double * __restrict__ ratio, int Npop, const unsigned * K)
 {
-	const int randomIndex = (int) round(st.from_state(z) * Npop);
+	int randomIndex = (int) round(st.from_state(z) * Npop);
 	const double selectValue = st.from_state(z + StreamDev::kGamma);
-	if (randomIndex <= 0 || randomIndex >= Npop) return 0;
-	return (selectValue <= ratio[randomIndex]) ? randomIndex : 0;
+	const bool in_range = randomIndex > 0 && randomIndex < Npop;
+	if (!in_range) randomIndex = 0;                       // a valid index for the (discarded) test
+	return (pipe_accept(selectValue, randomIndex, ratio, K) && in_range) ? randomIndex : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -91,8 +115,22 @@ ga_prep_kernel(const double * __restrict__ Fs, int Npop, int Nelite, double * __
 		const double d = fw - Fs[k];
 		const double fit = d * d;                                          // pow(F[Npop-1] - F[k], 2)
 		fitness[k] = fit;
-		ratio[k] = fit / maxFitness;
+		const double r = fit / maxFitness;
+		ratio[k] = r;
 		if (k < Nelite) Fchild[k] = Fs[k];
+		// K[b] = k + 1 for the b with ratio[k] >= b / B > ratio[k + 1] (pipe_accept; B a power of two: ratio * B is exact). A
+		// degenerate generation (NaN / inf ratios) is stopped by S->error before any trial reads the table.
+		unsigned * K = reinterpret_cast<unsigned *>(ratio + Npop);
+		if (r >= 0.0 && r <= 1.0) {
+			const int hi_b = (int) (r * kAccBuckets);
+			int lo_b = -1;
+			if (k + 1 < Npop) {
+				const double dn = fw - Fs[k + 1];
+				const double rn = (dn * dn) / maxFitness;
+				lo_b = (rn >= 0.0 && rn <= 1.0) ? (int) (rn * kAccBuckets) : hi_b;
+			}
+			for (int b = lo_b + 1; b <= hi_b; b++) K[b] = (unsigned) (k + 1);
+		}
 	}
 	if (k == 0) {
 		S->pos0 = pos0; S->cross_last_trial = -1; S->mut_last_q = -1; S->mut_children = 0; S->pos_elite = 0;
@@ -162,12 +200,15 @@ ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __res
 	unsigned * s_bits = cross_sm;                                // W acceptance words
 	unsigned * s_woff = cross_sm + W;                            // W: exclusive prefix of the words' popcounts inside the CTA
 	unsigned short * s_list = (unsigned short *) (cross_sm + 2 * W);   // accepted trials of a chunk (offset inside the chunk), rank order
+	__shared__ unsigned s_K[kAccBuckets + 1];                    // acceptance thresholds (pipe_accept)
 	__shared__ unsigned long long s_red[kCrossThreads / 32];
 	__shared__ unsigned long long s_before, s_total;
 	if (S->error) return;                                        // set before the launch: uniform over the grid
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int G = gridDim.x, cta = blockIdx.x;
 	const unsigned long long pos = S->pos0;
+	for (int b = tid; b <= kAccBuckets; b += kCrossThreads) s_K[b] = pipe_thresholds(ratio, Npop)[b];
+	__syncthreads();
 	unsigned long long done = 0;                                 // ranks filled by earlier rounds
 	for (int pass = 0; pass < max_rounds; pass++) {
 		const long long tb = ((long long) pass * G + cta) * (long long) W * 32;      // first trial of this CTA's range
@@ -178,16 +219,20 @@ ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __res
 			unsigned long long z = st.state(pos + 2ULL * (unsigned long long) (tb + (long long) warp * 32 + lane));
 			const unsigned long long dz = (unsigned long long) (2 * 32 * (kCrossThreads / 32)) * StreamDev::kGamma;
 			int w = warp;
-			for (; w + kCrossThreads / 32 < W; w += 2 * (kCrossThreads / 32), z += 2 * dz) {
-				// two independent trials per lane in flight: the ratio look-up of one hides behind the arithmetic of the other
-				const bool acc0 = pipe_trial_state(st, z, ratio, Npop) != 0;
-				const bool acc1 = pipe_trial_state(st, z + dz, ratio, Npop) != 0;
+			constexpr int kWS = kCrossThreads / 32;                  // word stride of a warp
+			for (; w + 3 * kWS < W; w += 4 * kWS, z += 4 * dz) {
+				// four independent trials per lane in flight
+				const bool acc0 = pipe_trial_state(st, z, ratio, Npop, s_K) != 0;
+				const bool acc1 = pipe_trial_state(st, z + dz, ratio, Npop, s_K) != 0;
+				const bool acc2 = pipe_trial_state(st, z + 2 * dz, ratio, Npop, s_K) != 0;
+				const bool acc3 = pipe_trial_state(st, z + 3 * dz, ratio, Npop, s_K) != 0;
 				const unsigned m0 = __ballot_sync(0xffffffffu, acc0), m1 = __ballot_sync(0xffffffffu, acc1);
-				if (lane == 0) { s_bits[w] = m0; s_bits[w + kCrossThreads / 32] = m1; }
-				cnt += __popc(m0) + __popc(m1);                  // the same in every lane
+				const unsigned m2 = __ballot_sync(0xffffffffu, acc2), m3 = __ballot_sync(0xffffffffu, acc3);
+				if (lane == 0) { s_bits[w] = m0; s_bits[w + kWS] = m1; s_bits[w + 2 * kWS] = m2; s_bits[w + 3 * kWS] = m3; }
+				cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);      // the same in every lane
 			}
-			for (; w < W; w += kCrossThreads / 32, z += dz) {
-				const bool acc = pipe_trial_state(st, z, ratio, Npop) != 0;
+			for (; w < W; w += kWS, z += dz) {
+				const bool acc = pipe_trial_state(st, z, ratio, Npop, s_K) != 0;
 				const unsigned m = __ballot_sync(0xffffffffu, acc);
 				if (lane == 0) s_bits[w] = m;
 				cnt += __popc(m);
@@ -195,7 +240,7 @@ ga_cross_kernel(StreamDev st, GaDevStatus * __restrict__ S, const double * __res
 		} else {
 			for (int w = warp; w < W; w += kCrossThreads / 32) {
 				const long long t = tb + (long long) w * 32 + lane;
-				const bool acc = pipe_trial(st, pos + 2ULL * (unsigned long long) t, ratio, Npop) != 0;
+				const bool acc = pipe_trial(st, pos + 2ULL * (unsigned long long) t, ratio, Npop, s_K) != 0;
 				const unsigned m = __ballot_sync(0xffffffffu, acc);
 				if (lane == 0) s_bits[w] = m;
 				cnt += __popc(m);
@@ -353,14 +398,14 @@ ga_mut_tables_kernel(StreamDev st, const GaDevStatus * __restrict__ S, const dou
 		unsigned long long z = st.state(P1 + (unsigned long long) G.g * (unsigned long long) (cand0 + (long long) (tid >> 5) * 32 + lane));
 		const unsigned long long dz = (unsigned long long) (G.g * 32 * (kMutThreads / 32)) * StreamDev::kGamma;
 		for (int w = tid >> 5; w < words; w += kMutThreads / 32, z += dz) {
-			const bool acc = pipe_trial_state(st, z, ratio, Npop) != 0;
+			const bool acc = pipe_trial_state(st, z, ratio, Npop, pipe_thresholds(ratio, Npop)) != 0;
 			const unsigned m = __ballot_sync(0xffffffffu, acc);
 			if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
 		}
 	} else {
 		for (int w = tid >> 5; w < words; w += kMutThreads / 32) {
 			const long long j = cand0 + (long long) w * 32 + lane;
-			const bool acc = pipe_trial(st, P1 + (unsigned long long) G.g * (unsigned long long) j, ratio, Npop) != 0;
+			const bool acc = pipe_trial(st, P1 + (unsigned long long) G.g * (unsigned long long) j, ratio, Npop, pipe_thresholds(ratio, Npop)) != 0;
 			const unsigned m = __ballot_sync(0xffffffffu, acc);
 			if (lane == 0) { bits[w] = m; accbits[(size_t) blockIdx.x * words + w] = m; }
 		}
@@ -1312,7 +1357,7 @@ int ga_pipe_create(pnol_ga * ga)
 		for (int r = 0; r < kGaMaxRanks; r++) P->table[b].base[r] = nullptr;
 		P->table[b].base[0] = P->XL[b];
 	}
-	PNOL_CHECK(pipe_alloc(ga, &P->ratio, (size_t) Npop));
+	PNOL_CHECK(pipe_alloc(ga, &P->ratio, (size_t) Npop + kAccBuckets / 2 + 2));      // + the acceptance thresholds K[0 .. kAccBuckets] (pipe_accept)
 	PNOL_CHECK(pipe_alloc(ga, &P->Fchild, std::max((size_t) P->per * R, (size_t) P->eper * ctx->nranks)));
 	PNOL_CHECK(pipe_alloc(ga, &P->bcount, (size_t) P->per * R));
 	PNOL_CHECK(pipe_alloc(ga, &P->dupflag, (size_t) Npop));

@@ -410,6 +410,15 @@ def test_jacobian_rows_outside_the_fast_range_fall_back(ctx):
     assert np.array_equal(F, Fw, equal_nan=True) and np.array_equal(J, Jw, equal_nan=True)
     Fr, _ = ctx.residual_eval(f, x)
     assert np.array_equal(Fr, Fw, equal_nan=True)
+    # row-invariant operands inside the range: only the rows with extreme abscissae leave the speculative pass (the row-per-thread
+    # residual kernel tests |t| + max |c| once per row); then one centre beyond 2^99, which sends every row to `/`
+    for c_far in (None, 1e40):
+        x2 = x.copy()
+        x2[6], x2[10] = 0.75, 1.25
+        if c_far is not None:
+            x2[9] = c_far
+        Fr2, _ = ctx.residual_eval(f, x2)
+        assert np.array_equal(Fr2, O.residual(of, x2), equal_nan=True)
 
 
 def test_lm_step_equals_the_separate_calls(ctx):
