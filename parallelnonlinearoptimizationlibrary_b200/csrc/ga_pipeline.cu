@@ -1009,9 +1009,12 @@ ga_bsort_count_kernel(const double * __restrict__ F, long long N, const double *
 // bucket starts (exclusive scan of the totals), scatter cursors = starts, totals cleared for the next sort
 __global__ void __launch_bounds__(1024)
 ga_bsort_scan_kernel(unsigned * __restrict__ totals, unsigned * __restrict__ bstart /* kBsBuckets + 1 */, unsigned * __restrict__ cursor,
-                     GaDevStatus * __restrict__ S)
+                     GaDevStatus * __restrict__ S, unsigned * __restrict__ large /* [0]: count, then the buckets of more than kBsCap keys */)
 {
 	__shared__ unsigned wsum[32];
+	__shared__ unsigned s_nlarge;
+	if (threadIdx.x == 0) s_nlarge = 0;
+	__syncthreads();
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	unsigned c[4];
 #pragma unroll
@@ -1029,10 +1032,13 @@ ga_bsort_scan_kernel(unsigned * __restrict__ totals, unsigned * __restrict__ bst
 	__syncthreads();
 	unsigned run = wsum[warp] + incl - mine;
 #pragma unroll
-	for (int q = 0; q < 4; q++) { bstart[4 * tid + q] = run; cursor[4 * tid + q] = run; run += c[q]; totals[4 * tid + q] = 0; }
+	for (int q = 0; q < 4; q++) {
+		bstart[4 * tid + q] = run; cursor[4 * tid + q] = run; run += c[q]; totals[4 * tid + q] = 0;
+		if (c[q] > (unsigned) kBsCap) large[1 + atomicAdd(&s_nlarge, 1u)] = (unsigned) (4 * tid + q);      // order is irrelevant
+	}
 	if (tid == 1023) bstart[kBsBuckets] = run;
 	const int overflow = __syncthreads_or(c[0] > (unsigned) kBsCapLarge || c[1] > (unsigned) kBsCapLarge || c[2] > (unsigned) kBsCapLarge || c[3] > (unsigned) kBsCapLarge);
-	if (tid == 0) S->sort_fallback = overflow;
+	if (tid == 0) { S->sort_fallback = overflow; large[0] = s_nlarge; }
 }
 static_assert(kBsBuckets == 4096 && (1 << kBsLog2) == kBsBuckets, "ga_bsort_scan_kernel scans four buckets per thread of one 1024-thread CTA");
 
@@ -1071,7 +1077,8 @@ ga_bsort_scatter_kernel(const double * __restrict__ F, long long N, const unsign
 template <int kThreads, int kPer>
 __global__ void __launch_bounds__(kThreads)
 ga_bsort_bucket_kernel(const unsigned long long * __restrict__ keys, const unsigned * __restrict__ vals, const unsigned * __restrict__ bstart,
-                       const GaDevStatus * __restrict__ S, double * __restrict__ Fsorted, unsigned * __restrict__ perm_out, unsigned min_cnt)
+                       const GaDevStatus * __restrict__ S, double * __restrict__ Fsorted, unsigned * __restrict__ perm_out, unsigned min_cnt,
+                       const unsigned * __restrict__ list /* nullptr: bucket = blockIdx.x; else [0] = count, buckets follow */)
 {
 	constexpr int kCap = kThreads * kPer;
 	extern __shared__ unsigned long long bs_smem[];
@@ -1082,8 +1089,11 @@ ga_bsort_bucket_kernel(const unsigned long long * __restrict__ keys, const unsig
 	__shared__ unsigned wtot[kThreads / 32];
 	if (S->sort_fallback) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const unsigned b0 = bstart[blockIdx.x], cnt = bstart[blockIdx.x + 1] - b0;
-	if (cnt <= min_cnt || cnt > (unsigned) kCap) return;
+	const unsigned n_list = list ? list[0] : 1u;
+	for (unsigned li = list ? blockIdx.x : 0u; li < n_list; li += gridDim.x) {
+	const unsigned bucket = list ? list[1 + li] : blockIdx.x;
+	const unsigned b0 = bstart[bucket], cnt = bstart[bucket + 1] - b0;
+	if (cnt <= min_cnt || cnt > (unsigned) kCap) { if (list) continue; else return; }
 	unsigned nsub = 32;
 	while (nsub < cnt) nsub <<= 1;                      // <= kCap
 	unsigned long long k[kPer];
@@ -1158,7 +1168,10 @@ ga_bsort_bucket_kernel(const unsigned long long * __restrict__ keys, const unsig
 			perm_out[b0 + s0 + smaller] = v[q];
 		}
 	}
+	__syncthreads();          // shared memory is reused by the next bucket of the list
+	}
 }
+
 constexpr size_t bsort_bucket_smem(int cap) { return (size_t) cap * 12 + ((size_t) cap + 1) * 4 + 8; }
 
 
@@ -1231,7 +1244,7 @@ struct GaPipe {
 	// sort
 	unsigned long long * skeys[2] = {nullptr, nullptr}; unsigned * svals[2] = {nullptr, nullptr}; unsigned * scounts = nullptr;
 	int sort_grid = 0; long long sort_range = 0;
-	unsigned * bs_tag = nullptr, * bs_totals = nullptr, * bs_start = nullptr, * bs_cursor = nullptr; bool bs_on = false; int bs_grid = 0;
+	unsigned * bs_tag = nullptr, * bs_totals = nullptr, * bs_start = nullptr, * bs_cursor = nullptr, * bs_large = nullptr; bool bs_on = false; int bs_grid = 0;
 	// status
 	GaDevStatus * status = nullptr; GaDevStatus * status_host = nullptr;
 	unsigned long long pos_elite_last = 0;           // start of the last generation's elite-mutation stage (for get_indices)
@@ -1406,6 +1419,7 @@ int ga_pipe_create(pnol_ga * ga)
 			PNOL_CHECK(pipe_alloc(ga, &P->bs_totals, (size_t) kBsBuckets));
 			PNOL_CHECK(pipe_alloc(ga, &P->bs_start, (size_t) kBsBuckets + 1));
 			PNOL_CHECK(pipe_alloc(ga, &P->bs_cursor, (size_t) kBsBuckets));
+			PNOL_CHECK(pipe_alloc(ga, &P->bs_large, (size_t) kBsBuckets + 1));
 			PNOL_CUDA(ctx, cudaMemsetAsync(P->bs_totals, 0, kBsBuckets * sizeof(unsigned), ctx->stream));
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_bsort_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBsBuckets * 12));
 			PNOL_CUDA(ctx, cudaFuncSetAttribute(ga_bsort_bucket_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bsort_bucket_smem(kBsCapLarge)));
@@ -1657,12 +1671,13 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 		double * Fo = P->Fs[nxt];
 		if (P->bs_on) {
 			PNOL_LAUNCH(ctx, ga_bsort_count_kernel, P->bs_grid, kBsCountThreads, kBsBuckets * 12, Fc, N, (const double *) P->Fs[cur], P->bs_tag, P->bs_totals);
-			PNOL_LAUNCH(ctx, ga_bsort_scan_kernel, 1, 1024, 0, P->bs_totals, P->bs_start, P->bs_cursor, S);
+			PNOL_LAUNCH(ctx, ga_bsort_scan_kernel, 1, 1024, 0, P->bs_totals, P->bs_start, P->bs_cursor, S, P->bs_large);
 			PNOL_LAUNCH(ctx, ga_bsort_scatter_kernel, P->bs_grid, kBsCountThreads, 0, Fc, N, (const unsigned *) P->bs_tag, P->bs_cursor, k0, v0);
 			PNOL_LAUNCH(ctx, (ga_bsort_bucket_kernel<128, 8>), kBsBuckets, 128, bsort_bucket_smem(kBsCap), (const unsigned long long *) k0, (const unsigned *) v0,
-			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, 0u);
-			PNOL_LAUNCH(ctx, (ga_bsort_bucket_kernel<512, 16>), kBsBuckets, 512, bsort_bucket_smem(kBsCapLarge), (const unsigned long long *) k0, (const unsigned *) v0,
-			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, (unsigned) kBsCap);
+			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, 0u, (const unsigned *) nullptr);
+			// the large buckets from the list the scan kernel made (4096 CTAs of 131 KB that only look and leave took 20 us)
+			PNOL_LAUNCH(ctx, (ga_bsort_bucket_kernel<512, 16>), ctx->sm_count, 512, bsort_bucket_smem(kBsCapLarge), (const unsigned long long *) k0, (const unsigned *) v0,
+			            (const unsigned *) P->bs_start, (const GaDevStatus *) S, Fo, po, (unsigned) kBsCap, (const unsigned *) P->bs_large);
 		}
 		void * args[] = {(void *) &Fc, (void *) &N, (void *) &range, (void *) &k0, (void *) &v0, (void *) &k1, (void *) &v1, (void *) &sc, (void *) &S,
 		                 (void *) &Fo, (void *) &po};
