@@ -641,8 +641,12 @@ def run_ours(args):
         if "residual" in timers:
             by = 3.0 * m_loc * 8
             a = by / (timers["residual"]["ms_avg"] * 1e-3) / 1e9
+            # row-per-thread kernel: 12 K + (K - 1) + 1 FP64 operations per row (K terms of a / (1 + w (t - c)^2) with IEEE divisions, the tree, y - S)
+            res_ops = (13.0 * K) * m_loc
             kern["residual"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": tr("residual"),
-                                "ms": timers["residual"]["ms_avg"], "algorithmic_bytes": by, "peak_source": hbm_src}
+                                "ms": timers["residual"]["ms_avg"], "algorithmic_bytes": by, "peak_source": hbm_src,
+                                "fp64_alu_frac": res_ops / (timers["residual"]["ms_avg"] * 1e-3) / (ctx.sm_count * 64 * 1.965e9),
+                                "note": "FP64-ALU-bound: 24 bytes but 13 K = 1664 FP64 operations per row; the HBM fraction says nothing here, the FP64-ALU fraction does"}
         dominant = max(timers, key=lambda k: timers[k]["ms_avg"] * timers[k]["count"]) if timers else None
         roof = kern.get(dominant) or kern.get("syrk") or {}
         roof = dict(roof, kernel=dominant,
