@@ -574,12 +574,23 @@ ga_mut_apply_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable c
 		const unsigned long long q = mut_stage_pos(S) + (unsigned long long) child_q[k] + 2ULL;
 		const double * src = cur.row(perm[child_idx[k]]);
 		double * dst = Xloc + (row - own_lo) * n;
-		for (int j = g; j < n; j += kRowLanes) {
-			const double mutation = spreadRatio * (ub[j] - lb[j]) * st.u(q + (unsigned long long) j);
-			const double v = __ldcg(src + j) + mutation;
-			dst[j] = v;
-			h += gene_hash(v, j);
-			oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+		// four genes of the lane at a time, all parent loads issued before the first store (the compiler keeps a load behind an
+		// earlier store it cannot tell apart: one HBM round trip per gene otherwise)
+		for (int j0 = g; j0 < n; j0 += 4 * kRowLanes) {
+			double pv[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) { const int j = j0 + u * kRowLanes; pv[u] = j < n ? __ldcg(src + j) : 0.0; }
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int j = j0 + u * kRowLanes;
+				if (j < n) {
+					const double mutation = spreadRatio * (ub[j] - lb[j]) * st.u(q + (unsigned long long) j);
+					const double v = pv[u] + mutation;
+					dst[j] = v;
+					h += gene_hash(v, j);
+					oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+				}
+			}
 		}
 	}
 	h = group_sum(h); oob = group_sum(oob);
@@ -606,15 +617,34 @@ ga_elite_mut_kernel(StreamDev st, const GaDevStatus * __restrict__ S, RowTable c
 	if (live) {
 		const unsigned long long P2 = S->pos_elite;
 		double * dst = Xloc + (row - own_lo) * n;
-		for (int j = g; j < n; j += kRowLanes) {
-			const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
-			const int randomEliteIdx = (int) round(st.u(P2 + 2ULL * e) * Nelite);
-			const double mutation = eliteMutationSize * (ub[j] - lb[j]) * st.u(P2 + 2ULL * e + 1ULL);
-			const double v = __ldcg(cur.row(perm[randomEliteIdx]) + j) + mutation;
-			dst[j] = v;
-			elite_idx[e] = randomEliteIdx;
-			h += gene_hash(v, j);
-			oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+		// four genes of the lane at a time: the four chains draw -> perm -> gene run side by side, stores last (see ga_mut_apply_kernel)
+		for (int j0 = g; j0 < n; j0 += 4 * kRowLanes) {
+			int idx[4];
+			unsigned slot[4];
+			double pv[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int j = j0 + u * kRowLanes;
+				const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
+				idx[u] = j < n ? (int) round(st.u(P2 + 2ULL * e) * Nelite) : 0;
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) slot[u] = perm[idx[u]];
+#pragma unroll
+			for (int u = 0; u < 4; u++) { const int j = j0 + u * kRowLanes; pv[u] = j < n ? __ldcg(cur.row(slot[u]) + j) : 0.0; }
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int j = j0 + u * kRowLanes;
+				if (j < n) {
+					const unsigned long long e = (unsigned long long) c * (unsigned long long) n + (unsigned long long) j;
+					const double mutation = eliteMutationSize * (ub[j] - lb[j]) * st.u(P2 + 2ULL * e + 1ULL);
+					const double v = pv[u] + mutation;
+					dst[j] = v;
+					elite_idx[e] = idx[u];
+					h += gene_hash(v, j);
+					oob += (v > ub[j] || v < lb[j]) ? 1u : 0u;
+				}
+			}
 		}
 	}
 	h = group_sum(h); oob = group_sum(oob);
