@@ -29,6 +29,9 @@
  *   PNOL_GA_LEGACY=1      genetic algorithm with the stage-by-stage generation of round 1 instead of the fused pipeline
  *   PNOL_GA_SHARD=rows|sweep   overrides pnol_ga_set_sharding
  *   PNOL_GA_NO_IPC=1      several GPUs: population replicas + all-gather instead of peer mappings (A/B runs, boxes without IPC)
+ *   PNOL_GA_SORT=radix    GA popSort with the cooperative radix kernel only (default: splitter buckets in front of it; read per pnol_ga_create)
+ *   PNOL_LM_PEER=0        several GPUs: the LM step's two sums through NCCL instead of the fused peer-memory kernels (csrc/peer.cu)
+ *   PNOL_LORENTZ_ROWWISE=0  trial residuals of the sum-of-Lorentzians model with the row-per-warp kernel (default: one row per thread)
  * and by the host classes (include/pnol/Runtime.hpp): PNOL_DEVICE, PNOL_POOL_WIDTH, PNOL_LM_JACOBIAN_CACHE.
  */
 #ifndef PNOL_B200_H_

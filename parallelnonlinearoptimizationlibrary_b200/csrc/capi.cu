@@ -680,23 +680,31 @@ static int lm_step_enqueue(pnol_ctx * ctx, const pnol_functor * f, const double 
 	const long long m = f->params.m;
 	const size_t nn = (size_t) n * n;
 	const size_t packed_count = nn + n;
+	// several ranks: the partial sums are exchanged over NVLink peer memory when every rank could map every other's buffer (peer.cu:
+	// all-reduce and damping in one kernel, the chi^2 sum in another), through NCCL otherwise. Collective decision, taken once.
+	const bool peer = ctx->nranks > 1 && peer_ensure(ctx, packed_count);
 	if (!reuse_jtj) {
+		double * packed = peer ? peer_partial_slot(ctx) : W.packed;
 		// J^T F: summed by the structured Jacobian kernel while it holds the rows of J (cheap there); the black-box kernel leaves
 		// it to the SYRK (extra tensor tiles). Either way it ends behind J^T J in `packed`, before the all-reduce.
 		if (!J) {
 			// no J buffer given: the normal equations are summed over row blocks, J is never stored (normal_eq_blocks)
-			PNOL_CHECK(normal_eq_blocks(ctx, f, x_dev, dx_dev, n, jac_mode, F, nullptr, W.packed));
+			PNOL_CHECK(normal_eq_blocks(ctx, f, x_dev, dx_dev, n, jac_mode, F, nullptr, packed));
 		} else {
 			bool jtf_done = false;
 			double * jtf = W.sig;      // free until the solve
 			PNOL_CHECK(launch_fd_jacobian(ctx, f, x_dev, dx_dev, n, J, nullptr, jac_mode, F, jtf, &jtf_done));
-			PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, W.packed));
-			if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(W.packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+			PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed));
+			if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 		}
-		if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.packed, packed_count));
-		PNOL_CHECK(launch_lm_damp(ctx, W.packed, n, lambda, JTJ, W.A, W.rhs, lambda_dev));
-		// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it
-		PNOL_CUDA(ctx, cudaMemcpyAsync(JTJ + nn, W.rhs, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		if (peer) {
+			PNOL_CHECK(launch_peer_reduce_damp(ctx, n, lambda, lambda_dev, JTJ, W.A, W.rhs));      // JTJ + nn takes the right-hand side as well
+		} else {
+			if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.packed, packed_count));
+			PNOL_CHECK(launch_lm_damp(ctx, W.packed, n, lambda, JTJ, W.A, W.rhs, lambda_dev));
+			// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it
+			PNOL_CUDA(ctx, cudaMemcpyAsync(JTJ + nn, W.rhs, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+		}
 	} else {
 		PNOL_CHECK(launch_lm_damp(ctx, JTJ, n, lambda, nullptr, W.A, nullptr, lambda_dev));
 		PNOL_CUDA(ctx, cudaMemcpyAsync(W.rhs, JTJ + nn, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -704,7 +712,8 @@ static int lm_step_enqueue(pnol_ctx * ctx, const pnol_functor * f, const double 
 	PNOL_CHECK(launch_spd_solve(ctx, W.A, W.rhs, n, W.sig, W.info));
 	PNOL_LAUNCH(ctx, lm_trial_point_kernel, (n + 127) / 128, 128, 0, x_dev, W.sig, W.info, n, W.xt, W.sigf);
 	PNOL_CHECK(launch_residual(ctx, f, W.xt, n, Ftrial, W.ss));
-	if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.ss, 1));
+	if (peer) PNOL_CHECK(launch_peer_scalar_sum(ctx, W.ss));
+	else if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.ss, 1));
 	return PNOL_OK;
 }
 
@@ -729,6 +738,7 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 	double * pin = ctx->pinned;
 	PNOL_CUDA(ctx, cudaMemcpyAsync(pin, W.xt, (2 * (size_t) n + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	PNOL_CHECK(finish(ctx));
+	PNOL_CHECK(peer_check(ctx));
 	if (x_trial_out) memcpy(x_trial_out, pin, (size_t) n * sizeof(double));
 	if (sigma_out) memcpy(sigma_out, pin + n, (size_t) n * sizeof(double));
 	if (sumsq_trial_out) *sumsq_trial_out = pin[2 * n];
@@ -832,6 +842,7 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 			}
 			PNOL_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, xs, ((size_t) n + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 			PNOL_CHECK(finish(ctx));
+			PNOL_CHECK(peer_check(ctx));
 			memcpy(&h, ctx->pinned + n, sizeof h);
 			done += k;
 		}

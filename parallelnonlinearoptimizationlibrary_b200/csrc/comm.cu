@@ -104,6 +104,7 @@ int comm_broadcast_dev(pnol_ctx * ctx, double * buf, size_t count, int root)
 
 void comm_destroy(pnol_ctx * ctx)
 {
+	peer_destroy(ctx);                               // the peer mappings belong to this communicator's ranks
 	if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy((ncclComm_t) ctx->comm);
 	ctx->comm = nullptr; ctx->nranks = 1; ctx->rank = 0;
 	ctx->local = false; ctx->comm_nranks = 1; ctx->comm_rank = 0;

@@ -13,6 +13,7 @@
 #include "pnol/functors.hpp"
 
 struct ncclComm;
+namespace pnol { struct PnolPeer; }
 
 struct PnolTimerEntry {
 	double total_ms = 0;
@@ -57,6 +58,7 @@ struct pnol_ctx {
 	int comm_nranks = 1;
 
 	int ga_sharding = 0;           // pnol_ga_set_sharding: 0 auto, 1 rows, 2 sweep
+	pnol::PnolPeer * peer = nullptr;   // NVLink peer-memory exchange of the sharded LM step (peer.cu)
 
 	// timers
 	bool timers_on = false;
@@ -280,5 +282,13 @@ int launch_hinv_literal(pnol_ctx * ctx, double * D, const double * g, const doub
 int comm_allreduce_dev(pnol_ctx * ctx, double * dev_buf, size_t count);
 int comm_allgather_dev(pnol_ctx * ctx, const double * send, double * recv, size_t count_per_rank);
 int comm_broadcast_dev(pnol_ctx * ctx, double * buf, size_t count, int root);
+
+// peer.cu: the sharded LM step's exchange over NVLink peer memory (fused all-reduce + damping); collective set-up, NCCL fallback
+bool peer_ensure(pnol_ctx * ctx, size_t count);
+double * peer_partial_slot(pnol_ctx * ctx);
+int launch_peer_reduce_damp(pnol_ctx * ctx, int n, double lambda, const double * lambda_dev, double * JTJ, double * A, double * rhs);
+int launch_peer_scalar_sum(pnol_ctx * ctx, double * ss);
+int peer_check(pnol_ctx * ctx);
+void peer_destroy(pnol_ctx * ctx);
 
 } // namespace pnol
