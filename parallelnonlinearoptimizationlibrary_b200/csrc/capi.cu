@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" glue of include/pnol_b200.h: context, memory, functors, and the evaluation / LM / BFGS
 // entry points (the GA entry points live in ga.cu, the communicator in comm.cu).
 #include "common.cuh"
+#include "peer.cuh"
 
 #include <mutex>
 #include <vector>
@@ -252,7 +253,7 @@ extern "C" int pnol_host_free(void * host_ptr)
 extern "C" int pnol_timer_enable(pnol_ctx * ctx, int on)
 {
 	if (!ctx) return PNOL_ERR_INVALID;
-	ctx->timers_on = on != 0;
+	ctx->timers_on = on == 2 ? 2 : (on != 0 ? 1 : 0);
 	return PNOL_OK;
 }
 extern "C" int pnol_timer_get(pnol_ctx * ctx, const char * name, double * total_ms, long long * count)
@@ -639,18 +640,6 @@ extern "C" int pnol_lm_damp(pnol_ctx * ctx, const double * JTJ, int n, double la
 // caller, exactly as in the reference. The five separate entry points above cost two synchronisations and five boundary
 // crossings per iteration, which is what is left of an iteration at 8 GPUs.
 // ---------------------------------------------------------------------------------------------------
-__global__ void lm_trial_point_kernel(const double * __restrict__ x, const double * __restrict__ sigma, const int * __restrict__ info, int n,
-                                      double * __restrict__ xt, double * __restrict__ sigma_out)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	// a non-positive pivot: the reference's luSolve would have produced inf / NaN and the step would be rejected by the NaN test
-	// of its chi^2 (Source/LevenbergMarquardtMPI.cpp:110); hand back a NaN step for the same outcome
-	double s = (*info != 0) ? __longlong_as_double(0x7ff8000000000000LL) : sigma[i];
-	sigma_out[i] = s;
-	xt[i] = x[i] + s;                       // X[i] = X[i] + sigma[i]   (:97-100)
-}
-
 static int normal_eq_blocks(pnol_ctx * ctx, const pnol_functor * f, const double * x_dev, const double * dx_dev, int n, int jac_mode,
                             const double * F_known, double * F_out, double * total);
 
@@ -673,9 +662,16 @@ static int lm_scratch(pnol_ctx * ctx, int n, LmScratch & W)
 
 // enqueue the device work of one LM step (no synchronisation): x_dev / dx_dev device pointers; lambda from the host scalar or, when
 // lambda_dev != nullptr, from device memory. Results stay in the scratch block: xt (trial point), sigf (step), ss (sum Ftrial^2), info.
+// tail != nullptr (pnol_lm_iterate): on one rank, or with the peer exchange, the trial sum of squares is left as block partials for
+// the caller's lm_tail_kernel (final sum + exchange + accept / reject in one launch); tail->deferred says whether that happened.
+struct LmTail {
+	const double * partials = nullptr;
+	int np = 0;
+	bool deferred = false, peer = false;
+};
 static int lm_step_enqueue(pnol_ctx * ctx, const pnol_functor * f, const double * x_dev, const double * dx_dev, int n, double * J,
                            const double * F, double * Ftrial, double lambda, const double * lambda_dev, int jac_mode, int reuse_jtj,
-                           double * JTJ, const LmScratch & W)
+                           double * JTJ, const LmScratch & W, LmTail * tail = nullptr)
 {
 	const long long m = f->params.m;
 	const size_t nn = (size_t) n * n;
@@ -694,23 +690,27 @@ static int lm_step_enqueue(pnol_ctx * ctx, const pnol_functor * f, const double 
 			bool jtf_done = false;
 			double * jtf = W.sig;      // free until the solve
 			PNOL_CHECK(launch_fd_jacobian(ctx, f, x_dev, dx_dev, n, J, nullptr, jac_mode, F, jtf, &jtf_done));
-			PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed));
-			if (jtf_done) PNOL_CUDA(ctx, cudaMemcpyAsync(packed + nn, jtf, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+			PNOL_CHECK(launch_syrk(ctx, J, jtf_done ? nullptr : F, m, n, packed, jtf_done ? jtf : nullptr));      // the finish kernel puts jtf behind J^T J
 		}
 		if (peer) {
 			PNOL_CHECK(launch_peer_reduce_damp(ctx, n, lambda, lambda_dev, JTJ, W.A, W.rhs));      // JTJ + nn takes the right-hand side as well
 		} else {
 			if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.packed, packed_count));
-			PNOL_CHECK(launch_lm_damp(ctx, W.packed, n, lambda, JTJ, W.A, W.rhs, lambda_dev));
 			// the right-hand side is kept behind J^T J in the caller's buffer so that a re-damped step can reuse it
-			PNOL_CUDA(ctx, cudaMemcpyAsync(JTJ + nn, W.rhs, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+			PNOL_CHECK(launch_lm_damp(ctx, W.packed, n, lambda, JTJ, W.A, W.rhs, lambda_dev, true));
 		}
 	} else {
 		PNOL_CHECK(launch_lm_damp(ctx, JTJ, n, lambda, nullptr, W.A, nullptr, lambda_dev));
 		PNOL_CUDA(ctx, cudaMemcpyAsync(W.rhs, JTJ + nn, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 	}
-	PNOL_CHECK(launch_spd_solve(ctx, W.A, W.rhs, n, W.sig, W.info));
-	PNOL_LAUNCH(ctx, lm_trial_point_kernel, (n + 127) / 128, 128, 0, x_dev, W.sig, W.info, n, W.xt, W.sigf);
+	// solve, and with it the trial point: sigf = sigma (NaN after a non-positive pivot), xt = x + sigf  (:88, :97-100)
+	PNOL_CHECK(launch_spd_solve(ctx, W.A, W.rhs, n, W.sig, W.info, x_dev, W.xt, W.sigf));
+	if (tail && (ctx->nranks == 1 || peer)) {
+		PNOL_CHECK(launch_residual(ctx, f, W.xt, n, Ftrial, nullptr, &tail->partials, &tail->np));
+		tail->deferred = true;
+		tail->peer = peer;
+		return PNOL_OK;
+	}
 	PNOL_CHECK(launch_residual(ctx, f, W.xt, n, Ftrial, W.ss));
 	if (peer) PNOL_CHECK(launch_peer_scalar_sum(ctx, W.ss));
 	else if (ctx->nranks > 1) PNOL_CHECK(comm_allreduce_dev(ctx, W.ss, 1));
@@ -761,6 +761,30 @@ struct LmDevState {
 	int accepted, rejected, stopped, last_accept;
 };
 
+// the rule itself, one thread: returns 1 when the step is accepted. `sum` = sum of the squared trial residuals over all rows
+__device__ __forceinline__ int lm_decide_one(LmDevState * st, double sum, const double * sig_sm, int n, double factor, double x_min_diff)
+{
+	st->last_accept = 0;
+	if (st->stopped) return 0;
+	const double root = sqrt(sum);
+	const double chi = root * root;                              // pow(vector2Norm(F),2)  (:108)
+	if (chi >= st->chisq || chi != chi) {                        // (:110) X and F stay, lambda grows (:118-129)
+		st->lambda = st->lambda * factor;
+		st->rejected++;
+		return 0;
+	}
+	st->lambda = st->lambda / factor;                            // (:132-141)
+	st->chisq = chi;
+	st->accepted++;
+	st->last_accept = 1;
+	if (x_min_diff > 0) {
+		double s2 = 0;
+		for (int i = 0; i < n; i++) s2 = s2 + sig_sm[i] * sig_sm[i];      // vector2Norm: one sequential sum
+		if (sqrt(s2) < x_min_diff) st->stopped = 1;
+	}
+	return 1;
+}
+
 // one block: thread 0 takes the decision, all threads move x (one thread walking n global-memory entries twice took 13 us at n = 256)
 __global__ void __launch_bounds__(256)
 lm_decide_kernel(LmDevState * __restrict__ st, double * __restrict__ x, const double * __restrict__ xt,
@@ -770,29 +794,29 @@ lm_decide_kernel(LmDevState * __restrict__ st, double * __restrict__ x, const do
 	__shared__ int s_accept;
 	if (x_min_diff > 0) for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		int accept = 0;
-		st->last_accept = 0;
-		if (!st->stopped) {
-			const double root = sqrt(ss[0]);
-			const double chi = root * root;                          // pow(vector2Norm(F),2)  (:108)
-			if (chi >= st->chisq || chi != chi) {                    // (:110) X and F stay, lambda grows (:118-129)
-				st->lambda = st->lambda * factor;
-				st->rejected++;
-			} else {
-				st->lambda = st->lambda / factor;                    // (:132-141)
-				st->chisq = chi;
-				st->accepted++;
-				st->last_accept = 1;
-				accept = 1;
-				if (x_min_diff > 0) {
-					double s2 = 0;
-					for (int i = 0; i < n; i++) s2 = s2 + sig_sm[i] * sig_sm[i];      // vector2Norm: one sequential sum
-					if (sqrt(s2) < x_min_diff) st->stopped = 1;
-				}
-			}
+	if (threadIdx.x == 0) s_accept = lm_decide_one(st, ss[0], sig_sm, n, factor, x_min_diff);
+	__syncthreads();
+	if (s_accept) for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xt[i];
+}
+
+// The end of a device-resident iteration in ONE launch (one block of 1024 threads): final stage of the trial sum of squares
+// (sumsq_final_sum: the bits of sumsq_final_kernel), its sum over the ranks through peer memory (peer_scalar_exchange_warp: the bits
+// of peer_scalar_sum_kernel; P.R <= 1: no exchange), the accept / reject rule and the move of x. Replaces three launches.
+__global__ void __launch_bounds__(1024)
+lm_tail_kernel(const double * __restrict__ partials, int np, const PeerScalarArgs P, LmDevState * __restrict__ st, double * __restrict__ x,
+               const double * __restrict__ xt, const double * __restrict__ sigma, double * __restrict__ ss, int n, double factor, double x_min_diff)
+{
+	extern __shared__ double sig_sm[];
+	__shared__ double red[1024];
+	__shared__ int s_accept;
+	if (x_min_diff > 0) for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
+	const double mine = sumsq_final_sum(partials, np, red);      // (ends in a barrier: sig_sm is complete as well)
+	if (threadIdx.x < 32) {
+		const double total = P.R > 1 ? peer_scalar_exchange_warp(P, mine) : mine;
+		if (threadIdx.x == 0) {
+			ss[0] = total;
+			s_accept = lm_decide_one(st, total, sig_sm, n, factor, x_min_diff);
 		}
-		s_accept = accept;
 	}
 	__syncthreads();
 	if (s_accept) for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xt[i];
@@ -848,8 +872,17 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 		while (done < iterations && !h.stopped) {
 			const int k = iterations - done < batch ? iterations - done : batch;
 			for (int it = 0; it < k; it++) {
-				PNOL_CHECK(lm_step_enqueue(ctx, f, xs, ddx.get(), n, J, F, Ftrial, 0.0, &st->lambda, jac_mode, 0, JTJ, W));
-				PNOL_LAUNCH(ctx, lm_decide_kernel, 1, 256, (size_t) n * sizeof(double), st, xs, W.xt, W.sigf, W.ss, n, lambda_factor, x_min_diff);
+				LmTail tail;
+				PNOL_CHECK(lm_step_enqueue(ctx, f, xs, ddx.get(), n, J, F, Ftrial, 0.0, &st->lambda, jac_mode, 0, JTJ, W, &tail));
+				if (tail.deferred) {
+					PeerScalarArgs pa;
+					if (tail.peer) pa = peer_scalar_next(ctx);
+					else { memset(&pa, 0, sizeof pa); }
+					PNOL_LAUNCH(ctx, lm_tail_kernel, 1, 1024, (size_t) n * sizeof(double), tail.partials, tail.np, pa, st, xs, W.xt, W.sigf, W.ss, n,
+					            lambda_factor, x_min_diff);
+				} else {
+					PNOL_LAUNCH(ctx, lm_decide_kernel, 1, 256, (size_t) n * sizeof(double), st, xs, W.xt, W.sigf, W.ss, n, lambda_factor, x_min_diff);
+				}
 				PNOL_LAUNCH(ctx, lm_commit_kernel, copy_grid, 256, 0, st, F, Ftrial, m);
 			}
 			PNOL_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, xs, ((size_t) n + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -61,7 +61,7 @@ struct pnol_ctx {
 	pnol::PnolPeer * peer = nullptr;   // NVLink peer-memory exchange of the sharded LM step (peer.cu)
 
 	// timers
-	bool timers_on = false;
+	int timers_on = 0;             // pnol_timer_enable: 0 off, 1 every scope, 2 the heavy kernels only (syrk, fd_jacobian, residual)
 	std::map<std::string, PnolTimerEntry> timers;
 };
 
@@ -194,6 +194,9 @@ class TimerScope {
 	TimerScope(pnol_ctx * ctx, const char * name) : ctx_(ctx)
 	{
 		if (!ctx->timers_on) return;
+		// mode 2: only the kernels that carry the step (an event pair costs about 5 us of stream time: seven scopes per LM iteration
+		// are 2 % of an iteration at 8 GPUs)
+		if (ctx->timers_on == 2 && strcmp(name, "syrk") != 0 && strcmp(name, "fd_jacobian") != 0 && strcmp(name, "residual") != 0) return;
 		cudaEventCreate(&a_); cudaEventCreate(&b_);
 		cudaEventRecord(a_, ctx->stream);
 		name_ = name; on_ = true;
@@ -264,16 +267,38 @@ int launch_alpha_pool(pnol_ctx * ctx, const pnol_functor * f, const double * xfu
                       const unsigned char * is_const, int nfull, const double * alpha, int npool, double dalpha,
                       const unsigned char * eval_ind, double * phi, double * dphi, int * bad_dev);
 
-int launch_residual(pnol_ctx * ctx, const pnol_functor * f, const double * x, int n, double * F, double * sumsq_dev);
+// sum of squares: deterministic, fixed 4096-row blocks -> partials -> one 1024-thread block (sumsq_final_sum). partials_out / np_out
+// (both): only the partials are produced and handed back, the caller's own kernel finishes with sumsq_final_sum
+int launch_residual(pnol_ctx * ctx, const pnol_functor * f, const double * x, int n, double * F, double * sumsq_dev,
+                    const double ** partials_out = nullptr, int * np_out = nullptr);
+
+// the final stage of the sum of squares, for a block of 1024 threads (red: 1024 doubles of shared memory); the result is returned
+// to every thread. One definition, so that every kernel that finishes the sum produces the same bits.
+__device__ __forceinline__ double sumsq_final_sum(const double * __restrict__ partials, int np, double * red)
+{
+	double s = 0;
+	for (int e = threadIdx.x; e < np; e += 1024) s = s + partials[e];
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 512; o > 0; o >>= 1) {
+		if (threadIdx.x < o) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + o];
+		__syncthreads();
+	}
+	return red[0];
+}
 int launch_fd_jacobian(pnol_ctx * ctx, const pnol_functor * f, const double * x, const double * dx, int n, double * J,
                        double * F, int mode, const double * Fw = nullptr, double * jtf_out = nullptr, bool * jtf_done = nullptr);
 
-int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed /* n*n + n */);
+// rhs_src (device, n; only looked at when F == nullptr): J^T F already summed by the caller -- copied behind J^T J by the finish kernel
+int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed /* n*n + n */,
+                const double * rhs_src = nullptr);
 int syrk_plan_selftest(long long m, int n, int sm_count, int with_f);
 int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs,
-                   const double * lambda_dev = nullptr);
+                   const double * lambda_dev = nullptr, bool rhs_behind_jtj = false /* JTJ holds n*n + n: -J^T F goes behind J^T J */);
 int launch_dgemm_nn(pnol_ctx * ctx, const double * A, const double * B, double * C, int M, int N, int K);
-int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev);
+// xbase / xtrial / step_out (all three or none): the kernel also writes step = x (NaN after a non-positive pivot) and xtrial = xbase + step
+int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev,
+                     const double * xbase = nullptr, double * xtrial = nullptr, double * step_out = nullptr);
 int launch_lu_inverse(pnol_ctx * ctx, const double * A, int n, double * Ainv, int * info_dev);
 int launch_matvec_neg(pnol_ctx * ctx, const double * D, const double * g, int n, double * p);
 int launch_hinv_rank2(pnol_ctx * ctx, double * D, const double * g, const double * s, int n);

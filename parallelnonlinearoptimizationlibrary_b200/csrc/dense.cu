@@ -20,7 +20,7 @@ __device__ __forceinline__ void ldg256_cached(const double * p, double (&v)[4])
 // a9: A = JTJ, A_ii = (1 + lambda) JTJ_ii ; rhs = -J^T F     (Source/LevenbergMarquardtMPI.cpp:66-85)
 // ---------------------------------------------------------------------------------------------------
 __global__ void lm_damp_kernel(const double * __restrict__ packed, int n, double lambda, const double * __restrict__ lambda_dev,
-                               double * __restrict__ JTJ, double * __restrict__ A, double * __restrict__ rhs)
+                               double * __restrict__ JTJ, double * __restrict__ A, double * __restrict__ rhs, int jtj_tail)
 {
 	long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	long long total = (long long) n * n;
@@ -32,16 +32,18 @@ __global__ void lm_damp_kernel(const double * __restrict__ packed, int n, double
 			int i = (int) (idx / n), j = (int) (idx - (long long) i * n);
 			A[idx] = (i == j) ? (1 + lambda) * v : v;
 		}
-	} else if (idx < total + n && rhs) {
-		rhs[idx - total] = -packed[idx];
+	} else if (idx < total + n) {
+		const double v = -packed[idx];
+		if (rhs) rhs[idx - total] = v;
+		if (jtj_tail && JTJ) JTJ[idx] = v;      // the LM step keeps the right-hand side behind J^T J (a re-damped step reuses it)
 	}
 }
 
 int launch_lm_damp(pnol_ctx * ctx, const double * packed, int n, double lambda, double * JTJ, double * A, double * rhs,
-                   const double * lambda_dev)
+                   const double * lambda_dev, bool rhs_behind_jtj)
 {
 	long long total = (long long) n * n + n;
-	PNOL_LAUNCH(ctx, lm_damp_kernel, (unsigned) ((total + 255) / 256), 256, 0, packed, n, lambda, lambda_dev, JTJ, A, rhs);
+	PNOL_LAUNCH(ctx, lm_damp_kernel, (unsigned) ((total + 255) / 256), 256, 0, packed, n, lambda, lambda_dev, JTJ, A, rhs, rhs_behind_jtj ? 1 : 0);
 	return PNOL_OK;
 }
 
@@ -229,9 +231,11 @@ constexpr int kPnP = kCholNB + 4;      // pitch of the staged panel: 8 rows x 4 
 
 __global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
 spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs, int n, double * __restrict__ W,
-                 double * __restrict__ x, int * __restrict__ info, int nbuf)
+                 double * __restrict__ x, int * __restrict__ info, int nbuf,
+                 const double * __restrict__ xbase, double * __restrict__ xtrial, double * __restrict__ step_out)
 {
 	extern __shared__ double sm[];
+	__shared__ int s_bad;
 	constexpr int P = kCholNB + 1;
 	double * LpT = sm;                              // 32 x 32: LpT[t * 32 + c] = L'[c][t], c > t (unit lower factor of the diagonal block)
 	double * Rsd = sm + kCholNB * kCholNB;          // 32: 1 / sqrt(d)
@@ -508,6 +512,19 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 			else if (kb > 0) backsub_stage(W, n, kb - kCholNB, kCholNB, Dd, Pd, pitch, async_ok, tid);
 		}
 		for (int i = tid; i < n; i += kCholThreads) x[i] = yv[i];
+		if (xtrial) {
+			// the LM trial point rides along (Source/LevenbergMarquardtMPI.cpp:97-100: X[i] = X[i] + sigma[i]). A non-positive pivot:
+			// the reference's luSolve would have produced inf / NaN and the step would be rejected by the NaN test of its chi^2 (:110);
+			// hand back a NaN step for the same outcome
+			if (tid == 0) s_bad = bad;
+			__syncthreads();
+			const int isbad = s_bad;
+			for (int i = tid; i < n; i += kCholThreads) {
+				const double s = isbad ? __longlong_as_double(0x7ff8000000000000LL) : yv[i];
+				step_out[i] = s;
+				xtrial[i] = xbase[i] + s;
+			}
+		}
 #ifdef PNOL_SOLVE_STAMPS
 		__syncthreads();
 		SOLVE_STAMP();
@@ -517,7 +534,8 @@ spd_solve_kernel(const double * __restrict__ A, const double * __restrict__ rhs,
 	}
 }
 
-int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev)
+int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n, double * x, int * info_dev,
+                     const double * xbase, double * xtrial, double * step_out)
 {
 	PNOL_REQUIRE(ctx, n >= 1 && n <= kCholMaxN, "spd_solve: n = %d outside [1, %d]", n, kCholMaxN);
 	TimerScope ts(ctx, "spd_solve");
@@ -533,7 +551,8 @@ int launch_spd_solve(pnol_ctx * ctx, const double * A, const double * rhs, int n
 	const size_t smem = doubles * sizeof(double);
 	PNOL_REQUIRE(ctx, smem <= ctx->smem_optin, "spd_solve: n = %d needs %zu bytes of shared memory", n, smem);
 	PNOL_CUDA(ctx, cudaFuncSetAttribute(spd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	PNOL_LAUNCH(ctx, spd_solve_kernel, kCholCluster, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev, nbuf);
+	if (!(xbase && xtrial && step_out)) { xbase = nullptr; xtrial = nullptr; step_out = nullptr; }
+	PNOL_LAUNCH(ctx, spd_solve_kernel, kCholCluster, kCholThreads, smem, A, rhs, n, (double *) ctx->ws[1], x, info_dev, nbuf, xbase, xtrial, step_out);
 	return PNOL_OK;
 }
 

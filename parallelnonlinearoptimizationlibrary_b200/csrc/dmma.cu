@@ -704,7 +704,7 @@ static PFN_encodeTiled tensor_map_encoder()
 __global__ void __launch_bounds__(256)
 syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __restrict__ part_rhs,
                    const int * __restrict__ role_slot0, const int * __restrict__ role_nslots, int n, int nb,
-                   double * __restrict__ packed)
+                   double * __restrict__ packed, const double * __restrict__ rhs_src)
 {
 	long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	long long total = (long long) n * n;
@@ -723,6 +723,8 @@ syrk_finish_kernel(const double * __restrict__ part_tiles, const double * __rest
 		}
 	} else if (idx < total + n) {
 		int p = (int) (idx - total);
+		// J^T F summed elsewhere (the structured Jacobian kernel): it only passes through, so that `packed` is complete after ONE launch
+		if (rhs_src) { packed[total + p] = rhs_src[p]; return; }
 		int b = p / kBT;
 		int role = b * (b + 1) / 2 + b;
 		const double * src = part_rhs + (size_t) role_slot0[role] * kBT + (p - b * kBT);
@@ -844,7 +846,7 @@ int syrk_plan_selftest(long long m, int n, int sm_count, int with_f)
 	return 0;
 }
 
-int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed)
+int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m, int n, double * packed, const double * rhs_src)
 {
 	PNOL_REQUIRE(ctx, n >= 1 && m >= 0, "syrk: bad shape m=%lld n=%d", m, n);
 	static const int no_f = [] { const char * e = getenv("PNOL_SYRK_NOF"); return e ? atoi(e) : 0; }();      // timing runs: J^T J only
@@ -956,7 +958,7 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 	unsigned char * ws = (unsigned char *) ctx->syrk_plan;
 	double * part_tiles = (double *) ctx->ws[0];
 	double * part_rhs = (double *) ((unsigned char *) ctx->ws[0] + bytes_tiles);
-	PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));
+	if (F || !rhs_src) PNOL_CUDA(ctx, cudaMemsetAsync(part_rhs, 0, bytes_rhs, ctx->stream));      // (nobody reads the slots when J^T F comes from rhs_src)
 
 	{
 		TimerScope ts(ctx, "syrk");
@@ -1016,7 +1018,7 @@ int launch_syrk(pnol_ctx * ctx, const double * J, const double * F, long long m,
 		TimerScope ts(ctx, "syrk_finish");
 		long long total = (long long) n * n + n;
 		PNOL_LAUNCH(ctx, syrk_finish_kernel, (unsigned) ((total + 255) / 256), 256, 0, part_tiles, part_rhs,
-		            (const int *) (ws + off_roles), (const int *) (ws + off_roles) + nroles, n, nb, packed);
+		            (const int *) (ws + off_roles), (const int *) (ws + off_roles) + nroles, n, nb, packed, F ? nullptr : rhs_src);
 	}
 	return PNOL_OK;
 }

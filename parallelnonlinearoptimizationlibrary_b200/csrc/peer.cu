@@ -15,16 +15,12 @@
 // peers never arrive reports PNOL_ERR_COMM instead of hanging the GPU. Without peer mappings (or PNOL_LM_PEER=0) the NCCL path is used.
 #include "common.cuh"
 #include "ga_common.cuh"      // comm_allgather_bytes_dev
+#include "peer.cuh"
 
 #include <stdlib.h>
 #include <vector>
 
 namespace pnol {
-
-constexpr int kPeerMax = 16;
-constexpr long long kPeerSpinLimit = 4000000000LL;      // clock cycles (about 2 s)
-
-struct PeerTable { double * base[kPeerMax]; };
 
 struct PnolPeer {
 	int R = 0, me = 0;
@@ -37,14 +33,6 @@ struct PnolPeer {
 	int * err_dev = nullptr;
 	bool ok = false, tried = false;
 };
-
-__device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long long * p) { return *(volatile const unsigned long long *) p; }
-__device__ __forceinline__ double ld_vol_f64(const double * p) { return *(volatile const double *) p; }
-__device__ __forceinline__ void st_release_sys(unsigned long long * p, unsigned long long v)
-{
-	__threadfence_system();
-	*(volatile unsigned long long *) p = v;
-}
 
 // J^T J | J^T F = sum over the ranks' partials (rank order), then A = J^T J with (1 + lambda) on the diagonal, rhs = -J^T F
 // (lm_damp_kernel of dense.cu, Source/LevenbergMarquardtMPI.cpp:66-85)
@@ -90,29 +78,10 @@ peer_reduce_damp_kernel(PeerTable T, int R, int me, size_t cap, int slot, unsign
 
 // ss[0] = sum over the ranks of their ss[0], rank order
 __global__ void __launch_bounds__(32)
-peer_scalar_sum_kernel(PeerTable T, int R, int me, size_t cap, int slot, unsigned long long epoch, double * __restrict__ ss, int * __restrict__ err)
+peer_scalar_sum_kernel(PeerScalarArgs P, double * __restrict__ ss)
 {
-	const int lane = threadIdx.x;
-	const size_t fl = 2 * cap + 2 * kPeerMax;                              // sc_flag, then sc_val
-	const double mine = ss[0];
-	bool bad = false;
-	double v = 0.0;
-	if (lane < R) {
-		double * pv = T.base[lane] + fl + 2 * kPeerMax + slot * kPeerMax + me;
-		*(volatile double *) pv = mine;
-		st_release_sys(reinterpret_cast<unsigned long long *>(T.base[lane] + fl) + slot * kPeerMax + me, epoch);
-		const unsigned long long * f = reinterpret_cast<const unsigned long long *>(T.base[me] + fl) + slot * kPeerMax + lane;
-		const long long t0 = clock64();
-		while (ld_vol_u64(f) < epoch) {
-			if (clock64() - t0 > kPeerSpinLimit) { bad = true; break; }
-			__nanosleep(64);
-		}
-		v = ld_vol_f64(T.base[me] + fl + 2 * kPeerMax + slot * kPeerMax + lane);
-	}
-	if (__any_sync(0xffffffffu, bad) && lane == 0) *err = 1;
-	double total = __shfl_sync(0xffffffffu, v, 0);
-	for (int r = 1; r < R; r++) total = total + __shfl_sync(0xffffffffu, v, r);
-	if (lane == 0) ss[0] = total;
+	const double total = peer_scalar_exchange_warp(P, ss[0]);
+	if (threadIdx.x == 0) ss[0] = total;
 }
 
 static void peer_teardown(PnolPeer * P)
@@ -220,11 +189,19 @@ int launch_peer_reduce_damp(pnol_ctx * ctx, int n, double lambda, const double *
 	return PNOL_OK;
 }
 
-int launch_peer_scalar_sum(pnol_ctx * ctx, double * ss)
+// the arguments of the NEXT scalar exchange (advances the epoch: the caller must launch exactly one kernel that performs it)
+PeerScalarArgs peer_scalar_next(pnol_ctx * ctx)
 {
 	PnolPeer * P = ctx->peer;
 	P->ep_sc++;
-	PNOL_LAUNCH(ctx, peer_scalar_sum_kernel, 1, 32, 0, P->table, P->R, P->me, P->cap, (int) (P->ep_sc & 1ULL), P->ep_sc, ss, P->err_dev);
+	PeerScalarArgs a;
+	a.T = P->table; a.R = P->R; a.me = P->me; a.slot = (int) (P->ep_sc & 1ULL); a.cap = P->cap; a.epoch = P->ep_sc; a.err = P->err_dev;
+	return a;
+}
+
+int launch_peer_scalar_sum(pnol_ctx * ctx, double * ss)
+{
+	PNOL_LAUNCH(ctx, peer_scalar_sum_kernel, 1, 32, 0, peer_scalar_next(ctx), ss);
 	return PNOL_OK;
 }
 
