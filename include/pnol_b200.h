@@ -77,6 +77,12 @@ int pnol_malloc(pnol_ctx * ctx, void ** dev_ptr, size_t bytes);
 int pnol_free(pnol_ctx * ctx, void * dev_ptr);
 int pnol_memcpy(pnol_ctx * ctx, void * dst, const void * src, size_t bytes);   /* any direction, stream ordered + sync */
 int pnol_memset(pnol_ctx * ctx, void * dev_ptr, int value, size_t bytes);
+/* A device -> host copy that runs BESIDE the work enqueued on the context's stream (copy streams of its own, driven by a worker
+ * thread): findMin reads F0 back while the iterations already run. dev_src must be complete when the call is made (synchronise
+ * first) and must not change, host_dst must not be touched, until pnol_copy_wait returns. One copy in flight per context (a second
+ * start, pnol_memcpy and pnol_ctx_destroy wait for it); small or pinned destinations are copied at once. */
+int pnol_copy_start(pnol_ctx * ctx, void * host_dst, const void * dev_src, size_t bytes);
+int pnol_copy_wait(pnol_ctx * ctx);
 int pnol_host_alloc(void ** host_ptr, size_t bytes);                          /* pinned host memory */
 int pnol_host_free(void * host_ptr);
 
@@ -277,6 +283,11 @@ int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const
 int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const double * dx, int n, double * J, double * F, double * Ftrial,
                     double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
                     int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out);
+
+/* What the last pnol_lm_iterate of this context ended with: *stopped_out != 0 when the stopping rule ||sigma||_2 < x_min_diff fired
+ * (Source/LevenbergMarquardtMPI.cpp:138-140 -- the reference leaves its loop there WITHOUT counting that pass in `iter`, so its
+ * iteration count is accepted + rejected - 1 in that case), *xdiff_out = ||sigma||_2 of the last accepted step (0 when none was). */
+int pnol_lm_last_run(pnol_ctx * ctx, int * stopped_out, double * xdiff_out);
 
 /* SURVEY.md 8(f) item 2 -- the normal equations without J in HBM: the rows are walked in blocks (512 MB of J per block by default,
  * $PNOL_FUSED_MB), each block's Jacobian is written to a scratch buffer, read back by the SYRK and its J^T J | J^T F added to the

@@ -91,6 +91,8 @@ int pnol_comm_allgather(pnol_ctx *, const double * send, double * recv, size_t n
 int pnol_malloc(pnol_ctx *, void ** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? PNOL_OK : PNOL_ERR_CUDA; }
 int pnol_free(pnol_ctx *, void * p) { std::free(p); return PNOL_OK; }
 int pnol_memcpy(pnol_ctx *, void * dst, const void * src, size_t bytes) { std::memmove(dst, src, bytes); return PNOL_OK; }
+int pnol_copy_start(pnol_ctx *, void * dst, const void * src, size_t bytes) { std::memmove(dst, src, bytes); return PNOL_OK; }      // (nothing runs beside the host here)
+int pnol_copy_wait(pnol_ctx *) { return PNOL_OK; }
 int pnol_memset(pnol_ctx *, void * p, int value, size_t bytes) { std::memset(p, value, bytes); return PNOL_OK; }
 
 int pnol_functor_create(pnol_ctx * ctx, const pnol_functor_desc * desc, pnol_functor ** out)
@@ -224,6 +226,53 @@ int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double * x, const
 	if (sigma_out) std::memcpy(sigma_out, sigma.data(), (size_t) n * sizeof(double));
 	if (x_trial_out) std::memcpy(x_trial_out, xt.data(), (size_t) n * sizeof(double));
 	if (spd_info_out) *spd_info_out = 0;
+	return PNOL_OK;
+}
+
+// the while loop of Source/LevenbergMarquardtMPI.cpp:55-141 behind one call (the product runs it on device-resident state with the
+// accept / reject rule in a kernel): here pnol_lm_step pass by pass plus the rule as the reference writes it
+static int g_lm_stopped = 0;
+static double g_lm_xdiff = 0.0;
+int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const double * dx, int n, double * J, double * F, double * Ftrial,
+                    double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
+                    int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out)
+{
+	if (f->d.kind < 100) return unavailable(ctx, "pnol_lm_iterate on a scalar functor");
+	const long long m = f->d.m;
+	std::vector<double> sigma(n), xt(n);
+	double lambda = *lambda_inout, chisq = *chisq_inout;
+	int acc = 0, rej = 0;
+	g_lm_stopped = 0;
+	g_lm_xdiff = 0.0;
+	for (int it = 0; it < iterations && !g_lm_stopped; it++) {
+		double ss = 0;
+		int info = 0;
+		int st = pnol_lm_step(ctx, f, x, dx, n, J, F, Ftrial, lambda, jac_mode, 0, JTJ, sigma.data(), xt.data(), &ss, &info);
+		if (st != PNOL_OK) return st;
+		const double root = std::sqrt(ss);
+		const double chi = root * root;                              // pow(vector2Norm(F),2)  (:108)
+		if (chi >= chisq || chi != chi) { lambda = lambda * lambda_factor; rej++; continue; }      // (:110-129)
+		lambda = lambda / lambda_factor;                             // (:132-141)
+		chisq = chi;
+		for (int i = 0; i < n; i++) x[i] = xt[i];
+		std::memcpy(F, Ftrial, (size_t) m * sizeof(double));
+		acc++;
+		double s2 = 0;
+		for (int i = 0; i < n; i++) s2 = s2 + sigma[i] * sigma[i];
+		g_lm_xdiff = std::sqrt(s2);
+		if (x_min_diff > 0 && g_lm_xdiff < x_min_diff) g_lm_stopped = 1;
+	}
+	*lambda_inout = lambda;
+	*chisq_inout = chisq;
+	if (accepted_out) *accepted_out = acc;
+	if (rejected_out) *rejected_out = rej;
+	if (swapped_out) *swapped_out = 0;
+	return PNOL_OK;
+}
+int pnol_lm_last_run(pnol_ctx *, int * stopped_out, double * xdiff_out)
+{
+	if (stopped_out) *stopped_out = g_lm_stopped;
+	if (xdiff_out) *xdiff_out = g_lm_xdiff;
 	return PNOL_OK;
 }
 

@@ -81,12 +81,12 @@ class GaStatus(C.Structure):
 # every symbol include/pnol_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "pnol_ctx_create", "pnol_ctx_destroy", "pnol_last_error", "pnol_ctx_device", "pnol_ctx_stream", "pnol_ctx_sync",
-    "pnol_ctx_sm_count", "pnol_ctx_launches", "pnol_version", "pnol_malloc", "pnol_free", "pnol_memcpy", "pnol_memset",
+    "pnol_ctx_sm_count", "pnol_ctx_launches", "pnol_version", "pnol_malloc", "pnol_free", "pnol_memcpy", "pnol_copy_start", "pnol_copy_wait", "pnol_memset",
     "pnol_host_alloc", "pnol_host_free", "pnol_comm_unique_id", "pnol_comm_init", "pnol_comm_rank", "pnol_comm_size",
     "pnol_comm_set_local", "pnol_comm_allreduce_sum", "pnol_comm_allgather", "pnol_comm_broadcast", "pnol_register_functor", "pnol_functor_registered", "pnol_functor_create",
     "pnol_functor_destroy", "pnol_functor_is_residual", "pnol_functor_rows", "pnol_eval_batch", "pnol_fd_gradient",
     "pnol_eval_recur", "pnol_fd_gradient_recur", "pnol_fd_hessian", "pnol_alpha_pool", "pnol_residual_eval",
-    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_normal_eq_fused", "pnol_spd_solve", "pnol_lu_inverse",
+    "pnol_fd_jacobian", "pnol_lm_normal_eq", "pnol_lm_damp", "pnol_lm_step", "pnol_lm_iterate", "pnol_lm_last_run", "pnol_lm_normal_eq_fused", "pnol_spd_solve", "pnol_lu_inverse",
     "pnol_matvec_neg", "pnol_bfgs_update_hinv", "pnol_dgemm_nn", "pnol_check_box_bounds", "pnol_compute_alpha_bnd",
     "pnol_stream_uniform", "pnol_ga_create", "pnol_ga_destroy", "pnol_ga_init", "pnol_ga_generation",
     "pnol_ga_status_get", "pnol_ga_set_sharding", "pnol_ga_peer_mode", "pnol_ga_get_population", "pnol_ga_get_indices", "pnol_ga_pop_sort", "pnol_ga_check_bounds",
@@ -437,6 +437,12 @@ class Context:
                                             C.byref(lam_c), C.byref(chi_c), C.c_double(factor), C.c_double(x_min_diff), int(iterations),
                                             int(jac_mode), C.byref(acc), C.byref(rej), C.byref(sw)))
         return x, lam_c.value, chi_c.value, acc.value, rej.value, sw.value
+
+    def lm_last_run(self):
+        """(stopped, xdiff2norm) of the last lm_iterate"""
+        st, xd = C.c_int(), C.c_double()
+        self.check(self.lib.pnol_lm_last_run(self.h, C.byref(st), C.byref(xd)))
+        return bool(st.value), xd.value
 
     def spd_solve(self, A, rhs, n, x=None):
         host = x is None

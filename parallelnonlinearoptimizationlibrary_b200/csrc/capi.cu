@@ -85,10 +85,13 @@ extern "C" int pnol_ctx_create(pnol_ctx ** out, int device)
 	return PNOL_OK;
 }
 
+static int bg_copy_join(pnol_ctx * ctx);
+
 extern "C" void pnol_ctx_destroy(pnol_ctx * ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	bg_copy_join(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	timers_collect(ctx);
 	comm_destroy(ctx);
@@ -147,7 +150,9 @@ constexpr size_t kStageChunk = (size_t) 4 << 20;
 constexpr int kStageMaxThreads = 8;
 // threads actually used: PNOL_COPY_THREADS (1..8), default 4
 static const int kStageThreads = [] { const char * e = getenv("PNOL_COPY_THREADS"); int t = e ? atoi(e) : 4; return t < 1 ? 1 : (t > kStageMaxThreads ? kStageMaxThreads : t); }();
-constexpr size_t kStageMinBytes = (size_t) 8 << 20;
+// copies from 1 MB on take this path; below 8 chunks of 4 MB the chunk shrinks so that every thread still gets two chunks to overlap
+// (a rank's data column at 8 GPUs is 4 MB: one chunk would be one thread's plain staged copy again)
+constexpr size_t kStageMinBytes = (size_t) 1 << 20;
 
 static bool is_pageable_host(const void * p)
 {
@@ -171,16 +176,19 @@ static int staged_copy(pnol_ctx * ctx, void * dst, const void * src, size_t byte
 {
 	PNOL_CHECK(stage_init(ctx));
 	cudaError_t errs[kStageMaxThreads];
-	auto worker = [&](int t) {
+	size_t chunk = (bytes + 2 * (size_t) kStageThreads - 1) / (2 * (size_t) kStageThreads);
+	chunk = (chunk + 65535) & ~(size_t) 65535;
+	if (chunk > kStageChunk) chunk = kStageChunk;
+	auto worker = [&, chunk](int t) {
 		cudaError_t e = cudaSetDevice(ctx->device);
 		unsigned char * pin = (unsigned char *) ctx->stage_pinned + (size_t) t * 2 * kStageChunk;
 		cudaStream_t st = ctx->stage_streams[t];
 		cudaEvent_t * ev = &ctx->stage_events[2 * t];
 		size_t prev_off = 0, prev_len = 0;
 		for (size_t i = 0; e == cudaSuccess; i++) {
-			const size_t off = ((size_t) t + i * kStageThreads) * kStageChunk;
+			const size_t off = ((size_t) t + i * kStageThreads) * chunk;
 			const bool have = off < bytes;
-			const size_t len = have ? (bytes - off < kStageChunk ? bytes - off : kStageChunk) : 0;
+			const size_t len = have ? (bytes - off < chunk ? bytes - off : chunk) : 0;
 			const int b = (int) (i & 1);
 			unsigned char * buf = pin + (size_t) b * kStageChunk;
 			if (h2d) {
@@ -214,10 +222,45 @@ static int staged_copy(pnol_ctx * ctx, void * dst, const void * src, size_t byte
 	return PNOL_OK;
 }
 
+// ---- a device -> host copy that runs BESIDE the context's stream (pnol_copy_start / pnol_copy_wait): a worker thread drives the
+// staged path above on the copy streams. The staging buffers have one user at a time: every other copy joins the worker first.
+int copy_now(pnol_ctx * ctx, void * dst, const void * src, size_t bytes);
+static int bg_copy_join(pnol_ctx * ctx)
+{
+	if (!ctx->bg_copy) return PNOL_OK;
+	ctx->bg_copy->join();
+	delete ctx->bg_copy;
+	ctx->bg_copy = nullptr;
+	const int st = ctx->bg_copy_status;
+	ctx->bg_copy_status = PNOL_OK;
+	return st;
+}
+
+extern "C" int pnol_copy_start(pnol_ctx * ctx, void * host_dst, const void * dev_src, size_t bytes)
+{
+	if (!ctx) return PNOL_ERR_INVALID;
+	PNOL_REQUIRE(ctx, host_dst && dev_src && is_device_ptr(dev_src) && !is_device_ptr(host_dst), "copy_start: device source and host destination expected");
+	PNOL_CHECK(bg_copy_join(ctx));
+	if (bytes < kStageMinBytes || !is_pageable_host(host_dst)) return copy_now(ctx, host_dst, dev_src, bytes);
+	PNOL_CHECK(stage_init(ctx));
+	ctx->bg_copy_status = PNOL_OK;
+	ctx->bg_copy = new std::thread([ctx, host_dst, dev_src, bytes] {
+		cudaSetDevice(ctx->device);
+		ctx->bg_copy_status = staged_copy(ctx, host_dst, dev_src, bytes, false);
+	});
+	return PNOL_OK;
+}
+extern "C" int pnol_copy_wait(pnol_ctx * ctx)
+{
+	if (!ctx) return PNOL_ERR_INVALID;
+	return bg_copy_join(ctx);
+}
+
 // host <-> device copy that is complete on return (any pointer kinds)
 int copy_now(pnol_ctx * ctx, void * dst, const void * src, size_t bytes)
 {
 	if (!bytes) return PNOL_OK;
+	PNOL_CHECK(bg_copy_join(ctx));
 	if (bytes >= kStageMinBytes) {
 		const bool dst_dev = is_device_ptr(dst), src_dev = is_device_ptr(src);
 		if (dst_dev != src_dev && is_pageable_host(dst_dev ? src : dst)) {
@@ -757,9 +800,11 @@ extern "C" int pnol_lm_step(pnol_ctx * ctx, const pnol_functor * f, const double
 // swapped pointers; kernels enqueued ahead cannot follow a pointer that is only known later).
 // ---------------------------------------------------------------------------------------------------
 struct LmDevState {
-	double lambda, chisq;
+	double lambda, chisq, xdiff;      // xdiff: ||sigma||_2 of the last accepted step
 	int accepted, rejected, stopped, last_accept;
 };
+constexpr int kLmStateDoubles = (int) (sizeof(LmDevState) / sizeof(double));
+static_assert(sizeof(LmDevState) % sizeof(double) == 0, "LmDevState travels as doubles behind x");
 
 // the rule itself, one thread: returns 1 when the step is accepted. `sum` = sum of the squared trial residuals over all rows
 __device__ __forceinline__ int lm_decide_one(LmDevState * st, double sum, const double * sig_sm, int n, double factor, double x_min_diff)
@@ -777,11 +822,11 @@ __device__ __forceinline__ int lm_decide_one(LmDevState * st, double sum, const 
 	st->chisq = chi;
 	st->accepted++;
 	st->last_accept = 1;
-	if (x_min_diff > 0) {
-		double s2 = 0;
-		for (int i = 0; i < n; i++) s2 = s2 + sig_sm[i] * sig_sm[i];      // vector2Norm: one sequential sum
-		if (sqrt(s2) < x_min_diff) st->stopped = 1;
-	}
+	double s2 = 0;
+	for (int i = 0; i < n; i++) s2 = s2 + sig_sm[i] * sig_sm[i];          // vector2Norm: one sequential sum
+	const double xd = sqrt(s2);
+	st->xdiff = xd;
+	if (x_min_diff > 0 && xd < x_min_diff) st->stopped = 1;              // (:138-140)
 	return 1;
 }
 
@@ -792,7 +837,7 @@ lm_decide_kernel(LmDevState * __restrict__ st, double * __restrict__ x, const do
 {
 	extern __shared__ double sig_sm[];
 	__shared__ int s_accept;
-	if (x_min_diff > 0) for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
+	for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
 	__syncthreads();
 	if (threadIdx.x == 0) s_accept = lm_decide_one(st, ss[0], sig_sm, n, factor, x_min_diff);
 	__syncthreads();
@@ -809,7 +854,7 @@ lm_tail_kernel(const double * __restrict__ partials, int np, const PeerScalarArg
 	extern __shared__ double sig_sm[];
 	__shared__ double red[1024];
 	__shared__ int s_accept;
-	if (x_min_diff > 0) for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
+	for (int i = threadIdx.x; i < n; i += blockDim.x) sig_sm[i] = sigma[i];
 	const double mine = sumsq_final_sum(partials, np, red);      // (ends in a barrier: sig_sm is complete as well)
 	if (threadIdx.x < 32) {
 		const double total = P.R > 1 ? peer_scalar_exchange_warp(P, mine) : mine;
@@ -854,15 +899,16 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 	double * xs = nullptr;
 	LmDevState * st = nullptr;
 	PNOL_CUDA(ctx, cudaMallocAsync((void **) &xs, ((size_t) n + 8) * sizeof(double), ctx->stream));
+	static_assert(kLmStateDoubles <= 8, "state block behind x");
 	st = (LmDevState *) (xs + n);
 	PNOL_CHECK(pinned_reserve(ctx, (size_t) n + 8));
 	LmDevState h0;
-	h0.lambda = *lambda_inout; h0.chisq = *chisq_inout; h0.accepted = 0; h0.rejected = 0; h0.stopped = 0; h0.last_accept = 0;
+	h0.lambda = *lambda_inout; h0.chisq = *chisq_inout; h0.xdiff = 0.0; h0.accepted = 0; h0.rejected = 0; h0.stopped = 0; h0.last_accept = 0;
 	int status = PNOL_OK;
 	auto body = [&]() -> int {
 		memcpy(ctx->pinned, x, (size_t) n * sizeof(double));
 		memcpy(ctx->pinned + n, &h0, sizeof h0);
-		PNOL_CUDA(ctx, cudaMemcpyAsync(xs, ctx->pinned, ((size_t) n + 4) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		PNOL_CUDA(ctx, cudaMemcpyAsync(xs, ctx->pinned, ((size_t) n + kLmStateDoubles) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		// without a stopping rule the whole run is enqueued at once; with one, in batches of four (a stop in the middle of a batch
 		// turns the rest of the batch into no-ops for X, F, lambda and chi^2)
 		const int batch = x_min_diff > 0 ? 4 : 64;
@@ -885,7 +931,7 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 				}
 				PNOL_LAUNCH(ctx, lm_commit_kernel, copy_grid, 256, 0, st, F, Ftrial, m);
 			}
-			PNOL_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, xs, ((size_t) n + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+			PNOL_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, xs, ((size_t) n + kLmStateDoubles) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 			PNOL_CHECK(finish(ctx));
 			PNOL_CHECK(peer_check(ctx));
 			memcpy(&h, ctx->pinned + n, sizeof h);
@@ -897,12 +943,24 @@ extern "C" int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * 
 		if (accepted_out) *accepted_out = h.accepted;
 		if (rejected_out) *rejected_out = h.rejected;
 		if (swapped_out) *swapped_out = 0;                           // accepted residuals are copied into F: they never end in Ftrial
+		ctx->lm_last_stopped = h.stopped;
+		ctx->lm_last_xdiff = h.xdiff;
 		return PNOL_OK;
 	};
+	ctx->lm_last_stopped = 0;
+	ctx->lm_last_xdiff = 0.0;
 	if (iterations > 0) status = body();
 	else { if (accepted_out) *accepted_out = 0; if (rejected_out) *rejected_out = 0; if (swapped_out) *swapped_out = 0; }
 	cudaFreeAsync(xs, ctx->stream);
 	return status;
+}
+
+extern "C" int pnol_lm_last_run(pnol_ctx * ctx, int * stopped_out, double * xdiff_out)
+{
+	if (!ctx) return PNOL_ERR_INVALID;
+	if (stopped_out) *stopped_out = ctx->lm_last_stopped;
+	if (xdiff_out) *xdiff_out = ctx->lm_last_xdiff;
+	return PNOL_OK;
 }
 
 // host-only: invariants of the SYRK's stream-K work plan for a shape (no device needed; see syrk_plan_selftest in dmma.cu)

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pnol_b200.h"
@@ -41,6 +42,9 @@ struct pnol_ctx {
 	cudaStream_t stage_streams[8] = {};
 	cudaEvent_t stage_events[16] = {};
 
+	std::thread * bg_copy = nullptr;       // pnol_copy_start: the worker of a device -> host copy in flight (one at a time)
+	int bg_copy_status = 0;
+
 	// SYRK work plan of the last (m, n) shape (device copy of the descriptor tables; see launch_syrk)
 	void * syrk_plan = nullptr;
 	size_t syrk_plan_bytes = 0;
@@ -56,6 +60,10 @@ struct pnol_ctx {
 	bool local = false;
 	int comm_rank = 0;
 	int comm_nranks = 1;
+
+	// what the last pnol_lm_iterate left behind (pnol_lm_last_run)
+	int lm_last_stopped = 0;
+	double lm_last_xdiff = 0.0;
 
 	int ga_sharding = 0;           // pnol_ga_set_sharding: 0 auto, 1 rows, 2 sweep
 	pnol::PnolPeer * peer = nullptr;   // NVLink peer-memory exchange of the sharded LM step (peer.cu)

@@ -36,10 +36,24 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 	vector <double> Xprev( Nparam, 0 ), Xtrial( Nparam, 0 );
 	dXdev.upload( dX.data(), Nparam );
 
+	// whether the while loop runs on device-resident state (see below)
+	const bool deviceLoop = verbose < 1 && !rt.jacobianCache() && maxIter > 0;
+
 	// Initial f values (:42-49)
 	double sumsq = 0;
 	rt.check( pnol_residual_eval( ctx, f, X.data(), Nparam, F.data(), &sumsq ) );
-	F.download( F0.data(), Ndata );
+	// F0 goes back to the host; with the device loop the read-back runs beside the iterations (from a copy: F changes with the
+	// first accepted step), and findMin waits for it before it returns -- also when it leaves through an exception
+	DeviceArray F0dev( deviceLoop ? (size_t) Ndata : 0 );
+	struct CopyGuard { pnol_ctx * c; bool on; ~CopyGuard() { if( on ) pnol_copy_wait( c ); } } f0Guard{ ctx, false };
+	if( deviceLoop )
+	{
+		rt.check( pnol_memcpy( ctx, F0dev.data(), F.data(), (size_t) Ndata*sizeof(double) ) );
+		rt.check( pnol_copy_start( ctx, F0.data(), F0dev.data(), (size_t) Ndata*sizeof(double) ) );
+		f0Guard.on = true;
+	}
+	else
+		F.download( F0.data(), Ndata );
 	for( int k = 0; k < Nparam; k++ ) Xprev[k] = X[k];
 	chiSq = pow( sqrt(sumsq), 2 );                               // pow(vector2Norm(F),2)  (:51)
 
@@ -47,6 +61,28 @@ void lmFindMin( MultiObjective * mObjPtr, double lambda0, double lambdaFactor, d
 	double xdiff2Norm = xMinDiff*2;
 	bool jacobianCurrent = false;      // J^T J is unchanged after a rejected step (X was restored): SURVEY.md 3.1
 	report = LMReport();
+
+	// Nobody watches the iterations (verbose < 1) and J is recomputed in every pass as in the reference (jacobianCache off): the whole
+	// while loop (:55-141) runs on device-resident state, accept / reject rule included (pnol_lm_iterate: same arithmetic, same
+	// decisions, X / lambda / chi^2 bit for bit those of the loop below -- tests/test_gpu_host_api.py), with one synchronisation per
+	// batch of iterations instead of one per iteration.
+	if( deviceLoop )
+	{
+		int accepted = 0, rejected = 0, swapped = 0, stopped = 0;
+		double xdiff = 0;
+		rt.check( pnol_lm_iterate( ctx, f, X.data(), dXdev.data(), Nparam, rt.storeJacobian() ? J.data() : nullptr, F.data(), Ftrial.data(),
+				JTJ.data(), &lambda, &chiSq, lambdaFactor, xMinDiff, maxIter, rt.jacobianMode(), &accepted, &rejected, &swapped ) );
+		rt.check( pnol_lm_last_run( ctx, &stopped, &xdiff ) );
+		if( swapped ) F.swap( Ftrial );
+		report.accepted = accepted;
+		report.rejected = rejected;
+		if( accepted > 0 ) xdiff2Norm = xdiff;
+		iter = accepted + rejected - ( stopped ? 1 : 0 );            // the pass that meets the stopping rule leaves through `break` (:138-140)
+		maxIter = 0;                                                 // (skips the host loop below)
+		f0Guard.on = false;
+		rt.check( pnol_copy_wait( ctx ) );                           // F0 has landed
+	}
+
 	while( iter < maxIter )
 	{
 		// Gradient, normal equations, damped solve, parameter update and the trial residuals (:60-103) are one device call with

@@ -79,6 +79,30 @@ def test_levmarq_iterates(host, K, serial):
     assert np.array_equal(r2["X"], r["X"])
 
 
+@pytest.mark.parametrize("xmindiff", [0.0, 1e-3, 1e-7])
+def test_levmarq_device_loop_equals_host_loop(host, xmindiff):
+    # jacobianCache off + verbose < 1: findMin runs its while loop on device-resident state (pnol_lm_iterate, accept / reject on the
+    # device); otherwise pass by pass with the decision on the host. Same arithmetic, same decisions: every number of the report must
+    # agree, bit for bit -- also when the stopping rule (Source/LevenbergMarquardtMPI.cpp:138-140) ends the run in the middle of a
+    # device batch, and the pass that meets it is not counted in `iterations` (the reference leaves through `break`)
+    c = "lm_lorentz_K16"
+    args = (g(c, "t"), g(c, "y"), float(g(c, "w")), g(c, "x0"), 0.001, 10.0, 1e-7, 25, xmindiff)
+    on_host = host.lm_lorentz(*args)
+    host.set_jacobian_cache(False)
+    try:
+        on_device = host.lm_lorentz(*args)
+    finally:
+        host.set_jacobian_cache(True)
+    for k in ("iterations", "accepted", "rejected", "chiSq", "lam", "xdiff2Norm"):
+        assert on_device[k] == on_host[k], k
+    for k in ("X", "F0", "F"):
+        assert np.array_equal(on_device[k], on_host[k]), k
+    if xmindiff == 1e-3:
+        assert on_host["iterations"] < 24 and on_host["iterations"] == on_host["accepted"] + on_host["rejected"] - 1      # it did stop early
+    if xmindiff == 0.0:
+        assert on_host["iterations"] == 25
+
+
 def test_levmarq_reference_examples(host):
     # testLMCubicLinearCoef (Source/Examples.cpp:415-450): linear problem, same data bits as the reference class
     r = host.lm_example("cubic", np.full(4, 0.1))

@@ -137,11 +137,14 @@ def test_simplex_search_bit_for_bit(hl):
 @pytest.mark.parametrize("case", ["lm_lorentz_K8", "lm_lorentz_K16"])
 @pytest.mark.parametrize("serial", [0, 1])
 @pytest.mark.parametrize("store_j", [1, 0])
-def test_levenberg_marquardt_bit_for_bit(hl, case, serial, store_j):
+@pytest.mark.parametrize("whole_loop_call", [0, 1])
+def test_levenberg_marquardt_bit_for_bit(hl, case, serial, store_j, whole_loop_call):
     # LevMarqMPI / LevMarq::findMin (accept / reject, damping, stop rule on the host; residuals, FD Jacobian, normal equations and solve
-    # behind pnol_residual_eval / pnol_lm_step), with a J buffer and without one (Runtime::setStoreJacobian(false))
+    # behind pnol_residual_eval / pnol_lm_step), with a J buffer and without one (Runtime::setStoreJacobian(false)); whole_loop_call:
+    # with the Jacobian cache off findMin hands its while loop to pnol_lm_iterate in one call
     t, y, w, x0, iters = g(case, "t"), g(case, "y"), float(g(case, "w")), g(case, "x0"), int(g(case, "iters"))
     hl.pnolhost_set_store_jacobian(store_j)
+    hl.pnolhost_set_jacobian_cache(0 if whole_loop_call else 1)
     try:
         X = x0.copy()
         m = t.size
@@ -150,6 +153,7 @@ def test_levenberg_marquardt_bit_for_bit(hl, case, serial, store_j):
                                     C.c_double(1e-7), C.c_double(iters), C.c_double(0.0), serial, _p(F0), _p(F), _p(rep))
     finally:
         hl.pnolhost_set_store_jacobian(1)
+        hl.pnolhost_set_jacobian_cache(1)
     assert st == 0, hl.pnolhost_last_error()
     assert np.array_equal(X, g(case, "X")) and np.array_equal(F0, g(case, "F0")) and np.array_equal(F, g(case, "F"))
     assert int(rep[0]) == iters and int(rep[1]) + int(rep[2]) == iters          # iterations = accepted + rejected
