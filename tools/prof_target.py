@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: LM iterations (pnol_lm_step) + one stand-alone normal-equation assembly at the cfg5 shape, one 1M x 32
+"""Small fixed workload for ncu: one LM iteration on device-resident state (pnol_lm_iterate) + one stand-alone normal-equation assembly at the cfg5 shape, one 1M x 32
 Rastrigin sweep, the dense BFGS kernels at n = 4096 (p = -D g, rank-2 update), the damped solve at n = 256 and one GA generation at
 1M x 32. Run plain first, then under ncu (see profiles/README.md). Everything is warmed up first; the part to be captured sits between
 cuProfilerStart / cuProfilerStop (ncu --profile-from-start off)."""
@@ -20,10 +20,12 @@ n = pr["n"]
 f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
 Jd, Fd, Ft, JTJd = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
 dx = np.full(n, 1e-7)
-ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+_, ss0 = ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+chi0 = float(np.sqrt(ss0) ** 2)
 # ---- warm-up of everything that will be captured ----
 for _ in range(2):
-    ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-3, JTJd)
+    ctx.lm_iterate(f, pr["x0"].copy(), dx, n, Jd, Fd, Ft, JTJd, 1e-3, chi0, 10.0, 1)
+    ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
 A, rhs = ctx.malloc(n * n * 8), ctx.malloc(n * 8)
 ctx.lm_normal_eq(Jd, Fd, m, n, 1e-3, A=A, rhs=rhs)
 B, nd = 1_000_000, 32
@@ -54,8 +56,9 @@ ctx.sync()
 # ---- the captured part: one of each ----
 cuda = ctypes.CDLL("libcuda.so.1")
 cuda.cuProfilerStart()
-# one LM iteration as the LM classes and bench.py run it (Jacobian + J^T F, SYRK, damped solve, trial residual) ...
-ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-3, JTJd)
+# one LM iteration as the LM classes and bench.py run it (pnol_lm_iterate: Jacobian + J^T F, SYRK, damping, solve + trial point, trial
+# residual, tail kernel = sum of squares + accept / reject, commit of F) ...
+ctx.lm_iterate(f, pr["x0"].copy(), dx, n, Jd, Fd, Ft, JTJd, 1e-3, chi0, 10.0, 1)
 # ... and the stand-alone normal-equation call on a given (J, F): the SYRK sums J^T F itself (extra tensor tiles)
 ctx.lm_normal_eq(Jd, Fd, m, n, 1e-3, A=A, rhs=rhs)
 ctx.eval_batch(fr, pts, B, nd, f_out=fo)
