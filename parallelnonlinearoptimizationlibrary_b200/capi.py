@@ -234,6 +234,13 @@ class Context:
     def memcpy(self, dst, src, nbytes):
         self.check(self.lib.pnol_memcpy(self.h, _ptr(dst), _ptr(src), C.c_size_t(nbytes)))
 
+    def copy_start(self, dst_host, src_dev, nbytes):
+        """device -> host copy that runs beside the context's stream; dst_host must stay alive and untouched until copy_wait()"""
+        self.check(self.lib.pnol_copy_start(self.h, _ptr(dst_host), _ptr(src_dev), C.c_size_t(nbytes)))
+
+    def copy_wait(self):
+        self.check(self.lib.pnol_copy_wait(self.h))
+
     def to_device(self, arr):
         arr = np.ascontiguousarray(arr)
         p = self.malloc(arr.nbytes)

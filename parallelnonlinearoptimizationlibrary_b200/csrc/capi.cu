@@ -239,8 +239,9 @@ static int bg_copy_join(pnol_ctx * ctx)
 extern "C" int pnol_copy_start(pnol_ctx * ctx, void * host_dst, const void * dev_src, size_t bytes)
 {
 	if (!ctx) return PNOL_ERR_INVALID;
-	PNOL_REQUIRE(ctx, host_dst && dev_src && is_device_ptr(dev_src) && !is_device_ptr(host_dst), "copy_start: device source and host destination expected");
 	PNOL_CHECK(bg_copy_join(ctx));
+	if (!bytes) return PNOL_OK;
+	PNOL_REQUIRE(ctx, host_dst && dev_src && is_device_ptr(dev_src) && !is_device_ptr(host_dst), "copy_start: device source and host destination expected");
 	if (bytes < kStageMinBytes || !is_pageable_host(host_dst)) return copy_now(ctx, host_dst, dev_src, bytes);
 	PNOL_CHECK(stage_init(ctx));
 	ctx->bg_copy_status = PNOL_OK;

@@ -173,3 +173,38 @@ def test_large_pageable_copies_round_trip(ctx):
         b = ctx.to_host(p, a.shape, dtype=np.int64)
         assert np.array_equal(a, b)
         ctx.free(p)
+
+
+@pytest.mark.parametrize("count", [0, 1000, 1 << 17, (1 << 21) + 12345])
+def test_copy_beside_the_stream(ctx, count):
+    # pnol_copy_start / pnol_copy_wait (findMin's F0 read-back beside the iterations): small copies complete at once, from 1 MB on a
+    # worker thread drives the staged copy while the context's stream works; every other copy waits for the one in flight
+    src = np.random.default_rng(count).normal(size=count)
+    dev = ctx.to_device(src) if count else ctx.malloc(8)
+    dst = np.zeros(count)
+    f = ctx.functor(capi.F_RASTRIGIN)
+    pts = np.random.default_rng(1).uniform(-5.12, 5.12, size=(4096, 32))
+    ctx.copy_start(dst, dev, dst.nbytes)
+    got = ctx.eval_batch(f, pts, 4096, 32)                      # work on the context's stream meanwhile (its own small copies join the worker)
+    ctx.copy_wait()
+    assert np.array_equal(dst, src)
+    assert np.array_equal(got, O.eval_batch(O.OFunctor(capi.F_RASTRIGIN), pts))
+    ctx.copy_wait()                                            # nothing in flight: a no-op
+    ctx.free(dev)
+
+
+def test_timer_modes(ctx):
+    # pnol_timer_enable: 0 off, 1 every scope, 2 the kernels that carry an LM iteration only (what bench.py's timed region uses)
+    pr = problems.lorentz_problem(2048, 8)
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), pr["m"])
+    for mode, want_sumsq in ((1, True), (2, False), (0, None)):
+        ctx.timer_enable(mode)
+        ctx.timer_reset()
+        ctx.residual_eval(f, pr["x0"], n=pr["n"])
+        _, c_res = ctx.timer_get("residual")
+        _, c_ss = ctx.timer_get("sumsq")
+        ctx.timer_enable(False)
+        if mode == 0:
+            assert c_res == 0 and c_ss == 0
+        else:
+            assert c_res == 1 and (c_ss == 1) == want_sumsq

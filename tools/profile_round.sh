@@ -13,3 +13,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/${R}_prof_target \
     python tools/prof_target.py > gpurun_out/${R}_prof_target_ncu.log 2>&1 || true
 tail -2 gpurun_out/${R}_prof_target_ncu.log
+# reduce on the box (gpurun brings back at most 64 MiB): the summary always, the report itself only when it is small enough
+python tools/ncu_summary.py gpurun_out/${R}_prof_target.ncu-rep gpurun_out/${R}_ncu_summary.json > /dev/null
+ncu -i gpurun_out/${R}_prof_target.ncu-rep --page raw --csv | gzip -9 > gpurun_out/${R}_prof_target_raw.csv.gz
+if [ $(stat -c %s gpurun_out/${R}_prof_target.ncu-rep) -gt 40000000 ]; then rm gpurun_out/${R}_prof_target.ncu-rep; fi
+du -sh gpurun_out
