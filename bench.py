@@ -686,7 +686,9 @@ def run_ours(args):
                                    "Jacobian row-sharded over %d GPU(s), packed J^T J|J^T r all-reduce" % (m_total, n, world),
                        "m": m_total, "n": n, "rows_per_gpu": m_loc, "parallelism": "rows/%d" % world, "restart_every": args.restart,
                        "l2": "inputs exceed L2 (J is %.2f GB per GPU, streamed every step)" % (m_loc * n * 8 / 1e9),
-                       "jacobian_cache": False, "accepted_steps": accepted, "rejected_steps": rejected},
+                       "jacobian_cache": False, "accepted_steps": accepted, "rejected_steps": rejected,
+                       "lm_exchange": {0: "one rank", 1: "NVLink peer memory inside the step's kernels (csrc/peer.cu)", 2: "NCCL all-reduce"}.get(
+                           ctx.lm_exchange_mode(), "undecided")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "LevMarqMPI::findMin (host C++ mirror of Source/LevenbergMarquardtMPI.hpp) over pageable host vectors",
                     "calls": calls, "iterations_per_call": e2e_chunk},

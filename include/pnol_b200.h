@@ -284,6 +284,11 @@ int pnol_lm_iterate(pnol_ctx * ctx, const pnol_functor * f, double * x, const do
                     double * JTJ, double * lambda_inout, double * chisq_inout, double lambda_factor, double x_min_diff, int iterations,
                     int jac_mode, int * accepted_out, int * rejected_out, int * swapped_out);
 
+/* Which way the sums of the row-sharded LM step (J^T J | J^T F and the trial chi^2, Source/LevenbergMarquardtMPI.cpp:60-108) travel on
+ * this context: 0 one rank, 1 NVLink peer memory inside the step's own kernels (csrc/peer.cu), 2 NCCL all-reduce (a peer mapping
+ * failed, or PNOL_LM_PEER=0), -1 not decided yet (the first sharded pnol_lm_step / pnol_lm_iterate decides, collectively). */
+int pnol_lm_exchange_mode(pnol_ctx * ctx);
+
 /* What the last pnol_lm_iterate of this context ended with: *stopped_out != 0 when the stopping rule ||sigma||_2 < x_min_diff fired
  * (Source/LevenbergMarquardtMPI.cpp:138-140 -- the reference leaves its loop there WITHOUT counting that pass in `iter`, so its
  * iteration count is accepted + rejected - 1 in that case), *xdiff_out = ||sigma||_2 of the last accepted step (0 when none was). */

@@ -205,6 +205,23 @@ int launch_peer_scalar_sum(pnol_ctx * ctx, double * ss)
 	return PNOL_OK;
 }
 
+} // namespace pnol
+
+// which way the sharded LM step's sums travel on this context: 0 one rank (no exchange), 1 NVLink peer memory (the fused kernels
+// above), 2 NCCL all-reduce, -1 not decided yet (the decision is taken collectively by the first sharded pnol_lm_step / pnol_lm_iterate)
+extern "C" int pnol_lm_exchange_mode(pnol_ctx * ctx)
+{
+	if (!ctx) return -1;
+	if (ctx->nranks <= 1) return 0;
+	const pnol::PnolPeer * P = ctx->peer;
+	if (P && P->ok) return 1;
+	if (P && P->tried) return 2;
+	static const bool disabled = [] { const char * e = getenv("PNOL_LM_PEER"); return e && atoi(e) == 0; }();
+	return disabled ? 2 : -1;
+}
+
+namespace pnol {
+
 // after a synchronisation: did a kernel of this context give up waiting for its peers?
 int peer_check(pnol_ctx * ctx)
 {

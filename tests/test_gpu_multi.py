@@ -84,7 +84,7 @@ def _worker(rank, world, port, out_dir, shard):
     r = hostapi.lm_lorentz(pr["t"][lo:hi], pr["y"][lo:hi], pr["w"], pr["x0"], 0.001, 10.0, 1e-7, int(GB["lm_K128/maxiter"]), 0.0)
     np.save(os.path.join(out_dir, "XK128_%d.npy" % rank), r["X"])
     np.save(os.path.join(out_dir, "F0K128_%d.npy" % rank), r["F0"])
-    np.save(os.path.join(out_dir, "repK128_%d.npy" % rank), np.array([r["iterations"], r["lam"]]))
+    np.save(os.path.join(out_dir, "repK128_%d.npy" % rank), np.array([r["iterations"], r["lam"], ctx.lm_exchange_mode()]))
     # GA with the generation sharded over the ranks: bit-exact like the single-GPU run
     c = "ga_rastrigin"
     hostapi.set_stream(seed=int(G[c + "/seed"]), scale=float(G[c + "/scale"]))
@@ -120,14 +120,17 @@ def _worker(rank, world, port, out_dir, shard):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shard,no_ipc", [(2, 1, 0), (2, 1, 1), (2, 2, 0), (4, 1, 0), (8, 1, 0), (8, 1, 1), (8, 2, 0)])
-def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, monkeypatch):
+@pytest.mark.parametrize("world,shard,no_ipc,lm_peer", [(2, 1, 0, 1), (2, 1, 1, 1), (2, 2, 0, 0), (4, 1, 0, 1), (4, 2, 0, 0), (8, 1, 0, 1), (8, 1, 1, 0),
+                                                        (8, 2, 0, 1)])
+def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, lm_peer, monkeypatch):
     """shard = 1: GA rows sharded over the ranks (no_ipc = 1: through replicas + all-gather, PNOL_GA_NO_IPC=1, instead of CUDA IPC
-    peer mappings); shard = 2: GA rows replicated, fitness sweep sharded"""
+    peer mappings); shard = 2: GA rows replicated, fitness sweep sharded; lm_peer = 0: the LM step's sums through NCCL
+    (PNOL_LM_PEER=0) instead of the fused peer-memory kernels"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     monkeypatch.setenv("PNOL_GA_NO_IPC", str(no_ipc))
+    monkeypatch.setenv("PNOL_LM_PEER", str(lm_peer))
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shard), nprocs=world, join=True)
     modes = {int(np.load(tmp_path / ("peer_mode_%d.npy" % r))[0]) for r in range(world)}
     assert len(modes) == 1, "every rank takes the same path"
@@ -144,6 +147,9 @@ def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, monke
         assert np.array_equal(F0, F0w)
     rep = np.load(tmp_path / "repK128_0.npy")
     assert int(rep[0]) == int(GB["lm_K128/iters"]) and rep[1] == float(GB["lm_K128/lam"])
+    modes_lm = {int(np.load(tmp_path / ("repK128_%d.npy" % r))[2]) for r in range(world)}
+    assert modes_lm == ({2} if lm_peer == 0 else modes_lm) and len(modes_lm) == 1 and modes_lm <= {1, 2}, "LM exchange path: %s" % modes_lm
+    print("LM exchange mode at world %d: %s" % (world, modes_lm))
     gas = [np.load(tmp_path / ("gaX_%d.npy" % r)) for r in range(world)]
     for r in range(1, world):
         assert np.array_equal(gas[0], gas[r]), "default-stream GA: ranks disagree"
