@@ -590,27 +590,29 @@ def run_ours(args):
         gas2.close()
         gas.close()
         if world > 1:
-            # the other way of splitting a generation, for the record (include/pnol_b200.h, pnol_ga_set_sharding): the default at this
-            # size keeps the rows on every GPU and splits the sweep; "rows" shards the population itself (parents read over NVLink)
+            # the other ways of splitting a generation, for the record (include/pnol_b200.h, pnol_ga_set_sharding): the default (auto) at
+            # this size is replicas -- the 0.057 ms sweep does not pay for an all-gather of its 8 MB of values (peer_mode 4); "sweep"
+            # splits the sweep and all-gathers F as the reference does (3), "rows" shards the population itself (parents over NVLink; 1)
             modes = {"default": {"peer_mode": ga["peer_mode"], "ms_per_generation": gen_ms}}
-            try:
-                ctx.ga_set_sharding(1)
-                gas3 = ctx.ga_create(fr, 32, np.full(32, -5.12), np.full(32, 5.12), npop, gens + 2, dict(seed=GA_SHAPE["seed"], scale=GA_SHAPE["scale"]), nstatic=1e9)
-                gas3.init(np.full(32, GA_SHAPE["x0"]))
-                gas3.generation()
-                sync_all()
-                g0.record(stream)
-                for _ in range(gens):
+            for label, shard_mode in (("rows_sharded", 1), ("sweep_sharded", 2)):
+                try:
+                    ctx.ga_set_sharding(shard_mode)
+                    gas3 = ctx.ga_create(fr, 32, np.full(32, -5.12), np.full(32, 5.12), npop, gens + 2, dict(seed=GA_SHAPE["seed"], scale=GA_SHAPE["scale"]), nstatic=1e9)
+                    gas3.init(np.full(32, GA_SHAPE["x0"]))
                     gas3.generation()
-                g1.record(stream)
-                sync_all()
-                ms3 = launch.max_over_ranks(g0.elapsed_time(g1)) / gens
-                _, F3 = gas3.population()
-                modes["rows_sharded"] = {"peer_mode": gas3.peer_mode(), "ms_per_generation": ms3,
-                                         "same_fingerprint": bool(ga_fingerprint(F3, gas3.status().stream_pos) == fp)}
-                gas3.close()
-            except Exception as e:
-                modes["rows_sharded"] = {"error": repr(e)}
+                    sync_all()
+                    g0.record(stream)
+                    for _ in range(gens):
+                        gas3.generation()
+                    g1.record(stream)
+                    sync_all()
+                    ms3 = launch.max_over_ranks(g0.elapsed_time(g1)) / gens
+                    _, F3 = gas3.population()
+                    modes[label] = {"peer_mode": gas3.peer_mode(), "ms_per_generation": ms3,
+                                    "same_fingerprint": bool(ga_fingerprint(F3, gas3.status().stream_pos) == fp)}
+                    gas3.close()
+                except Exception as e:
+                    modes[label] = {"error": repr(e)}
             ctx.ga_set_sharding(0)
             ga["sharding_modes"] = modes
 

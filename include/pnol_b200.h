@@ -27,7 +27,7 @@
  *   PNOL_COPY_THREADS=k   host threads of the staged pageable <-> device copies (1..8, default 4)
  *   PNOL_FUSED_MB=x       MB of J per row block of pnol_lm_normal_eq_fused / J == NULL steps (read per call, default 512)
  *   PNOL_GA_LEGACY=1      genetic algorithm with the stage-by-stage generation of round 1 instead of the fused pipeline
- *   PNOL_GA_SHARD=rows|sweep   overrides pnol_ga_set_sharding
+ *   PNOL_GA_SHARD=rows|sweep|none   overrides pnol_ga_set_sharding
  *   PNOL_GA_NO_IPC=1      several GPUs: population replicas + all-gather instead of peer mappings (A/B runs, boxes without IPC)
  *   PNOL_GA_SORT=radix    GA popSort with the cooperative radix kernel only (default: splitter buckets in front of it; read per pnol_ga_create)
  *   PNOL_LM_PEER=0        several GPUs: the LM step's two sums through NCCL instead of the fused peer-memory kernels (csrc/peer.cu)
@@ -386,12 +386,16 @@ int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * st);
  *                        unavailable); row hashes / box counts and objective values are all-gathered. Memory per GPU ~ 1 / ranks.
  *   PNOL_GA_SHARD_SWEEP  every rank keeps the population and makes all children; the fitness sweep is split and the objective values
  *                        are all-gathered (the reference's evaluatePopulationParallel, Source/GeneticAlgorithmMPI.cpp:283-414).
- *   PNOL_GA_SHARD_AUTO   sweep while the population fits one GPU comfortably, rows beyond (default).
+ *   PNOL_GA_SHARD_NONE   replicas: every rank keeps the population, makes all children and sweeps all of them -- no collective. For a
+ *                        cheap objective the split sweep does not pay for its all-gather (1M x 32 Rastrigin: the whole sweep 0.057 ms,
+ *                        the all-gather of the 8 MB of objective values 0.06 - 0.17 ms at 2 - 8 GPUs).
+ *   PNOL_GA_SHARD_AUTO   (default) rows when the population does not fit one GPU comfortably; otherwise sweep when the share of the
+ *                        sweep the other ranks take over costs more than the all-gather (always for user functors), else none.
  * Results are bit-identical in every mode and at every rank count. */
-enum { PNOL_GA_SHARD_AUTO = 0, PNOL_GA_SHARD_ROWS = 1, PNOL_GA_SHARD_SWEEP = 2 };
+enum { PNOL_GA_SHARD_AUTO = 0, PNOL_GA_SHARD_ROWS = 1, PNOL_GA_SHARD_SWEEP = 2, PNOL_GA_SHARD_NONE = 3 };
 int pnol_ga_set_sharding(pnol_ctx * ctx, int mode);
 /* what a GA object does: 0 one rank (or the stage-by-stage generation), 1 rows sharded + peer mappings, 2 rows sharded + replicas
- * (peer mappings unavailable, or PNOL_GA_NO_IPC=1), 3 rows replicated + sweep sharded */
+ * (peer mappings unavailable, or PNOL_GA_NO_IPC=1), 3 rows replicated + sweep sharded, 4 replicas (no collective) */
 int pnol_ga_peer_mode(pnol_ga * ga);
 /* sorted population (npop x n) and objective values; either may be NULL */
 int pnol_ga_get_population(pnol_ga * ga, double * xpop, double * F);

@@ -510,7 +510,7 @@ class Context:
         return GA(self, h, int(npop), int(n), keep, f)
 
     def ga_set_sharding(self, mode):
-        """0 auto, 1 rows sharded over the ranks, 2 rows replicated + sweep sharded (before ga_create)"""
+        """0 auto, 1 rows sharded over the ranks, 2 rows replicated + sweep sharded, 3 replicas: no collective (before ga_create)"""
         self.check(self.lib.pnol_ga_set_sharding(self.h, int(mode)))
 
     def ga_pop_sort(self, xpop, F):

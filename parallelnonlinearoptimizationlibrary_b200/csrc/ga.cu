@@ -1010,7 +1010,7 @@ extern "C" int pnol_ga_status_get(pnol_ga * ga, pnol_ga_status * s)
 extern "C" int pnol_ga_set_sharding(pnol_ctx * ctx, int mode)
 {
 	if (!ctx) return PNOL_ERR_INVALID;
-	PNOL_REQUIRE(ctx, mode >= 0 && mode <= 2, "ga_set_sharding: mode %d (0 auto, 1 rows, 2 sweep)", mode);
+	PNOL_REQUIRE(ctx, mode >= 0 && mode <= 3, "ga_set_sharding: mode %d (0 auto, 1 rows, 2 sweep, 3 none)", mode);
 	ctx->ga_sharding = mode;
 	return PNOL_OK;
 }

@@ -1253,6 +1253,7 @@ struct GaPipe {
 	bool use_ipc = false;
 	int R = 1;                                        // row partitions: the communicator's ranks (rows sharded) or 1 (rows replicated, sweep sharded)
 	long long eper = 0;                               // rows replicated: rows of the fitness sweep per rank
+	bool shard_sweep = true;                          // rows replicated: split the sweep and all-gather F (false: every rank sweeps everything)
 	// replicated per-row arrays (sorted order: Fs, ratio, perm; child order: hash, bcount, dupflag, Fchild, offs)
 	unsigned * perm[2] = {nullptr, nullptr};
 	double * Fs[2] = {nullptr, nullptr};
@@ -1375,14 +1376,27 @@ int ga_pipe_create(pnol_ga * ga)
 	//           (1.41 against 1.09 ms at 2 GPUs, profiles/).
 	//   sweep : every rank keeps the whole population and makes all children (no row ever crosses a link); the fitness sweep
 	//           is split and the objective values are all-gathered, as in the reference's evaluatePopulationParallel.
-	// auto = sweep while two copies of the population fit in a quarter of the GPU's memory, rows beyond.
+	//   none  : every rank keeps the population, makes all children AND sweeps all of them: replicas, no collective at all. For a
+	//           cheap objective the split sweep does not pay for its all-gather: at 1M x 32 Rastrigin the whole sweep is 0.057 ms,
+	//           an eighth of it 0.015 ms, the all-gather of the 8 MB of objective values 0.06 / 0.11 / 0.17 ms at 2 / 4 / 8 GPUs
+	//           (a generation: 1.12 ms with the split sweep against 0.88 ms on one GPU).
+	// auto = rows when two copies of the population exceed a quarter of the GPU's memory; otherwise sweep when the part of the sweep
+	// that the other ranks take over costs more than the all-gather (built-in objectives: streaming time of the population at 4.6 TB/s
+	// against 0.02 ms + 18 ns per KB gathered, the measured figures above; user functors: always, their cost is unknown), else none.
 	int mode = ctx->ga_sharding;
-	if (const char * e = getenv("PNOL_GA_SHARD")) { if (!strcmp(e, "rows")) mode = 1; else if (!strcmp(e, "sweep")) mode = 2; }
+	if (const char * e = getenv("PNOL_GA_SHARD")) { if (!strcmp(e, "rows")) mode = 1; else if (!strcmp(e, "sweep")) mode = 2; else if (!strcmp(e, "none")) mode = 3; }
 	if (mode == 0) {
 		size_t free_b = 0, total_b = 0;
 		cudaMemGetInfo(&free_b, &total_b);
-		mode = ((size_t) Npop * n * 16 > total_b / 4) ? 1 : 2;
+		if ((size_t) Npop * n * 16 > total_b / 4) mode = 1;
+		else {
+			const double Rr = (double) (ctx->nranks > 1 ? ctx->nranks : 1);
+			const double sweep_ms = (double) Npop * (n + 1) * 8.0 / 4.6e9;
+			const double gather_ms = 0.02 + (double) Npop * 8.0 / 1024.0 * 18e-6 * (1.0 - 1.0 / Rr) / 0.875;
+			mode = (is_user_kind(ga->f->kind) || sweep_ms * (1.0 - 1.0 / Rr) > gather_ms) ? 2 : 3;
+		}
 	}
+	P->shard_sweep = mode != 3;
 	const int R = (ctx->nranks > 1 && mode == 1) ? ctx->nranks : 1;
 	P->R = R;
 	P->per = (Npop + R - 1) / R;
@@ -1675,7 +1689,7 @@ static int pipe_enqueue(pnol_ga * ga, double window_scale)
 			            P->dupflag, P->bcount, P->offs, Xloc, P->indicator);
 	}
 	// 6. the fitness sweep over this rank's rows (:217)
-	if (R == 1 && ctx->nranks > 1) {
+	if (R == 1 && ctx->nranks > 1 && P->shard_sweep) {
 		// rows replicated: this rank sweeps individuals [r eper, (r+1) eper) and the objective values are all-gathered
 		// (GeneticAlgorithmMPI::evaluatePopulationParallel, Source/GeneticAlgorithmMPI.cpp:283-414)
 		const long long elo = std::min<long long>(P->eper * ctx->rank, Npop), ehi = std::min<long long>(elo + P->eper, Npop);
@@ -1772,7 +1786,7 @@ int ga_pipe_generation(pnol_ga * ga)
 int ga_pipe_peer_mode(pnol_ga * ga)
 {
 	if (!ga->pipe || ga->ctx->nranks <= 1) return 0;
-	if (ga->pipe->R <= 1) return 3;
+	if (ga->pipe->R <= 1) return ga->pipe->shard_sweep ? 3 : 4;
 	return ga->pipe->use_ipc ? 1 : 2;
 }
 

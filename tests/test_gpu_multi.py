@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir, shard):
     launch.init_process_group("nccl")
     ctx = capi.Context(rank)
     assert launch.attach_communicator(ctx) == world and ctx.comm_size() == world and ctx.comm_rank() == rank
-    ctx.ga_set_sharding(shard)                     # 1: GA rows sharded over the ranks, 2: rows replicated + sweep sharded
+    ctx.ga_set_sharding(shard)                     # 1: GA rows sharded over the ranks, 2: rows replicated + sweep sharded, 3: replicas
     # raw all-reduce
     buf = np.arange(5, dtype=np.float64) + rank
     ctx.allreduce_sum(buf, 5)
@@ -97,7 +97,8 @@ def _worker(rank, world, port, out_dir, shard):
     stream = dict(seed=4242, scale=1.0 - 1.0 / npop)
     fr = ctx.functor(capi.F_RASTRIGIN)
     ga = ctx.ga_create(fr, n, lb, ub, npop, gens, stream)
-    assert ga.peer_mode() == (3 if shard == 2 else (2 if os.environ.get("PNOL_GA_NO_IPC") == "1" else ga.peer_mode())) and ga.peer_mode() in (1, 2, 3)
+    assert ga.peer_mode() == (3 if shard == 2 else 4 if shard == 3 else (2 if os.environ.get("PNOL_GA_NO_IPC") == "1" else ga.peer_mode()))
+    assert ga.peer_mode() in (1, 2, 3, 4)
     np.save(os.path.join(out_dir, "peer_mode_%d.npy" % rank), np.array([ga.peer_mode()]))
     ga.init(x0)
     for gen in range(1, gens + 1):
@@ -120,11 +121,11 @@ def _worker(rank, world, port, out_dir, shard):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shard,no_ipc,lm_peer", [(2, 1, 0, 1), (2, 1, 1, 1), (2, 2, 0, 0), (4, 1, 0, 1), (4, 2, 0, 0), (8, 1, 0, 1), (8, 1, 1, 0),
-                                                        (8, 2, 0, 1)])
+@pytest.mark.parametrize("world,shard,no_ipc,lm_peer", [(2, 1, 0, 1), (2, 1, 1, 1), (2, 2, 0, 0), (2, 3, 0, 1), (4, 1, 0, 1), (4, 2, 0, 0), (8, 1, 0, 1),
+                                                        (8, 1, 1, 0), (8, 2, 0, 1), (8, 3, 0, 1)])
 def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, lm_peer, monkeypatch):
     """shard = 1: GA rows sharded over the ranks (no_ipc = 1: through replicas + all-gather, PNOL_GA_NO_IPC=1, instead of CUDA IPC
-    peer mappings); shard = 2: GA rows replicated, fitness sweep sharded; lm_peer = 0: the LM step's sums through NCCL
+    peer mappings); shard = 2: GA rows replicated, fitness sweep sharded; shard = 3: replicas (no collective in a generation); lm_peer = 0: the LM step's sums through NCCL
     (PNOL_LM_PEER=0) instead of the fused peer-memory kernels"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -134,7 +135,7 @@ def test_sharded_paths_match_the_reference(tmp_path, world, shard, no_ipc, lm_pe
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shard), nprocs=world, join=True)
     modes = {int(np.load(tmp_path / ("peer_mode_%d.npy" % r))[0]) for r in range(world)}
     assert len(modes) == 1, "every rank takes the same path"
-    assert modes == ({3} if shard == 2 else ({2} if no_ipc else modes)) and modes <= {1, 2, 3}
+    assert modes == ({3} if shard == 2 else {4} if shard == 3 else ({2} if no_ipc else modes)) and modes <= {1, 2, 3, 4}
     print("GA peer mode at world %d: %s" % (world, modes))
     G = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden.npz"))
     GB = np.load(os.path.join(ROOT, "tests", "golden", "baseline_lm_golden.npz"))
