@@ -25,7 +25,7 @@ ubench: tools/ubench/fp64_ubench
 tools/ubench/fp64_ubench: tools/ubench/fp64_ubench.cu
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -o $@ $<
 
-$(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h) $(wildcard include/pnol/*)
+$(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h) $(wildcard include/pnol/*) $(wildcard include/pnol/device/*)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
 

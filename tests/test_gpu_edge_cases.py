@@ -20,7 +20,7 @@ def test_empty_and_single_row_batches(ctx):
         assert np.array_equal(ctx.eval_batch(f, pts, B, 7), O.eval_batch(of, pts))
 
 
-@pytest.mark.parametrize("B,n", [(1, 32), (63, 32), (64, 32), (65, 32), (1000, 4), (1000, 36), (257, 100)])
+@pytest.mark.parametrize("B,n", [(1, 32), (63, 32), (64, 32), (65, 32), (1000, 4), (1000, 36), (257, 100), (200000, 32), (100001, 64), (3000, 96), (5000, 48)])
 def test_separable_sweep_sizes(ctx, B, n):
     # Rastrigin takes the row-wise / warp-tile kernels for aligned n and the generic tile kernel otherwise: same bits everywhere
     f = ctx.functor(capi.F_RASTRIGIN)

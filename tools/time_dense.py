@@ -50,6 +50,22 @@ for n in [int(v) for v in os.environ.get("PROF_N", "4096").split(",")]:
     ms = timed("hinv_rank2", lambda: ctx.bfgs_update_hinv(Dd, gd, sd, n, mode=capi.HINV_RANK2))
     by = 3.0 * n * n * 8.0
     print("n=%d hinv_rank2  %.4f ms  %.0f GB/s  frac %.3f  rel err %.2e" % (n, ms, by / ms / 1e6, by / ms / 1e6 / HBM, e_h))
+    # the BFGS loop's order: update, then the next search direction (three passes over D per iteration, back to back)
+    def pair():
+        ctx.bfgs_update_hinv(Dd, gd, sd, n, mode=capi.HINV_RANK2)
+        ctx.matvec_neg(Dd, gd, n, p=pd)
+    for _ in range(3):
+        pair()
+    ctx.sync()
+    ctx.timer_enable(True)
+    ctx.timer_reset()
+    for _ in range(30):
+        pair()
+    m1, c1 = ctx.timer_get("hinv_rank2")
+    m2, c2 = ctx.timer_get("matvec_neg")
+    ctx.timer_enable(False)
+    print("n=%d update + direction interleaved: hinv_rank2 %.4f ms, matvec_neg %.4f ms  (PNOL_DENSE_SERPENTINE=%s)"
+          % (n, m1 / max(c1, 1), m2 / max(c2, 1), os.environ.get("PNOL_DENSE_SERPENTINE", "default")))
     for q in (Dd, gd, sd, pd):
         ctx.free(q)
 
