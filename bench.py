@@ -648,15 +648,16 @@ def run_ours(args):
         if "fd_jacobian" in timers:
             by = float(m_loc) * n * 8 + 3.0 * m_loc * 8            # J written once; data columns t, y and the residual F read once
             a = by / (timers["fd_jacobian"]["ms_avg"] * 1e-3) / 1e9
-            # the same launch against the FP64-ALU roofline: 237 FP64 warp instructions per row (SASS count of the staged row: 229 for
-            # J, 8 for J^T F) x 32 lanes, peak = SMs x 64 lanes x SM clock
-            fp64_ops = 237.0 * 32 * m_loc
+            # the same launch against the FP64-ALU roofline: 221 FP64 warp instructions per row (SASS count of the staged row with the
+            # three-operation FD quotient, which the bench's dX = 1e-7 qualifies for: 213 for J, 8 for J^T F; 237 with the five-operation
+            # quotient) x 32 lanes, peak = SMs x 64 lanes x SM clock
+            fp64_ops = 221.0 * 32 * m_loc
             fp64_peak = ctx.sm_count * 64 * 1.965e9
             kern["fd_jacobian"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                                    "traffic": tr("fd_jacobian"), "ms": timers["fd_jacobian"]["ms_avg"], "algorithmic_bytes": by,
                                    "peak_source": hbm_src,
                                    "fp64_alu_frac": fp64_ops / (timers["fd_jacobian"]["ms_avg"] * 1e-3) / fp64_peak,
-                                   "note": "FP64-ALU-bound on B200: 237 FP64 instructions per row (bit-exact FD quotients + J^T F) put the ceiling at 0.77 of the HBM roofline"}
+                                   "note": "FP64-ALU-bound on B200: 221 FP64 instructions per row (bit-exact FD quotients in three operations + J^T F) put the ceiling at 0.83 of the HBM roofline"}
         if "residual" in timers:
             by = 3.0 * m_loc * 8
             a = by / (timers["residual"]["ms_avg"] * 1e-3) / 1e9

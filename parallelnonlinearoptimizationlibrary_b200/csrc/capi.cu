@@ -1310,6 +1310,21 @@ __global__ void fast_div_selftest_kernel(unsigned long long seed, long long per_
 			double got = pnol::div_exact_core(a, rd), want = a / b;
 			if (__double_as_longlong(got) != __double_as_longlong(want)) nbad++;
 		}
+		// the three-operation quotient for the divisors with a good rounded reciprocal (about half of them), x = -0 excluded as in the row
+		if (pnol::recip_three_ok(rd) && pnol::div_exact_x_ok_pz(a)) {
+			double got = pnol::div_exact3_core(a, rd), want = a / b;
+			if (__double_as_longlong(got) != __double_as_longlong(want)) nbad++;
+		}
+		// ... and with the quotient next to a floating-point number or a midpoint: x = RN(b q + k b ulp(q) / 2) for a random q, k = -1 .. 2
+		if (pnol::recip_three_ok(rd) && (mode == 0 || mode == 2)) {
+			const double q = __longlong_as_double((long long) (((unsigned long long) (ea + 1023) << 52) | (ma & 0xFFFFFFFFFFFFFULL)));
+			const double u = __longlong_as_double(__double_as_longlong(q) + 1) - q;
+			const double xq = fma(b, q, 0.5 * (double) ((int) (s >> 40 & 3) - 1) * (b * u));
+			if (pnol::div_exact_x_ok_pz(xq)) {
+				double got = pnol::div_exact3_core(xq, rd), want = xq / b;
+				if (__double_as_longlong(got) != __double_as_longlong(want)) nbad++;
+			}
+		}
 	}
 	if (nbad) atomicAdd(bad, nbad);
 }

@@ -199,6 +199,36 @@ def test_jacobian_nonuniform_steps_and_ragged_rows(ctx):
         assert np.array_equal(J, Jw) and np.array_equal(F, Fw)
 
 
+@pytest.mark.parametrize("K", [8, 32, 64, 128, 256])
+@pytest.mark.parametrize("steps", ["1e-6", "1e-5", "1.3e-6", "mixed"])
+def test_jacobian_fd_quotient_in_three_and_in_five_operations(ctx, K, steps):
+    # The FD quotient of the structured row takes three operations when EVERY dX has a good rounded reciprocal (|RN(1/dX) dX - 1| <=
+    # (15/32) 2^-53: 1e-6, 1e-7, ...), five otherwise (1e-5: 0.574 x 2^-53, 1.3e-6: 0.536; one such step among good ones is enough):
+    # the bits of the oracle's `/` either way, and J^T F beside it (exact_div.cuh, residual_kernels.cu: warp_q3)
+    m = 2000 + K
+    pr = problems.lorentz_problem(m, K)
+    n = pr["n"]
+    dx = {"1e-6": np.full(n, 1e-6), "1e-5": np.full(n, 1e-5), "1.3e-6": np.full(n, 1.3e-6),
+          "mixed": np.where(np.arange(n) == n // 2 + 1, 1e-5, 1e-6)}[steps]
+    f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    of = O.OFunctor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
+    J, F = ctx.fd_jacobian(f, pr["x0"], dx)
+    Jw, Fw = O.fd_jacobian(of, pr["x0"], dx)
+    assert np.array_equal(F, Fw)
+    assert np.array_equal(J, Jw), "max rel diff %g" % np.max(np.abs(J - Jw) / (np.abs(Jw) + 1e-300))
+    # the LM step's kernel (J and J^T F in one launch) stores the same J
+    lam = 0.01
+    JTJw, Aw, rhsw = O.lm_normal_eq(Jw, Fw, lam)
+    Jd, Fd, Ft, JTJd = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
+    ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
+    ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, lam, JTJd)
+    assert np.array_equal(ctx.to_host(Jd, m * n).reshape(m, n), Jw)
+    packed = ctx.to_host(JTJd, n * n + n)
+    assert rel(packed[:n * n].reshape(n, n), JTJw) < 1e-12 and rel(packed[n * n:], rhsw) < 1e-12
+    for p in (Jd, Fd, Ft, JTJd):
+        ctx.free(p)
+
+
 @pytest.mark.parametrize("m,n", [(100, 3), (1000, 16), (4099, 16), (777, 4), (600, 130), (512, 256), (3000, 256), (50, 300)])
 def test_lm_normal_eq(ctx, m, n):
     rng = np.random.default_rng(m + n)

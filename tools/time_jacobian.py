@@ -15,7 +15,7 @@ pr = problems.lorentz_problem(m, K)
 n = pr["n"]
 f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
 Jd, Fd = ctx.malloc(m * n * 8), ctx.malloc(m * 8)
-xd, dxd = ctx.to_device(pr["x0"]), ctx.to_device(np.full(n, 1e-7))
+xd, dxd = ctx.to_device(pr["x0"]), ctx.to_device(np.full(n, float(os.environ.get("PROF_DX", 1e-7))))
 for _ in range(3):
     ctx.fd_jacobian(f, xd, dxd, J=Jd, F=Fd, n=n)
     ctx.residual_eval(f, xd, F=Fd, n=n)

@@ -15,7 +15,7 @@ pr = problems.lorentz_problem(m, K)
 n = pr["n"]
 f = ctx.functor(capi.F_LORENTZ_SUM, (pr["w"],), (), (pr["t"], pr["y"]), m)
 Jd, Fd, Ft, JTJd = ctx.malloc(m * n * 8), ctx.malloc(m * 8), ctx.malloc(m * 8), ctx.malloc((n * n + n) * 8)
-dx = np.full(n, 1e-7)
+dx = np.full(n, float(os.environ.get("PROF_DX", 1e-7)))      # 1e-5: the five-operation FD quotient (exact_div.cuh)
 ctx.residual_eval(f, pr["x0"], F=Fd, n=n)
 for _ in range(2):
     ctx.lm_step(f, pr["x0"], dx, n, Jd, Fd, Ft, 1e-3, JTJd)
